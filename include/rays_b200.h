@@ -18,6 +18,7 @@
 #ifndef RAYS_B200_H
 #define RAYS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -250,6 +251,9 @@ int rays_b200_trace_device(int store_trajectories);
 int rays_b200_results_download(rays_results *res);
 /* device time (ms) of the last rays_b200_trace_device kernel, its launch count, ray-steps */
 int rays_b200_last_trace_stats(double *kernel_ms, int64_t *ray_steps, int32_t *n_launches);
+/* RHS evaluations of the last trace (SG accounting), the kernel specialisation that ran, its grid and
+ * resident CTAs per SM (for profiles/ and bench.py) */
+int rays_b200_last_trace_info(int64_t *rhs_evals, char *kernel_name, int name_len, int32_t *grid, int32_t *blocks_per_sm);
 /* sharding helper: keep rays iray with iray % world == rank */
 int rays_b200_fan_shard(int rank, int world);
 
@@ -304,9 +308,17 @@ int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_
 /* DFMA-only microbenchmark: measured fp64 FMA throughput of this GPU in TFLOP/s (2 flop/FMA)
  * and the SM clock (MHz) NVML/driver reported under load (0 if unavailable). */
 int rays_b200_fp64_peak(double *tflops, double *sm_mhz);
+/* page-locked host memory for the result arrays (allocate_ray_results, ray_results_m.f90:132-142):
+ * lets the trajectory copy-out of rays_b200_trace run at PCIe rate; pageable arrays work too */
+int rays_b200_host_alloc(void **p, size_t bytes);
+int rays_b200_host_free(void *p);
 /* the CUDA stream (cudaStream_t as void*) the library launches on, for external event timing */
 void *rays_b200_stream(void);
 int rays_b200_version(void);
+/* sizeof() of the ABI structs in the order rays_cfg, rays_fan, rays_results, rays_deposition,
+ * rays_solovev_launch, rays_axisym_launch, rays_slab_launch, rays_spline1d, rays_spline2d, rays_slab_eq,
+ * rays_solovev_eq, rays_axisym_eq, rays_mirror_eq: lets a binding in another language check its layout */
+int rays_b200_struct_sizes(int32_t *out, int n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,738 @@
+// ray_trace.cuh — per-ray engine on the device: eqn_ray, check_save, initialize_ode_vector, the RK4
+// and Shampine-Gordon steppers and the persistent trace kernel that replaces the OpenMP ray loop of
+// trace_rays (RAYS_project/RAYS_lib/ray_tracing.f90:62-266).
+//
+// Execution model: one fp64 ray per thread, ray state in registers.  Each CTA is persistent: a lane
+// whose ray has ended takes the next ray index from a global counter (one warp-aggregated atomicAdd
+// per refill: __ballot_sync compacts the requests), so ray-length divergence and the adaptive
+// stepper's step-count divergence do not idle lanes until the fan is exhausted.  Trajectory points
+// are stored straight into the reference's result layout ray_vec(nv, npoints, iray)
+// (ray_results_m.f90:44-58): each lane writes the nv contiguous doubles of one point with 16-byte
+// stores, consecutive points of a ray are adjacent, so L2 write-back merges them into full sectors
+// and no transpose is needed before the copy to the host.
+#pragma once
+#include "ray_physics.cuh"
+
+namespace rays_dev {
+
+// compile-time description of one kernel specialisation; DAMP_/GRADS_ = -1 selects the run-time
+// ("generic") form that handles every nv layout of ode_m.f90:160-173
+template <int EQ_, int NS_, int DERIV_, int DAMP_, int GRADS_> struct Traits {
+    static constexpr int EQ = EQ_, NS = NS_, DERIV = DERIV_;
+    static constexpr bool GENERIC = DAMP_ < 0;
+    static constexpr int NV = GENERIC ? RAYS_NV_MAX : 7 + (DAMP_ > 0 ? 1 : 0) + (GRADS_ > 0 ? 5 : 0);
+    RD_INLINE static bool damp() { return GENERIC ? g_dc.c.damping_model != RAYS_DAMP_NONE : DAMP_ == 1; }
+    RD_INLINE static bool grads() { return GENERIC ? g_dc.c.integrate_eq_gradients != 0 : GRADS_ == 1; }
+    RD_INLINE static bool multi() { return GENERIC ? g_dc.c.multi_spec_damping != 0 : false; }
+    RD_INLINE static int nv() { return GENERIC ? g_dc.c.nv : NV; }
+};
+
+// ---- eqn_ray (eqn_ray.f90:1-236): returns 0 or the stop code ------------------------------------------
+template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    const rays_cfg &c = g_dc.c;
+    const double k0 = c.k0;
+    const double nvec[3] = {v[3] / k0, v[4] / k0, v[5] / k0};
+    Eq<NSM> e;
+    equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
+    if (e.err) return e.err;
+    double dddx[3], dddk[3], dddw;
+    if (T::DERIV == RAYS_DERIV_COLD) deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);
+    else {
+        int pert_err;
+        const double r0[3] = {v[0], v[1], v[2]}, kv[3] = {v[3], v[4], v[5]};
+        deriv_num<T::EQ, T::NS>(e, r0, kv, dddx, dddk, dddw, pert_err);
+        if (pert_err) return pert_err;
+    }
+    if (dddw == 0.0) return RAYS_STOP_INFINITE_VG_RHS;
+    const double vg[3] = {-dddk[0] / dddw, -dddk[1] / dddw, -dddk[2] / dddw};
+    const double vg0 = sqrt(vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2]);
+    double dsd;
+    if (c.ray_param == RAYS_PARAM_ARCL) {
+        if (dddk[0] != 0.0 || dddk[1] != 0.0 || dddk[2] != 0.0) {
+            const double sg = copysign(1.0, dddw);
+            const double nrm = sqrt(dddk[0] * dddk[0] + dddk[1] * dddk[1] + dddk[2] * dddk[2]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { dvds[i] = -sg * dddk[i] / nrm; dvds[3 + i] = sg * dddx[i] / nrm; }
+            dsd = 1.0;
+        } else return RAYS_STOP_RAY_STALLED;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { dvds[i] = vg[i]; dvds[3 + i] = dddx[i] / dddw; }
+        dsd = vg0;
+    }
+    dvds[6] = dsd;
+    int nv0 = 7;
+    if (T::damp()) {
+        const double kv[3] = {v[3], v[4], v[5]};
+        const double ki = damp_fund_ECH<NSM>(e, kv, vg);
+        dvds[7] = dsd * 2.0 * ki * (1.0 - v[7]);
+        nv0 = 8;
+        if (T::multi()) {  // ksi(0) = ki, ksi(1:nspec) = 0 (damp_fund_ECH.f90:121-125)
+            dvds[8] = dsd * 2.0 * ki * (1.0 - v[7]);
+            for (int is = 1; is <= c.nspec; ++is) dvds[8 + is] = dsd * 2.0 * 0.0 * (1.0 - v[7]);
+            nv0 = 9 + c.nspec;
+        }
+    }
+    if (T::grads()) {
+        const double u0 = vg[0] / vg0, u1 = vg[1] / vg0, u2 = vg[2] / vg0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dvds[nv0 + j] = dsd * u0 * e.g[0][j] + dsd * u1 * e.g[1][j] + dsd * u2 * e.g[2][j];
+        dvds[nv0 + 3] = dsd * u0 * e.gradns[0][0] + dsd * u1 * e.gradns[1][0] + dsd * u2 * e.gradns[2][0];
+        dvds[nv0 + 4] = dsd * u0 * e.gradts0[0] + dsd * u1 * e.gradts0[1] + dsd * u2 * e.gradts0[2];
+    }
+    return 0;
+}
+// out-of-line copy for the Shampine-Gordon stepper, which evaluates the RHS from three places
+template <class T> RD_NOINLINE int eqn_ray_call(const double *v, double *dvds) { return eqn_ray<T>(v, dvds); }
+
+// ---- check_save (check_save.f90:1-161): residual + stop tests at a saved point -------------------------
+// flag/stop follow ode_stop semantics: a flag may be set without stopping (equilibrium error, A.5 (X))
+template <class T> RD_INLINE void check_save(const double *v, double &resid, bool &stop, int &flag) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    const int ns = NSpec<T::NS>::n();
+    const rays_cfg &c = g_dc.c;
+    const double k0 = c.k0;
+    Eq<NSM> e;
+    equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
+    if (e.err) {
+        flag = e.err;
+        resid = 0.0;
+        if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+        return;
+    }
+    const double kv[3] = {v[3], v[4], v[5]};
+    double k3, k1;
+    kpar_kperp(kv, e.bunit, k3, k1);
+    const double nvec[3] = {kv[0] / k0, kv[1] / k0, kv[2] / k0};
+    resid = residual<NSM>(e, ns, k1, k3);
+    if (resid > c.dispersion_resid_limit) { stop = true; flag = RAYS_STOP_DISP_RESIDUAL; }
+    double dddx[3], dddk[3], dddw;
+    deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);   // always cold (check_save.f90:79-87)
+    if (!(fabs(dddw) > DBL_MIN)) { stop = true; flag = RAYS_STOP_INFINITE_VG_CHECK; }
+    if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+}
+
+// ---- initialize_ode_vector (initialize_ode_vector.f90:1-57) ---------------------------------------------
+template <class T> RD_INLINE void initialize_ode_vector(const double *rvec0, const double *rindex_vec0, double *v) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    const rays_cfg &c = g_dc.c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { v[i] = rvec0[i]; v[3 + i] = c.k0 * rindex_vec0[i]; }
+    v[6] = 0.0;
+    int nv0 = 7;
+    if (T::damp()) {
+        v[7] = 0.0; nv0 = 8;
+        if (T::multi()) { for (int s = 0; s <= c.nspec; ++s) v[8 + s] = 0.0; nv0 = 9 + c.nspec; }
+    }
+    if (T::grads()) {
+        Eq<NSM> e;
+        equilibrium<T::EQ, T::NS, false>(v[0], v[1], v[2], e);
+        const bool ok = e.err == 0;   // on error the reference leaves eq undefined; zeros here (oracle choice)
+        v[nv0] = ok ? e.bvec[0] : 0.0; v[nv0 + 1] = ok ? e.bvec[1] : 0.0; v[nv0 + 2] = ok ? e.bvec[2] : 0.0;
+        v[nv0 + 3] = ok ? e.ns[0] : 0.0;
+        v[nv0 + 4] = ok ? e.ts[0] : 0.0;
+    }
+}
+
+// ---- RK4_ode (RK4_ode_m.f90:59-94): returns the stop code, v and s untouched on a stop ----------------
+template <class T> RD_INLINE int RK4_ode(double *v, double &s, double sout) {
+    constexpr int NV = T::NV;
+    const int nv = T::nv();
+    const double ds = sout - s;
+    double w[NV], acc[NV], f[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { w[i] = v[i]; acc[i] = 0.0; f[i] = 0.0; }
+    int code = 0;
+#pragma unroll 1
+    for (int stage = 0; stage < 4; ++stage) {
+        code = eqn_ray<T>(w, f);
+        if (code) break;
+        // (f1 + 2.0*f2 + 2.0*f3 + f4), left to right; v + ds*f/2.0 for stages 1,2 and v + ds*f for 3
+        const double ca = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+        const double cw = stage == 2 ? 1.0 : 0.5;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (i < nv) {
+                acc[i] = stage == 0 ? f[i] : acc[i] + ca * f[i];
+                w[i] = v[i] + ds * f[i] * cw;
+            }
+    }
+    if (code) return code;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + ds * acc[i] / 6.0;
+    s = sout;
+    return 0;
+}
+
+// ---- SG_ode (SG_ode_m.f90:89-159) + ode/de/step/intrp (ode_RAYS.f90:1-1362) -----------------------------
+// `work`/`iwork` are automatic in SG_ode and iflag = 1 on every call, so each ds segment restarts the
+// integrator at order 1; the work arrays therefore live only inside sg_de, in local
+// memory (phi is indexed by the run-time order k).  Arrays keep the Fortran's 1-based subscripts.
+template <int NV> struct SGWork {
+    double yy[NV], wt[NV], p[NV], yp[NV];
+    double phi[17][NV];
+    double alpha[13], beta[13], sig[14], v[13], w[13], g[14], psi[13];
+    double x, h, hold;
+    bool start, phase1, nornd;
+    int ns, k, kold;
+};
+__device__ const double kSGgstr[14] = {  // ode_RAYS.f90:776-779 (single-precision literals)
+    0.0, (double)0.50e+00f, (double)0.0833e+00f, (double)0.0417e+00f, (double)0.0264e+00f, (double)0.0188e+00f,
+    (double)0.0143e+00f, (double)0.0114e+00f, (double)0.00936e+00f, (double)0.00789e+00f, (double)0.00679e+00f,
+    (double)0.00592e+00f, (double)0.00524e+00f, (double)0.00468e+00f};
+__device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0, 1024.0, 2048.0, 4096.0, 8192.0};
+
+// step (ode_RAYS.f90:595-1234); returns a stop code from the RHS or 0
+template <class T> __device__ int sg_step(int neqn, SGWork<T::NV> &W, double &eps, bool &crash, unsigned &nrhs) {
+    double &x = W.x, &h = W.h, &hold = W.hold;
+    double *y = W.yy, *wt = W.wt, *p = W.p, *yp = W.yp;
+    double(*phi)[T::NV] = W.phi;
+    double *alpha = W.alpha, *beta = W.beta, *sig = W.sig, *v = W.v, *w = W.w, *g = W.g, *psi = W.psi;
+    int &k = W.k, &kold = W.kold, &ns = W.ns;
+    const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
+    crash = true;
+    if (fabs(h) < fouru * fabs(x)) { h = copysign(fouru * fabs(x), h); return 0; }
+    const double p5eps = 0.5 * eps;
+    double sum = 0.0;
+    for (int l = 0; l < neqn; ++l) { const double q = y[l] / wt[l]; sum = sum + q * q; }
+    const double round = twou * sqrt(sum);
+    if (p5eps < round) { eps = 2.0 * round * (1.0 + fouru); return 0; }
+    crash = false;
+    g[1] = 1.0; g[2] = 0.5; sig[1] = 1.0;
+    double absh;
+    if (W.start) {
+        const int code = eqn_ray_call<T>(y, yp); ++nrhs;
+        if (code) return code;
+        double tot = 0.0;
+        for (int l = 0; l < neqn; ++l) {
+            phi[1][l] = yp[l]; phi[2][l] = 0.0;
+            const double q = yp[l] / wt[l]; tot = tot + q * q;
+        }
+        const double total = sqrt(tot);
+        absh = fabs(h);
+        if (eps < 16.0 * total * h * h) absh = 0.25 * sqrt(eps / total);
+        h = copysign(fmax(absh, fouru * fabs(x)), h);
+        hold = 0.0;
+        k = 1; kold = 0;
+        W.start = false; W.phase1 = true; W.nornd = true;
+        if (p5eps <= 100.0 * round) {
+            W.nornd = false;
+            for (int l = 0; l < neqn; ++l) phi[15][l] = 0.0;
+        }
+    }
+    int ifail = 0;
+    int kp1, kp2, km1, km2, knew;
+    double erkm2, erkm1, erk, err, xold;
+    for (;;) {
+        kp1 = k + 1; kp2 = k + 2; km1 = k - 1; km2 = k - 2;
+        if (h != hold) ns = 0;
+        if (ns <= kold) ns = ns + 1;
+        const int nsp1 = ns + 1;
+        if (ns <= k) {
+            beta[ns] = 1.0;
+            alpha[ns] = 1.0 / (double)ns;
+            double temp1 = h * (double)ns;
+            sig[nsp1] = 1.0;
+            for (int i = nsp1; i <= k; ++i) {
+                const double temp2 = psi[i - 1];
+                psi[i - 1] = temp1;
+                beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+                temp1 = temp2 + h;
+                alpha[i] = h / temp1;
+                sig[i + 1] = (double)i * alpha[i] * sig[i];
+            }
+            psi[k] = temp1;
+            if (ns <= 1) {
+                for (int iq = 1; iq <= k; ++iq) { v[iq] = 1.0 / (double)(iq * (iq + 1)); w[iq] = v[iq]; }
+            } else {
+                if (kold < k) {
+                    v[k] = 1.0 / (double)(k * kp1);
+                    for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
+                }
+                for (int iq = 1; iq <= kp1 - ns; ++iq) { v[iq] = v[iq] - alpha[ns] * v[iq + 1]; w[iq] = v[iq]; }
+                g[nsp1] = w[1];
+            }
+            for (int i = ns + 2; i <= kp1; ++i) {
+                for (int iq = 1; iq <= kp2 - i; ++iq) w[iq] = w[iq] - alpha[i - 1] * w[iq + 1];
+                g[i] = w[1];
+            }
+        }
+        for (int i = nsp1; i <= k; ++i)
+            for (int l = 0; l < neqn; ++l) phi[i][l] = beta[i] * phi[i][l];
+        for (int l = 0; l < neqn; ++l) { phi[kp2][l] = phi[kp1][l]; phi[kp1][l] = 0.0; p[l] = 0.0; }
+        for (int j = 1; j <= k; ++j) {
+            const int i = kp1 - j;
+            for (int l = 0; l < neqn; ++l) {
+                p[l] = p[l] + phi[i][l] * g[i];
+                phi[i][l] = phi[i][l] + phi[i + 1][l];
+            }
+        }
+        if (!W.nornd) {
+            for (int l = 0; l < neqn; ++l) {
+                const double tau = h * p[l] - phi[15][l];
+                p[l] = y[l] + tau;
+                phi[16][l] = (p[l] - y[l]) - tau;
+            }
+        } else {
+            for (int l = 0; l < neqn; ++l) p[l] = y[l] + h * p[l];
+        }
+        xold = x;
+        x = x + h;
+        absh = fabs(h);
+        {
+            const int code = eqn_ray_call<T>(p, yp); ++nrhs;
+            if (code) return code;
+        }
+        erkm2 = 0.0; erkm1 = 0.0; erk = 0.0;
+        for (int l = 0; l < neqn; ++l) {
+            if (0 < km2) { const double q = (phi[km1][l] + yp[l] - phi[1][l]) / wt[l]; erkm2 = erkm2 + q * q; }
+            if (0 <= km2) { const double q = (phi[k][l] + yp[l] - phi[1][l]) / wt[l]; erkm1 = erkm1 + q * q; }
+            const double q = (yp[l] - phi[1][l]) / wt[l];
+            erk = erk + q * q;
+        }
+        if (0 < km2) erkm2 = absh * sig[km1] * kSGgstr[km2] * sqrt(erkm2);
+        if (0 <= km2) erkm1 = absh * sig[k] * kSGgstr[km1] * sqrt(erkm1);
+        err = absh * sqrt(erk) * (g[k] - g[kp1]);
+        erk = absh * sqrt(erk) * sig[kp1] * kSGgstr[k];
+        knew = k;
+        if (0 < km2) {
+            if (fmax(erkm1, erkm2) <= erk) knew = km1;
+        } else if (0 == km2) {
+            if (erkm1 <= 0.5 * erk) knew = km1;
+        }
+        if (err <= eps) break;
+        // step failed: restore x, phi, psi; halve (or more) the step
+        W.phase1 = false;
+        x = xold;
+        for (int i = 1; i <= k; ++i)
+            for (int l = 0; l < neqn; ++l) phi[i][l] = (phi[i][l] - phi[i + 1][l]) / beta[i];
+        for (int i = 2; i <= k; ++i) psi[i - 1] = psi[i] - h;
+        ifail = ifail + 1;
+        double temp2 = 0.5;
+        if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sqrt(p5eps / erk); }
+        if (3 <= ifail) knew = 1;
+        h = temp2 * h;
+        k = knew;
+        if (fabs(h) < fouru * fabs(x)) {
+            crash = true;
+            h = copysign(fouru * fabs(x), h);
+            eps = eps + eps;
+            return 0;
+        }
+    }
+    kold = k;
+    hold = h;
+    if (!W.nornd) {
+        for (int l = 0; l < neqn; ++l) {
+            const double rho = h * g[kp1] * (yp[l] - phi[1][l]) - phi[16][l];
+            y[l] = p[l] + rho;
+            phi[15][l] = (y[l] - p[l]) - rho;
+        }
+    } else {
+        for (int l = 0; l < neqn; ++l) y[l] = p[l] + h * g[kp1] * (yp[l] - phi[1][l]);
+    }
+    {
+        const int code = eqn_ray_call<T>(y, yp); ++nrhs;
+        if (code) return code;
+    }
+    for (int l = 0; l < neqn; ++l) {
+        phi[kp1][l] = yp[l] - phi[1][l];
+        phi[kp2][l] = phi[kp1][l] - phi[kp2][l];
+    }
+    for (int i = 1; i <= k; ++i)
+        for (int l = 0; l < neqn; ++l) phi[i][l] = phi[i][l] + phi[kp1][l];
+    double erkp1 = 0.0;
+    if (knew == km1 || k == 12) W.phase1 = false;
+    if (W.phase1) {
+        k = kp1; erk = erkp1;
+    } else if (knew == km1) {
+        k = km1; erk = erkm1;
+    } else if (kp1 <= ns) {
+        for (int l = 0; l < neqn; ++l) { const double q = phi[kp2][l] / wt[l]; erkp1 = erkp1 + q * q; }
+        erkp1 = absh * kSGgstr[kp1] * sqrt(erkp1);
+        if (k == 1) {
+            if (erkp1 < 0.5 * erk) { k = kp1; erk = erkp1; }
+        } else if (erkm1 <= fmin(erk, erkp1)) {
+            k = km1; erk = erkm1;
+        } else if (erkp1 < erk && k < 12) {
+            k = kp1; erk = erkp1;
+        }
+    }
+    double hnew = h + h;
+    if (!W.phase1) {
+        if (p5eps < erk * kSGtwo[k + 1]) {
+            hnew = h;
+            if (p5eps < erk) {
+                const double temp2 = (double)(k + 1);
+                const double r = pow(p5eps / erk, 1.0 / temp2);
+                hnew = absh * fmax(0.5, fmin((double)0.9f, r));
+                hnew = copysign(fmax(hnew, fouru * fabs(x)), h);
+            }
+        }
+    }
+    h = hnew;
+    return 0;
+}
+
+// intrp (ode_RAYS.f90:1235-1362); ypout is not used by the caller
+template <int NV> __device__ void sg_intrp(int neqn, const SGWork<NV> &W, double xout, double *yout) {
+    double g[14], rho[14], w[14];
+    const double hi = xout - W.x;
+    const int ki = W.kold + 1;
+    for (int i = 1; i <= ki; ++i) w[i] = 1.0 / (double)i;
+    g[1] = 1.0; rho[1] = 1.0;
+    double term = 0.0;
+    for (int j = 2; j <= ki; ++j) {
+        const double psijm1 = W.psi[j - 1];
+        const double gamma = (hi + term) / psijm1;
+        const double eta = hi / psijm1;
+        for (int i = 1; i <= ki + 1 - j; ++i) w[i] = gamma * w[i] - eta * w[i + 1];
+        g[j] = w[1];
+        rho[j] = gamma * rho[j - 1];
+        term = psijm1;
+    }
+    for (int l = 0; l < neqn; ++l) yout[l] = 0.0;
+    for (int j = 1; j <= ki; ++j) {
+        const int i = ki + 1 - j;
+        for (int l = 0; l < neqn; ++l) yout[l] = yout[l] + g[i] * W.phi[i][l];
+    }
+    for (int l = 0; l < neqn; ++l) yout[l] = W.yy[l] + hi * yout[l];
+}
+
+// ode + de with iflag = 1 on entry (ode_RAYS.f90:1-593).  Returns iflag; `code` is the RHS stop code.
+template <class T>
+__device__ int sg_de(int neqn, double *y, double &t, double tout, double &relerr, double &abserr, int &code, int &flag, unsigned &nrhs) {
+    SGWork<T::NV> W;
+    const int maxnum = 500;
+    const double fouru = 4.0 * DBL_EPSILON;
+    code = 0;
+    if (t == tout) { flag = RAYS_STOP_SG_T_EQ_TOUT; return 6; }
+    if (relerr < 0.0 || abserr < 0.0) { flag = RAYS_STOP_SG_BAD_TOL; return 6; }
+    double eps = fmax(relerr, abserr);
+    if (eps <= 0.0) { flag = RAYS_STOP_SG_EPS_LE_0; return 6; }
+    int iflag = 1;
+    const double del = tout - t;
+    const double absdel = fabs(del);
+    const double tend = t + 10.0 * del;
+    int nostep = 0, kle4 = 0;
+    bool stiff = false;
+    const double releps = relerr / eps;
+    const double abseps = abserr / eps;
+    W.start = true;
+    W.x = t;
+    for (int l = 0; l < neqn; ++l) W.yy[l] = y[l];
+    W.h = copysign(fmax(fabs(tout - W.x), fouru * fabs(W.x)), tout - W.x);
+    W.ns = 0; W.k = 0; W.kold = 0; W.hold = 0.0; W.phase1 = false; W.nornd = true;
+    for (;;) {
+        if (absdel <= fabs(W.x - t)) {
+            sg_intrp<T::NV>(neqn, W, tout, y);
+            iflag = 2;
+            t = tout;
+            break;
+        }
+        if (maxnum <= nostep) {
+            iflag = 4;
+            flag = RAYS_STOP_SG_MAXNUM;
+            if (stiff) { iflag = 5; flag = RAYS_STOP_SG_STIFF; }
+            for (int l = 0; l < neqn; ++l) y[l] = W.yy[l];
+            t = W.x;
+            break;
+        }
+        W.h = copysign(fmin(fabs(W.h), fabs(tend - W.x)), W.h);
+        for (int l = 0; l < neqn; ++l) W.wt[l] = releps * fabs(W.yy[l]) + abseps;
+        bool crash;
+        code = sg_step<T>(neqn, W, eps, crash, nrhs);
+        if (code) { flag = code; return iflag; }
+        if (crash) {
+            iflag = 3;
+            relerr = eps * releps;
+            abserr = eps * abseps;
+            for (int l = 0; l < neqn; ++l) y[l] = W.yy[l];
+            t = W.x;
+            break;
+        }
+        nostep = nostep + 1;
+        kle4 = kle4 + 1;
+        if (4 < W.kold) kle4 = 0;
+        if (50 <= kle4) stiff = true;
+    }
+    return iflag;
+}
+
+// SG_ode driver (SG_ode_m.f90:89-159): returns true if the ray stops; flag carries the reason
+template <class T>
+__device__ bool SG_ode(double *v, double &s, double &sout, double &rel_err, double &abs_err, int &flag, unsigned &nrhs) {
+    const int nv = T::nv();
+    for (;;) {
+        int code;
+        const int iflag = sg_de<T>(nv, v, s, sout, rel_err, abs_err, code, flag, nrhs);
+        if (code) { sout = s; return true; }
+        if (iflag == 2) return false;
+        if (iflag == 3) {
+            const double total_error = fabs(rel_err) + fabs(abs_err);
+            if (total_error > g_dc.c.SG_error_limit) { flag = RAYS_STOP_ODE_TOTAL_ERROR; return true; }
+            continue;
+        }
+        return true;  // error return: flag already set by de
+    }
+}
+
+// ---- the trace kernel ------------------------------------------------------------------------------------
+struct TraceArgs {
+    long long nray;                 // rays in this launch
+    const double *rvec0;            // [nray][3]   (Fortran rvec0(3,nray))
+    const double *rindex_vec0;      // [nray][3]
+    const double *ray_pwr_wt;       // [nray]
+    double *ray_vec;                // [nray][npoints_alloc][nv] or NULL (no trajectory storage)
+    double *residual;               // [nray][npoints_alloc] or NULL
+    int npoints_alloc;
+    int *npoints;                   // [nray]
+    int *stop_code;                 // [nray]
+    double *initial_ray_power, *end_residuals, *max_residuals, *end_ray_parameter;  // [nray]
+    double *start_ray_vec, *end_ray_vec;   // [nray][nv]
+    unsigned long long *queue;      // next ray index to hand out
+    unsigned long long *counters;   // [0] ray-steps, [1] RHS evaluations
+    // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_bins == NULL disables it
+    double *dep_bins;               // [n_bins] global accumulator
+    int n_bins;
+    double grid_min, grid_max;
+};
+
+RD_INLINE void store_point(double *dst, const double *v, int nv) {
+    // dst is 8-byte aligned; pair up into 16-byte stores when the row start allows it
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        int i = 0;
+        for (; i + 1 < nv; i += 2) *reinterpret_cast<double2 *>(dst + i) = make_double2(v[i], v[i + 1]);
+        if (i < nv) dst[i] = v[i];
+    } else {
+        dst[0] = v[0];
+        int i = 1;
+        for (; i + 1 < nv; i += 2) *reinterpret_cast<double2 *>(dst + i) = make_double2(v[i], v[i + 1]);
+        if (i < nv) dst[i] = v[i];
+    }
+}
+template <int NV> RD_INLINE void store_point_fixed(double *dst, const double (&v)[NV]) {
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i + 1 < NV; i += 2) *reinterpret_cast<double2 *>(dst + i) = make_double2(v[i], v[i + 1]);
+        if (NV & 1) dst[NV - 1] = v[NV - 1];
+    } else {
+        dst[0] = v[0];
+#pragma unroll
+        for (int i = 1; i + 1 < NV; i += 2) *reinterpret_cast<double2 *>(dst + i) = make_double2(v[i], v[i + 1]);
+        if (!(NV & 1)) dst[NV - 1] = v[NV - 1];
+    }
+}
+
+// binner_real for one segment (bin_to_uniform_grid_m.f90:179-262): spreads delta_Q = Q1 - Q0 uniformly
+// over the bins spanned by [x0, x1]
+RD_INLINE void bin_segment(double *bins, int n_bins, double xmin, double xmax, double xa, double xb, double Qa, double Qb) {
+    const double x_bin_width = (xmax - xmin) / n_bins;
+    const double x_low = fmin(xa, xb), x_high = fmax(xa, xb);
+    double ix_low = (x_low - xmin) / x_bin_width, ix_high = (x_high - xmin) / x_bin_width;
+    const double delta_ix = ix_high - ix_low;
+    int index_low = (int)floor(ix_low) + 1, index_high = (int)floor(ix_high) + 1;
+    if (x_high >= xmax) index_high = n_bins;
+    int delta_i = index_high - index_low;
+    double delta_Q = Qb - Qa;
+    const double Q_density = delta_Q / delta_ix;
+    if (fabs(delta_Q) < 4.0 * DBL_MIN) return;
+    if (x_high < xmin || x_low > xmax) return;
+    if (x_low < xmin) {
+        delta_Q = delta_Q * (ix_high / delta_ix);
+        ix_low = 0.0; index_low = 1;
+        delta_i = index_high - index_low;
+    }
+    if (x_high > xmax) {
+        delta_Q = delta_Q * (((double)n_bins - ix_low) / delta_ix);
+        ix_high = (double)n_bins; index_high = n_bins;
+        delta_i = index_high - index_low;
+    }
+    if (delta_i == 0) atomicAdd(bins + index_low - 1, delta_Q);
+    else if (delta_i > 0) {
+        atomicAdd(bins + index_low - 1, delta_Q * (((double)index_low - ix_low) / delta_ix));
+        atomicAdd(bins + index_high - 1, delta_Q * ((ix_high - (double)(index_high - 1)) / delta_ix));
+        for (int i = index_low + 1; i <= index_high - 1; ++i) atomicAdd(bins + i - 1, Q_density);
+    }
+}
+// abscissa of the deposition profile: Ptotal_x (slab) / Ptotal_psi (axisym_toroid)
+// (deposition_profiles_m.f90:438-499)
+template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
+    if (EQ_ == RAYS_EQ_SLAB) return v[0];
+    return solovev_psiN(v[0], v[1], v[2]);
+}
+
+constexpr int kTraceBlock = 128;
+
+template <class T, int ODE_>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
+    constexpr int NV = T::NV;
+    const int nv = T::nv();
+    const rays_cfg &c = g_dc.c;
+    const unsigned lane = threadIdx.x & 31;
+    // per-lane ray state
+    double v[NV];
+    double s = 0.0, sout = 0.0, rel_err = 0.0, abs_err = 0.0;
+    double resid_prev = 0.0, resid_last = 0.0, resid_max = 0.0;
+    double dep_x = 0.0, dep_Q = 0.0, pwr = 0.0;
+    long long iray = -1;
+    int nstep = 0, flag = 0;
+    bool active = false, exhausted = false;
+    unsigned long long my_steps = 0;
+    unsigned my_rhs = 0;
+    const bool binning = a.dep_bins != nullptr && T::damp();
+
+    for (;;) {
+        // ---- refill: lanes without a ray take the next indices from the queue (one atomic per warp)
+        const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+        if (want) {
+            unsigned long long base = 0;
+            const int leader = __ffs(want) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active && !exhausted) {
+                const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+                if (idx >= a.nray) exhausted = true;
+                else {
+                    iray = idx;
+                    nstep = 0; s = 0.0; sout = 0.0; flag = 0;
+                    rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_ode_solver (SG_ode_m.f90:73-85)
+                    resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
+                    initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                    pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
+                    if (a.ray_vec) {
+                        double *dst = a.ray_vec + (size_t)iray * a.npoints_alloc * nv;
+                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                    }
+                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc] = 0.0;
+                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                    double resid = 0.0;
+                    bool stop = false;
+                    check_save<T>(v, resid, stop, flag);
+                    if (stop) {   // "did not start": only npoints, flag and the first point are set (:101-112)
+                        a.npoints[iray] = 1;
+                        a.stop_code[iray] = flag;
+                        if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
+                        if (a.end_residuals) a.end_residuals[iray] = 0.0;
+                        if (a.max_residuals) a.max_residuals[iray] = 0.0;
+                        if (a.end_ray_parameter) a.end_ray_parameter[iray] = 0.0;
+                        if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = 0.0;
+                        if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = 0.0;
+                    } else {
+                        active = true;
+                        if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            continue;
+        }
+        // ---- one pass of the trajectory loop body (ray_tracing.f90:116-245) for every active lane
+        if (active) {
+            bool stop = false;
+            s = sout;
+            sout = sout + c.ds;
+            if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
+            else if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; nstep = c.nstep_max; }
+            else {
+                if (ODE_ == RAYS_ODE_RK4) {
+                    const int code = RK4_ode<T>(v, s, sout);
+                    my_rhs += 4;
+                    if (code) { stop = true; flag = code; }
+                } else {
+                    stop = SG_ode<T>(v, s, sout, rel_err, abs_err, flag, my_rhs);
+                }
+                double resid = 0.0;
+                if (!stop) check_save<T>(v, resid, stop, flag);
+                if (!stop) {
+                    nstep = nstep + 1;
+                    if (a.ray_vec) {
+                        double *dst = a.ray_vec + ((size_t)iray * a.npoints_alloc + nstep) * nv;
+                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                    }
+                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc + nstep] = resid;
+                    resid_prev = resid_last;
+                    resid_last = resid;
+                    if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
+                    if (binning) {
+                        const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
+                        bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
+                        dep_x = xn; dep_Q = Qn;
+                    }
+                    ++my_steps;
+                }
+            }
+            if (stop) {   // summary block (ray_tracing.f90:252-260)
+                a.npoints[iray] = nstep + 1;
+                a.stop_code[iray] = flag;
+                if (a.initial_ray_power) a.initial_ray_power[iray] = pwr;
+                if (a.end_residuals) a.end_residuals[iray] = nstep >= 1 ? resid_prev : 0.0;       // residual(nstep), (X) nstep = 0
+                if (a.max_residuals) a.max_residuals[iray] = nstep >= 1 ? resid_max : -DBL_MAX;   // maxval of an empty array
+                if (a.end_ray_parameter) a.end_ray_parameter[iray] = v[6];
+                if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
+                active = false;
+            }
+        }
+    }
+    // ---- per-warp totals -> global counters
+    unsigned long long st = my_steps, rh = my_rhs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
+    if (lane == 0) { atomicAdd(a.counters, st); atomicAdd(a.counters + 1, rh); }
+}
+
+// ---- one-point probes (unit parity tests through the C ABI) -----------------------------------------------
+template <class T> __global__ void probe_equilibrium_kernel(long long n, const double *rvec, double *out, int *err) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Eq<NSM> e;
+    equilibrium<T::EQ, T::NS, true>(rvec[3 * i], rvec[3 * i + 1], rvec[3 * i + 2], e);
+    double *o = out + (size_t)i * RAYS_EQ_OUT;
+    for (int k = 0; k < RAYS_EQ_OUT; ++k) o[k] = 0.0;
+    err[i] = e.err;
+    if (e.err) return;
+    int k = 0;
+    for (int q = 0; q < 3; ++q) o[k++] = e.bvec[q];
+    for (int jj = 0; jj < 3; ++jj) for (int ii = 0; ii < 3; ++ii) o[k++] = e.g[ii][jj];
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.ns[s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) for (int ii = 0; ii < 3; ++ii) o[k++] = s < NSM ? e.gradns[ii][s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.ts[s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) for (int ii = 0; ii < 3; ++ii) o[k++] = s == 0 ? e.gradts0[ii] : 0.0;  // electrons only
+    o[k++] = e.bmag;
+    for (int q = 0; q < 3; ++q) o[k++] = e.gradbmag[q];
+    for (int q = 0; q < 3; ++q) o[k++] = e.bunit[q];
+    for (int jj = 0; jj < 3; ++jj) for (int ii = 0; ii < 3; ++ii) o[k++] = e.gradbunit[ii][jj];
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.omgc[s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.omgp2[s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.alpha[s < NSM ? s : 0] : 0.0;
+    for (int s = 0; s < RAYS_NSPECIES; ++s) o[k++] = s < NSM ? e.gamma[s < NSM ? s : 0] : 0.0;
+}
+template <class T> __global__ void probe_rhs_kernel(long long n, const double *v, double *dvds, int *stop) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nv = T::nv();
+    double w[T::NV], f[T::NV];
+    for (int k = 0; k < T::NV; ++k) { w[k] = k < nv ? v[(size_t)i * nv + k] : 0.0; f[k] = 0.0; }
+    const int code = eqn_ray<T>(w, f);
+    for (int k = 0; k < nv; ++k) dvds[(size_t)i * nv + k] = code ? 0.0 : f[k];
+    stop[i] = code;
+}
+template <class T> __global__ void probe_check_save_kernel(long long n, const double *v, double *resid, int *stop) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nv = T::nv();
+    double w[T::NV];
+    for (int k = 0; k < T::NV; ++k) w[k] = k < nv ? v[(size_t)i * nv + k] : 0.0;
+    double r = 0.0;
+    bool st = false;
+    int flag = 0;
+    check_save<T>(w, r, st, flag);
+    resid[i] = r;
+    stop[i] = st ? flag : 0;
+}
+
+}  // namespace rays_dev

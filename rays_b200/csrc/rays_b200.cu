@@ -1,0 +1,905 @@
+// rays_b200.cu — the C ABI of include/rays_b200.h: device/stream life cycle, upload of the marshalled
+// module state and spline tables, fan and result buffers in HBM, kernel selection and launch, batched
+// trajectory copy-out in the reference's ray_results_m layout, launch-fan compaction, deposition
+// binning and the measurement helpers.  No CPU fallback: every entry point fails with RAYS_ERR_CUDA
+// when no GPU is present.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "trace_tu.cuh"
+
+namespace rays_dev {
+#define RAYS_TU_DECL(eq, ode) extern const TuOps rays_tu_ops_##eq##_##ode;
+RAYS_TU_DECL(1, 1) RAYS_TU_DECL(1, 2) RAYS_TU_DECL(2, 1) RAYS_TU_DECL(2, 2)
+RAYS_TU_DECL(3, 1) RAYS_TU_DECL(3, 2) RAYS_TU_DECL(4, 1) RAYS_TU_DECL(4, 2)
+const TuOps *tu_ops(int eq, int ode) {
+    static const TuOps *tab[5][3] = {{nullptr, nullptr, nullptr},
+                                     {nullptr, &rays_tu_ops_1_1, &rays_tu_ops_1_2},
+                                     {nullptr, &rays_tu_ops_2_1, &rays_tu_ops_2_2},
+                                     {nullptr, &rays_tu_ops_3_1, &rays_tu_ops_3_2},
+                                     {nullptr, &rays_tu_ops_4_1, &rays_tu_ops_4_2}};
+    if (eq < 1 || eq > 4 || ode < 1 || ode > 2) return nullptr;
+    return tab[eq][ode];
+}
+}  // namespace rays_dev
+
+using namespace rays_dev;
+
+namespace {
+
+std::string g_err;
+int set_err(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return set_err(RAYS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+template <class Tp> struct DevBuf {
+    Tp *p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(Tp));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct Ctx {
+    bool inited = false;
+    int device = -1, num_sms = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_batch[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    // config
+    bool cfg_set = false;
+    DevCfg dc{};
+    KernelSel sel{};
+    DevBuf<double> zx, zf, rgrid, zgrid, br, bz, aphi;
+    // fan (device)
+    long long nray = 0;
+    DevBuf<double> rvec0, nvec0, wt;
+    // results (device)
+    long long res_nray = 0;
+    int res_nv = 0, res_npa = 0;
+    bool have_traj = false;
+    DevBuf<double> ray_vec, residual, pwr, endres, maxres, endpar, startv, endv;
+    DevBuf<int> npoints, stop;
+    DevBuf<unsigned long long> queue;   // [0] queue, [1] ray-steps, [2] RHS evaluations
+    // deposition
+    DevBuf<double> dep;
+    int dep_bins = 0;
+    double dep_min = 0, dep_max = 0;
+    bool dep_fused = false;
+    // stats
+    double last_ms = 0;
+    long long last_steps = 0, last_rhs = 0;
+    int last_launches = 0;
+    const char *last_kernel = "";
+    int last_grid = 0, last_bps = 0;
+    // pinned staging for small results
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+} g;
+
+int need_init() { return g.inited ? 0 : set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_init has not been called"); }
+
+const char *kStopStrings[RAYS_STOP_CODE_MAX] = {
+    "", "sout > s_max", " nstep > nstep_max", "infinite Vg", "ray stalled", "dispersion_residual",
+    "infinite_Vg", "total_absorption", "ODE total error", "step number .ge. maxnum", "equations stiff",
+    "t == tout", "relerr or abserr < 0", "eps <= 0", "", "", "", "", "", "",
+    "x out_of_bounds", "y out_of_bounds", "z out_of_bounds", "R out_of_box", "z out_of_box",
+    "R_out_of_box", "Z_out_of_box", "out_of_plasma", "R out_of_bounds", "z out_of_bounds",
+    "negative_dens", "negative_temp"};
+
+int upload_table(DevBuf<double> &b, const double *src, size_t n) {
+    CK(b.reserve(n));
+    CK(cudaMemcpyAsync(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    return 0;
+}
+
+int validate_cfg(const rays_cfg &c) {
+    if (c.equilib_model < RAYS_EQ_SLAB || c.equilib_model > RAYS_EQ_MULTIPLE_MIRROR) return set_err(RAYS_ERR_INVALID_CONFIG, "equilibrium: improper equilib_model");
+    if (c.ode_solver != RAYS_ODE_RK4 && c.ode_solver != RAYS_ODE_SG) return set_err(RAYS_ERR_INVALID_CONFIG, "ode_solver: invalid ode solver");
+    if (c.ray_deriv != RAYS_DERIV_COLD && c.ray_deriv != RAYS_DERIV_NUM) return set_err(RAYS_ERR_INVALID_CONFIG, "EQN_RAY: invalid value, ray_deriv_name");
+    if (c.ray_param != RAYS_PARAM_ARCL && c.ray_param != RAYS_PARAM_TIME) return set_err(RAYS_ERR_INVALID_CONFIG, "EQN_RAY: invalid ray parameter");
+    if (c.nspec < 0 || c.nspec > RAYS_NSPEC0) return set_err(RAYS_ERR_INVALID_CONFIG, "species: nspec out of range");
+    if (c.damping_model != RAYS_DAMP_NONE && c.damping_model != RAYS_DAMP_FUND_ECH) return set_err(RAYS_ERR_INVALID_CONFIG, "damping: Unimplemented damping model");
+    int nv = 7;
+    if (c.damping_model != RAYS_DAMP_NONE) { nv += 1; if (c.multi_spec_damping) nv += 1 + c.nspec; }
+    if (c.integrate_eq_gradients) nv += 5;
+    if (c.nv != nv) return set_err(RAYS_ERR_INVALID_CONFIG, "ode_m: nv does not match damping/gradient options (ode_m.f90:160-173)");
+    if (c.nstep_max < 0) return set_err(RAYS_ERR_INVALID_CONFIG, "ode_m: nstep_max < 0");
+    if (c.damping_model == RAYS_DAMP_FUND_ECH && (!c.zfun_re.x_grid || !c.zfun_re.fspl || c.zfun_re.nx < 2))
+        return set_err(RAYS_ERR_INVALID_CONFIG, "damping: Z-function spline table missing");
+    if (c.equilib_model == RAYS_EQ_MULTIPLE_MIRROR) {
+        const rays_mirror_eq &m = c.mirror;
+        if (!m.Br_spline.fspl || !m.Bz_spline.fspl || !m.Aphi_spline.fspl || !m.Br_spline.x_grid || !m.Br_spline.y_grid)
+            return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: spline tables missing");
+        if (m.Bz_spline.nx != m.Br_spline.nx || m.Aphi_spline.nx != m.Br_spline.nx || m.Bz_spline.ny != m.Br_spline.ny || m.Aphi_spline.ny != m.Br_spline.ny)
+            return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: Br, Bz, Aphi must share one (r,z) grid");
+    }
+    return 0;
+}
+
+// ---- small utility kernels -------------------------------------------------------------------------------
+__global__ void fill_kernel(double *p, long long n, double v) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// order-preserving compaction of the launch-fan candidates: block-level exclusive scan of the
+// validity flags (one pass over per-block counts on a single block, then scatter)
+constexpr int kScanBlock = 256;
+__global__ void fan_count_kernel(const int *valid, long long n, int *block_counts) {
+    __shared__ int sh[kScanBlock / 32];
+    const long long i = blockIdx.x * (long long)kScanBlock + threadIdx.x;
+    const int f = (i < n) ? valid[i] : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, f != 0);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < kScanBlock / 32; ++w) s += sh[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+__global__ void fan_offsets_kernel(int *block_counts, int nblocks, long long *total) {
+    // single thread block, sequential over chunks: nblocks <= ~ 33k for 8M candidates
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int c = i < nblocks ? block_counts[i] : 0;
+        // inclusive scan in the block via warp shuffles
+        int x = c;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        __shared__ int wsum[32];
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int wv = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, wv, o); if (threadIdx.x >= o) wv += y; }
+            wsum[threadIdx.x] = wv;
+        }
+        __syncthreads();
+        const int woff = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+        const long long excl = carry + woff + x - c;
+        if (i < nblocks) block_counts[i] = (int)excl;   // fans are < 2^31 rays per GPU
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void fan_scatter_kernel(const int *valid, long long n, const int *block_offsets, const double *rv, const double *nv,
+                                   double *rvec0, double *nvec0) {
+    __shared__ int sh[kScanBlock / 32];
+    const long long i = blockIdx.x * (long long)kScanBlock + threadIdx.x;
+    const int f = (i < n) ? valid[i] : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, f != 0);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = __popc(b);
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < w; ++k) woff += sh[k];
+    if (f) {
+        const long long dst = (long long)block_offsets[blockIdx.x] + woff + __popc(b & ((1u << lane) - 1u));
+        for (int k = 0; k < 3; ++k) { rvec0[3 * dst + k] = rv[3 * i + k]; nvec0[3 * dst + k] = nv[3 * i + k]; }
+    }
+}
+// keep rays with iray % world == rank, order preserved
+__global__ void fan_shard_kernel(long long n_out, int rank, int world, const double *rv, const double *nv, const double *w,
+                                 double *rv_o, double *nv_o, double *w_o) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    const long long i = j * world + rank;
+    for (int k = 0; k < 3; ++k) { rv_o[3 * j + k] = rv[3 * i + k]; nv_o[3 * j + k] = nv[3 * i + k]; }
+    w_o[j] = w[i];
+}
+// calculate_deposition_profiles on stored trajectories (deposition_profiles_m.f90:228-292): one thread per ray
+template <int EQ_> __global__ void deposition_kernel(long long nray, int nv, int npa, const double *ray_vec, const int *npoints,
+                                                      const double *pwr, double *bins, int n_bins, double gmin, double gmax) {
+    const long long iray = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (iray >= nray) return;
+    const int np = npoints[iray];
+    const double *v = ray_vec + (size_t)iray * npa * nv;
+    const double P = pwr[iray];
+    double xa = dep_abscissa<EQ_>(v), Qa = v[7] * P;
+    for (int ip = 1; ip < np; ++ip) {
+        const double *vp = v + (size_t)ip * nv;
+        const double xb = dep_abscissa<EQ_>(vp), Qb = vp[7] * P;
+        bin_segment(bins, n_bins, gmin, gmax, xa, xb, Qa, Qb);
+        xa = xb; Qa = Qb;
+    }
+}
+// DFMA-only microbenchmark (fp64 roofline denominator): 8 independent chains per thread
+__global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int ensure_results(long long nray, int nv, int npa, bool traj) {
+    CK(g.npoints.reserve((size_t)nray));
+    CK(g.stop.reserve((size_t)nray));
+    CK(g.pwr.reserve((size_t)nray));
+    CK(g.endres.reserve((size_t)nray));
+    CK(g.maxres.reserve((size_t)nray));
+    CK(g.endpar.reserve((size_t)nray));
+    CK(g.startv.reserve((size_t)nray * nv));
+    CK(g.endv.reserve((size_t)nray * nv));
+    CK(g.queue.reserve(4));
+    if (traj) {
+        CK(g.ray_vec.reserve((size_t)nray * npa * nv));
+        CK(g.residual.reserve((size_t)nray * npa));
+    }
+    g.res_nray = nray; g.res_nv = nv; g.res_npa = npa; g.have_traj = traj;
+    return 0;
+}
+
+// launch the trace kernel over rays [first, first+count) of the device fan into result slots [first..)
+// trajectories go to traj_base (indexed from 0 for ray `first`) when non-null
+int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned) {
+    const rays_cfg &c = g.dc.c;
+    const TuOps *ops = tu_ops(c.equilib_model, c.ode_solver);
+    if (!ops) return set_err(RAYS_ERR_INVALID_CONFIG, "no kernel for this equilibrium/ode pair");
+    TraceArgs a{};
+    a.nray = count;
+    a.rvec0 = g.rvec0.p + 3 * first;
+    a.rindex_vec0 = g.nvec0.p + 3 * first;
+    a.ray_pwr_wt = g.wt.p + first;
+    a.ray_vec = traj_base;
+    a.residual = resid_base;
+    a.npoints_alloc = g.res_npa;
+    a.npoints = g.npoints.p + first;
+    a.stop_code = g.stop.p + first;
+    a.initial_ray_power = g.pwr.p + first;
+    a.end_residuals = g.endres.p + first;
+    a.max_residuals = g.maxres.p + first;
+    a.end_ray_parameter = g.endpar.p + first;
+    a.start_ray_vec = g.startv.p + (size_t)first * g.res_nv;
+    a.end_ray_vec = g.endv.p + (size_t)first * g.res_nv;
+    a.queue = g.queue.p;
+    a.counters = g.queue.p + 1;
+    a.dep_bins = binned ? g.dep.p : nullptr;
+    a.n_bins = g.dep_bins; a.grid_min = g.dep_min; a.grid_max = g.dep_max;
+    int bps = 0;
+    const char *name = "";
+    CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name));
+    if (bps < 1) bps = 1;
+    long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;
+    int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
+    CK(cudaMemsetAsync(g.queue.p, 0, sizeof(unsigned long long), g.stream));
+    CK(ops->trace(g.sel, a, grid, g.stream, nullptr, nullptr));
+    g.last_kernel = name; g.last_grid = grid; g.last_bps = bps;
+    g.last_launches += 1;
+    return 0;
+}
+
+int fetch_counters() {
+    unsigned long long h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, g.queue.p, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.last_steps = (long long)h[1];
+    g.last_rhs = (long long)h[2];
+    return 0;
+}
+
+int copy_small_results(rays_results *res, long long first, long long count) {
+    const int nv = g.res_nv;
+    auto cp = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        if (!dst || bytes == 0) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream);
+    };
+    CK(cp(res->npoints ? res->npoints + first : nullptr, g.npoints.p + first, count * sizeof(int)));
+    CK(cp(res->ray_stop_code ? res->ray_stop_code + first : nullptr, g.stop.p + first, count * sizeof(int)));
+    CK(cp(res->initial_ray_power ? res->initial_ray_power + first : nullptr, g.pwr.p + first, count * sizeof(double)));
+    CK(cp(res->end_residuals ? res->end_residuals + first : nullptr, g.endres.p + first, count * sizeof(double)));
+    CK(cp(res->max_residuals ? res->max_residuals + first : nullptr, g.maxres.p + first, count * sizeof(double)));
+    CK(cp(res->end_ray_parameter ? res->end_ray_parameter + first : nullptr, g.endpar.p + first, count * sizeof(double)));
+    CK(cp(res->start_ray_vec ? res->start_ray_vec + (size_t)first * nv : nullptr, g.startv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
+    CK(cp(res->end_ray_vec ? res->end_ray_vec + (size_t)first * nv : nullptr, g.endv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
+    return 0;
+}
+
+void fill_flags(rays_results *res, const std::vector<int> &codes, long long first) {
+    if (!res->ray_stop_flag) return;
+    for (size_t i = 0; i < codes.size(); ++i) rays_b200_stop_string(codes[i], res->ray_stop_flag + (size_t)(first + (long long)i) * RAYS_FLAG_LEN, RAYS_FLAG_LEN);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rays_b200_version(void) { return 100; }
+int rays_b200_struct_sizes(int32_t *out, int n) {
+    const int32_t sz[13] = {(int32_t)sizeof(rays_cfg), (int32_t)sizeof(rays_fan), (int32_t)sizeof(rays_results), (int32_t)sizeof(rays_deposition),
+                            (int32_t)sizeof(rays_solovev_launch), (int32_t)sizeof(rays_axisym_launch), (int32_t)sizeof(rays_slab_launch),
+                            (int32_t)sizeof(rays_spline1d), (int32_t)sizeof(rays_spline2d), (int32_t)sizeof(rays_slab_eq),
+                            (int32_t)sizeof(rays_solovev_eq), (int32_t)sizeof(rays_axisym_eq), (int32_t)sizeof(rays_mirror_eq)};
+    for (int i = 0; i < n && i < 13; ++i) out[i] = sz[i];
+    return 13;
+}
+const char *rays_b200_last_error(void) { return g_err.c_str(); }
+
+int rays_b200_stop_string(int code, char *buf, int len) {
+    const char *s = (code >= 0 && code < RAYS_STOP_CODE_MAX) ? kStopStrings[code] : "";
+    const int n = (int)std::strlen(s);
+    for (int i = 0; i < len; ++i) buf[i] = i < n ? s[i] : ' ';
+    return 0;
+}
+
+int rays_b200_init(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(RAYS_ERR_CUDA, "rays_b200_init: device index out of range");
+    if (g.inited && g.device == device) return 0;
+    if (g.inited) rays_b200_finalize();
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init: kernels are built for sm_100a only; found ") + prop.name);
+    g.device = device;
+    g.num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g.ev0));
+    CK(cudaEventCreate(&g.ev1));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&g.ev_batch[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming));
+    }
+    g.inited = true;
+    return 0;
+}
+
+int rays_b200_finalize(void) {
+    if (!g.inited) return 0;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
+                              &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv, &g.dep};
+    for (auto *b : bufs) b->release();
+    g.npoints.release(); g.stop.release(); g.queue.release();
+    if (g.pinned) cudaFreeHost(g.pinned);
+    g.pinned = nullptr; g.pinned_bytes = 0;
+    cudaEventDestroy(g.ev0); cudaEventDestroy(g.ev1);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(g.ev_batch[i]); cudaEventDestroy(g.ev_copy[i]); }
+    cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream);
+    g = Ctx{};
+    return 0;
+}
+
+void *rays_b200_stream(void) { return g.inited ? (void *)g.stream : nullptr; }
+
+int rays_b200_set_config(const rays_cfg *cfg) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!cfg) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_set_config: null config");
+    int rc = validate_cfg(*cfg);
+    if (rc) return rc;
+    CK(cudaSetDevice(g.device));
+    DevCfg &d = g.dc;
+    d.c = *cfg;
+    rays_cfg &c = d.c;
+    // tables -> HBM; the struct then carries device pointers
+    if (c.damping_model == RAYS_DAMP_FUND_ECH) {
+        if ((rc = upload_table(g.zx, cfg->zfun_re.x_grid, (size_t)cfg->zfun_re.nx))) return rc;
+        if ((rc = upload_table(g.zf, cfg->zfun_re.fspl, (size_t)4 * cfg->zfun_re.nx))) return rc;
+        c.zfun_re.x_grid = g.zx.p; c.zfun_re.fspl = g.zf.p;
+    } else { c.zfun_re.x_grid = nullptr; c.zfun_re.fspl = nullptr; c.zfun_re.nx = 0; }
+    if (c.equilib_model == RAYS_EQ_MULTIPLE_MIRROR) {
+        const rays_mirror_eq &m = cfg->mirror;
+        const size_t nx = (size_t)m.Br_spline.nx, ny = (size_t)m.Br_spline.ny;
+        if ((rc = upload_table(g.rgrid, m.Br_spline.x_grid, nx))) return rc;
+        if ((rc = upload_table(g.zgrid, m.Br_spline.y_grid, ny))) return rc;
+        if ((rc = upload_table(g.br, m.Br_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(g.bz, m.Bz_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(g.aphi, m.Aphi_spline.fspl, 16 * nx * ny))) return rc;
+        rays_spline2d base = m.Br_spline;
+        base.x_grid = g.rgrid.p; base.y_grid = g.zgrid.p;
+        c.mirror.Br_spline = base; c.mirror.Br_spline.fspl = g.br.p;
+        c.mirror.Bz_spline = base; c.mirror.Bz_spline.fspl = g.bz.p;
+        c.mirror.Aphi_spline = base; c.mirror.Aphi_spline.fspl = g.aphi.p;
+    } else {
+        rays_spline2d none{};
+        c.mirror.Br_spline = none; c.mirror.Bz_spline = none; c.mirror.Aphi_spline = none;
+    }
+    // constant products, formed with the same IEEE operations the reference performs per call
+    for (int s = 0; s < RAYS_NSPECIES; ++s) { d.qs2[s] = c.qs[s] * c.qs[s]; d.eps0ms[s] = c.eps0 * c.ms[s]; }
+    d.omgrf2 = c.omgrf * c.omgrf;
+    d.two_over_k0 = 2.0 / c.k0;
+    d.two_over_omgrf = 2.0 / c.omgrf;
+    d.m2_over_omgrf = -(2.0 / c.omgrf);
+    d.one_over_omgrf = 1.0 / c.omgrf;
+    if (c.equilib_model == RAYS_EQ_SOLOVEV) {
+        d.sv_rmaj = c.solovev.rmaj; d.sv_kappa = c.solovev.kappa; d.sv_bphi0 = c.solovev.bphi0; d.sv_iota0 = c.solovev.iota0; d.sv_psiB = c.solovev.psiB;
+    } else {
+        d.sv_rmaj = c.axisym.sm_rmaj; d.sv_kappa = c.axisym.sm_kappa; d.sv_bphi0 = c.axisym.sm_bphi0; d.sv_iota0 = c.axisym.sm_iota0; d.sv_psiB = c.axisym.sm_psiB;
+    }
+    d.sv_bp0 = d.sv_bphi0 * d.sv_iota0;
+    d.sv_rk = d.sv_rmaj * d.sv_kappa;
+    d.sv_rk2 = d.sv_rk * d.sv_rk;
+    d.sv_rmaj2 = d.sv_rmaj * d.sv_rmaj;
+    d.sv_bphi0_rmaj = d.sv_bphi0 * d.sv_rmaj;
+    d.dn_delta = (double)1.e-6f;
+    d.dn_two_delta = 2.0 * d.dn_delta;
+    d.dn_omg_p = c.omgrf * (1.0 + d.dn_delta / 2.0);
+    d.dn_omg_m = c.omgrf * (1.0 - d.dn_delta / 2.0);
+    d.dn_k0_p = d.dn_omg_p / c.clight;
+    d.dn_k0_m = d.dn_omg_m / c.clight;
+    d.dn_omg_p2 = d.dn_omg_p * d.dn_omg_p;
+    d.dn_omg_m2 = d.dn_omg_m * d.dn_omg_m;
+    d.dn_omg_delta = c.omgrf * d.dn_delta;
+    // kernel selection: the two-species specialisations cover electron + one ion without per-species damping slots
+    g.sel.ray_deriv = c.ray_deriv;
+    g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
+    g.sel.damp = c.damping_model != RAYS_DAMP_NONE;
+    g.sel.grads = c.integrate_eq_gradients != 0;
+    for (int ode = 1; ode <= 2; ++ode) {
+        const TuOps *ops = tu_ops(c.equilib_model, ode);
+        if (ops) CK(ops->upload(&d, g.stream));
+    }
+    CK(cudaMemcpyToSymbolAsync(g_dc, &d, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, g.stream));   // this TU: deposition kernel
+    CK(cudaStreamSynchronize(g.stream));
+    g.cfg_set = true;
+    return 0;
+}
+
+int rays_b200_fan_upload(const rays_fan *fan) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!fan || fan->nray < 0 || (fan->nray > 0 && (!fan->rvec0 || !fan->rindex_vec0))) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_fan_upload: bad fan");
+    CK(cudaSetDevice(g.device));
+    const size_t n = (size_t)fan->nray;
+    CK(g.rvec0.reserve(3 * n)); CK(g.nvec0.reserve(3 * n)); CK(g.wt.reserve(n));
+    if (n) {
+        CK(cudaMemcpyAsync(g.rvec0.p, fan->rvec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(g.nvec0.p, fan->rindex_vec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        if (fan->ray_pwr_wt) CK(cudaMemcpyAsync(g.wt.p, fan->ray_pwr_wt, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        else CK(cudaMemsetAsync(g.wt.p, 0, n * sizeof(double), g.stream));
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    g.nray = fan->nray;
+    return 0;
+}
+
+int rays_b200_fan_download(double *rvec0, double *rindex_vec0, double *ray_pwr_wt) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    const size_t n = (size_t)g.nray;
+    if (n == 0) return 0;
+    if (rvec0) CK(cudaMemcpyAsync(rvec0, g.rvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (rindex_vec0) CK(cudaMemcpyAsync(rindex_vec0, g.nvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (ray_pwr_wt) CK(cudaMemcpyAsync(ray_pwr_wt, g.wt.p, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+int rays_b200_fan_shard(int rank, int world) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (world < 1 || rank < 0 || rank >= world) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_fan_shard: bad rank/world");
+    if (world == 1 || g.nray == 0) return 0;
+    const long long n_out = (g.nray - rank + world - 1) / world;
+    DevBuf<double> rv, nv, w;
+    CK(rv.reserve((size_t)3 * std::max<long long>(n_out, 1))); CK(nv.reserve((size_t)3 * std::max<long long>(n_out, 1))); CK(w.reserve((size_t)std::max<long long>(n_out, 1)));
+    if (n_out > 0) {
+        fan_shard_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, g.stream>>>(n_out, rank, world, g.rvec0.p, g.nvec0.p, g.wt.p, rv.p, nv.p, w.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    std::swap(g.rvec0, rv); std::swap(g.nvec0, nv); std::swap(g.wt, w);
+    rv.release(); nv.release(); w.release();
+    g.nray = n_out;
+    return 0;
+}
+
+static int trace_device_impl(int store_trajectories, bool binned) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    CK(cudaSetDevice(g.device));
+    const rays_cfg &c = g.dc.c;
+    const int npa = c.nstep_max + 1;
+    if (store_trajectories) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const double need = (double)g.nray * npa * (c.nv + 1) * 8.0;
+        const double have = (double)free_b + (double)(g.ray_vec.n + g.residual.n) * 8.0;
+        if (need > 0.92 * have)
+            return set_err(RAYS_ERR_ALLOC, "rays_b200_trace_device: trajectories of this fan do not fit in HBM; trace without storage (binned) or use rays_b200_trace, which batches");
+    }
+    int rc = ensure_results(g.nray, c.nv, npa, store_trajectories != 0);
+    if (rc) return rc;
+    g.last_launches = 0;
+    CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
+    if (binned) CK(cudaMemsetAsync(g.dep.p, 0, (size_t)g.dep_bins * sizeof(double), g.stream));
+    CK(cudaEventRecord(g.ev0, g.stream));
+    if (g.nray > 0) {
+        rc = launch_trace(0, g.nray, store_trajectories ? g.ray_vec.p : nullptr, store_trajectories ? g.residual.p : nullptr, binned);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(g.ev1, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+    g.last_ms = ms;
+    g.dep_fused = binned;
+    return fetch_counters();
+}
+
+int rays_b200_trace_device(int store_trajectories) { return trace_device_impl(store_trajectories, false); }
+
+int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (n_bins < 1 || !(grid_max > grid_min)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad grid");
+    const rays_cfg &c = g.dc.c;
+    if (c.damping_model == RAYS_DAMP_NONE) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: needs a damping model (v(8) = absorbed power)");
+    if (c.equilib_model != RAYS_EQ_SLAB && c.equilib_model != RAYS_EQ_AXISYM_TOROID)
+        return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
+    CK(g.dep.reserve((size_t)n_bins));
+    g.dep_bins = n_bins; g.dep_min = grid_min; g.dep_max = grid_max;
+    return trace_device_impl(store_trajectories, true);
+}
+
+int rays_b200_last_trace_stats(double *kernel_ms, int64_t *ray_steps, int32_t *n_launches) {
+    if (kernel_ms) *kernel_ms = g.last_ms;
+    if (ray_steps) *ray_steps = g.last_steps;
+    if (n_launches) *n_launches = g.last_launches;
+    return 0;
+}
+// extra stats for bench/profiles: RHS evaluations, kernel name, grid, resident CTAs per SM
+int rays_b200_last_trace_info(int64_t *rhs_evals, char *kernel_name, int name_len, int32_t *grid, int32_t *blocks_per_sm) {
+    if (rhs_evals) *rhs_evals = g.last_rhs;
+    if (kernel_name && name_len > 0) { std::strncpy(kernel_name, g.last_kernel, (size_t)name_len - 1); kernel_name[name_len - 1] = 0; }
+    if (grid) *grid = g.last_grid;
+    if (blocks_per_sm) *blocks_per_sm = g.last_bps;
+    return 0;
+}
+
+int rays_b200_results_download(rays_results *res) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!res) return set_err(RAYS_ERR_INVALID_CONFIG, "null results");
+    if (res->nray < g.res_nray || res->nv != g.res_nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: result arrays do not match the last trace");
+    const long long n = g.res_nray;
+    const int nv = g.res_nv;
+    int rc = copy_small_results(res, 0, n);
+    if (rc) return rc;
+    std::vector<int> np((size_t)n), codes((size_t)n);
+    if (n) {
+        CK(cudaMemcpyAsync(np.data(), g.npoints.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaMemcpyAsync(codes.data(), g.stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    if (g.have_traj && n && (res->ray_vec || res->residual)) {
+        if (res->npoints_alloc < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "npoints_alloc < 1");
+        int maxnp = 1;
+        for (long long i = 0; i < n; ++i) maxnp = std::max(maxnp, np[(size_t)i]);
+        if (maxnp > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
+        if (res->ray_vec)
+            CK(cudaMemcpy2DAsync(res->ray_vec, (size_t)res->npoints_alloc * nv * 8, g.ray_vec.p, (size_t)g.res_npa * nv * 8, (size_t)maxnp * nv * 8, (size_t)n,
+                                 cudaMemcpyDeviceToHost, g.stream));
+        if (res->residual)
+            CK(cudaMemcpy2DAsync(res->residual, (size_t)res->npoints_alloc * 8, g.residual.p, (size_t)g.res_npa * 8, (size_t)maxnp * 8, (size_t)n,
+                                 cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    fill_flags(res, codes, 0);
+    res->total_trace_time = g.last_ms * 1e-3;
+    res->total_ray_steps = g.last_steps;
+    if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = n ? res->total_trace_time / (double)n : 0.0;
+    return 0;
+}
+
+// trace_rays with HOST buffers (ray_tracing.f90:1-290): H2D of the fan, trace in batches sized to HBM with
+// two trajectory buffers so that the copy-out of batch b overlaps the integration of batch b+1, results
+// land in the caller's arrays in the reference layout.
+int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!fan || !res) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: null argument");
+    int rc;
+    if (cfg) { if ((rc = rays_b200_set_config(cfg))) return rc; }
+    else if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_trace: no config");
+    const rays_cfg &c = g.dc.c;
+    if (res->nray < fan->nray || res->nv != c.nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: result arrays do not match fan/nv");
+    if (!res->npoints) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: npoints array is required");
+    const bool want_traj = res->ray_vec != nullptr || res->residual != nullptr;
+    const int npa = c.nstep_max + 1;
+    if (want_traj && res->npoints_alloc < npa) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: npoints_alloc < nstep_max+1");
+    CK(cudaEventRecord(g.ev0, g.stream));
+    if ((rc = rays_b200_fan_upload(fan))) return rc;
+    const long long n = g.nray;
+    const int nv = c.nv;
+    // batch size: two trajectory buffers within ~70% of free HBM
+    long long batch = std::max<long long>(n, 1);
+    if (want_traj && n > 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const double avail = 0.70 * ((double)free_b + (double)(g.ray_vec.n + g.residual.n) * 8.0);
+        const double per_ray = (double)npa * (nv + 1) * 8.0;
+        if ((double)n * per_ray > avail) {
+            batch = (long long)(avail / (2.0 * per_ray));
+            batch = std::max<long long>(batch / kTraceBlock * kTraceBlock, kTraceBlock);
+        }
+    }
+    const int nbuf = (batch < n) ? 2 : 1;
+    if ((rc = ensure_results(n, nv, npa, false))) return rc;
+    if (want_traj) {
+        CK(g.ray_vec.reserve((size_t)nbuf * batch * npa * nv));
+        CK(g.residual.reserve((size_t)nbuf * batch * npa));
+        g.have_traj = (nbuf == 1);
+    }
+    g.last_launches = 0;
+    CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
+    std::vector<int> np((size_t)std::max<long long>(n, 1)), codes((size_t)std::max<long long>(n, 1));
+    int ib = 0;
+    for (long long first = 0; first < n; first += batch, ++ib) {
+        const long long count = std::min(batch, n - first);
+        const int b = ib % nbuf;
+        double *tv = want_traj ? g.ray_vec.p + (size_t)b * batch * npa * nv : nullptr;
+        double *tr = want_traj ? g.residual.p + (size_t)b * batch * npa : nullptr;
+        if (ib >= nbuf) CK(cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0));   // buffer b free again
+        if ((rc = launch_trace(first, count, tv, tr, false))) return rc;
+        CK(cudaMemcpyAsync(np.data() + first, g.npoints.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaMemcpyAsync(codes.data() + first, g.stop.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaEventRecord(g.ev_batch[b], g.stream));
+        if (want_traj) {
+            CK(cudaEventSynchronize(g.ev_batch[b]));   // npoints of this batch are on the host: trim the copy
+            int maxnp = 1;
+            for (long long i = first; i < first + count; ++i) maxnp = std::max(maxnp, np[(size_t)i]);
+            if (res->ray_vec)
+                CK(cudaMemcpy2DAsync(res->ray_vec + (size_t)first * res->npoints_alloc * nv, (size_t)res->npoints_alloc * nv * 8, tv, (size_t)npa * nv * 8,
+                                     (size_t)maxnp * nv * 8, (size_t)count, cudaMemcpyDeviceToHost, g.copy_stream));
+            if (res->residual)
+                CK(cudaMemcpy2DAsync(res->residual + (size_t)first * res->npoints_alloc, (size_t)res->npoints_alloc * 8, tr, (size_t)npa * 8, (size_t)maxnp * 8,
+                                     (size_t)count, cudaMemcpyDeviceToHost, g.copy_stream));
+            CK(cudaEventRecord(g.ev_copy[b], g.copy_stream));
+        }
+    }
+    if ((rc = copy_small_results(res, 0, n))) return rc;
+    CK(cudaEventRecord(g.ev1, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(g.copy_stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+    g.last_ms = ms;
+    if ((rc = fetch_counters())) return rc;
+    if (res->ray_stop_code == nullptr) { /* codes only needed for the strings */ }
+    codes.resize((size_t)n);
+    fill_flags(res, codes, 0);
+    res->total_trace_time = g.last_ms * 1e-3;
+    res->total_ray_steps = g.last_steps;
+    if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = n ? res->total_trace_time / (double)n : 0.0;
+    g.dep_fused = false;
+    return 0;
+}
+
+// ======================= launch fans =========================================================================
+static int run_launch_fan(int kind, long long npos, const std::vector<double> &pos_host, const double *dir_host, int n_a, int n_b, double a0,
+                          double da, double b0, double db, int64_t *nray_out) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    CK(cudaSetDevice(g.device));
+    const rays_cfg &c = g.dc.c;
+    const TuOps *ops = tu_ops(c.equilib_model, RAYS_ODE_RK4);
+    const long long ncand = kind == 4 ? npos : npos * n_a * n_b;
+    if (ncand <= 0) { g.nray = 0; if (nray_out) *nray_out = 0; return 0; }
+    if (ncand >= (1LL << 31)) return set_err(RAYS_ERR_INVALID_CONFIG, "launch fan: more than 2^31 candidates on one GPU");
+    DevBuf<double> pos, dir, rv, nv;
+    DevBuf<int> valid, counts;
+    DevBuf<long long> total;
+    CK(pos.reserve(pos_host.size()));
+    CK(cudaMemcpyAsync(pos.p, pos_host.data(), pos_host.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    if (kind == 4) {
+        CK(dir.reserve((size_t)3 * ncand));
+        CK(cudaMemcpyAsync(dir.p, dir_host, (size_t)3 * ncand * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    }
+    const int nblocks = (int)((ncand + kScanBlock - 1) / kScanBlock);
+    CK(rv.reserve((size_t)3 * ncand)); CK(nv.reserve((size_t)3 * ncand)); CK(valid.reserve((size_t)ncand));
+    CK(counts.reserve((size_t)nblocks)); CK(total.reserve(1));
+    FanLaunchArgs f{};
+    f.kind = kind; f.ncand = ncand; f.rvec_in = pos.p; f.nvec_in = dir.p; f.n_a = n_a; f.n_b = n_b;
+    f.a0 = a0; f.da = da; f.b0 = b0; f.db = db; f.rvec_out = rv.p; f.nvec_out = nv.p; f.valid = valid.p;
+    CK(ops->launch_fan(g.sel, f, g.stream));
+    fan_count_kernel<<<nblocks, kScanBlock, 0, g.stream>>>(valid.p, ncand, counts.p);
+    CK(cudaGetLastError());
+    fan_offsets_kernel<<<1, 1024, 0, g.stream>>>(counts.p, nblocks, total.p);
+    CK(cudaGetLastError());
+    long long nray = 0;
+    CK(cudaMemcpyAsync(&nray, total.p, sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    CK(g.rvec0.reserve((size_t)3 * std::max<long long>(nray, 1))); CK(g.nvec0.reserve((size_t)3 * std::max<long long>(nray, 1)));
+    CK(g.wt.reserve((size_t)std::max<long long>(nray, 1)));
+    if (nray > 0) {
+        fan_scatter_kernel<<<nblocks, kScanBlock, 0, g.stream>>>(valid.p, ncand, counts.p, rv.p, nv.p, g.rvec0.p, g.nvec0.p);
+        CK(cudaGetLastError());
+        double w = 1.0 / (double)nray;
+        if (kind == 1) w = 1.0 / (double)nray / (double)nray;   // (R) divided by nray twice (simple_slab_ray_init_m.f90:179,182)
+        fill_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, g.stream>>>(g.wt.p, nray, w);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    pos.release(); dir.release(); rv.release(); nv.release(); valid.release(); counts.release(); total.release();
+    g.nray = nray;
+    if (nray_out) *nray_out = nray;
+    return 0;
+}
+
+int rays_b200_launch_fan_slab(const rays_slab_launch *p, int64_t *nray_out) {
+    if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
+    if (g.cfg_set && g.dc.c.equilib_model != RAYS_EQ_SLAB) return set_err(RAYS_ERR_INVALID_CONFIG, "simple_slab ray init needs equilib_model 'slab'");
+    std::vector<double> pos;
+    for (int iz = 1; iz <= p->n_z_launch; ++iz)
+        for (int iy = 1; iy <= p->n_y_launch; ++iy)
+            for (int ix = 1; ix <= p->n_x_launch; ++ix) {
+                pos.push_back(p->x_launch0 + (ix - 1) * p->dx_launch);
+                pos.push_back(p->y_launch0 + (iy - 1) * p->dy_launch);
+                pos.push_back(p->z_launch0 + (iz - 1) * p->dy_launch);   // (R) z uses dy_launch (simple_slab_ray_init_m.f90:122)
+            }
+    return run_launch_fan(1, (long long)pos.size() / 3, pos, nullptr, p->n_ky_launch, p->n_kz_launch, p->rindex_y0, p->delta_rindex_y0, p->rindex_z0,
+                          p->delta_rindex_z0, nray_out);
+}
+int rays_b200_launch_fan_solovev(const rays_solovev_launch *p, int64_t *nray_out) {
+    if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (g.dc.c.equilib_model != RAYS_EQ_SOLOVEV) return set_err(RAYS_ERR_INVALID_CONFIG, "solovev ray init needs equilib_model 'solovev'");
+    std::vector<double> pos;
+    const double rmaj = g.dc.c.solovev.rmaj;
+    for (int ir = 1; ir <= p->n_r_launch; ++ir)
+        for (int it = 1; it <= p->n_theta_launch; ++it) {
+            const double theta = p->theta_launch0 + (it - 1) * p->dtheta_launch;
+            const double rmin_launch = p->r_launch0 + (ir - 1) * p->dr_launch;
+            pos.push_back(rmaj + rmin_launch * std::cos(theta));
+            pos.push_back(0.0);
+            pos.push_back(rmin_launch * std::sin(theta));
+        }
+    return run_launch_fan(2, (long long)pos.size() / 3, pos, nullptr, p->n_rindex_theta, p->n_rindex_phi, p->rindex_theta0, p->delta_rindex_theta,
+                          p->rindex_phi0, p->delta_rindex_phi, nray_out);
+}
+int rays_b200_launch_fan_axisym(const rays_axisym_launch *p, int64_t *nray_out) {
+    if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (g.dc.c.equilib_model != RAYS_EQ_AXISYM_TOROID) return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid ray init needs equilib_model 'axisym_toroid'");
+    std::vector<double> pos;
+    for (int iR = 1; iR <= p->n_R_launch; ++iR)
+        for (int iZ = 1; iZ <= p->n_Z_launch; ++iZ) {   // (R) every (i_R, i_Z) launches from the same point
+            pos.push_back(p->R_launch0); pos.push_back(0.0); pos.push_back(p->Z_launch0);
+        }
+    return run_launch_fan(3, (long long)pos.size() / 3, pos, nullptr, p->n_rindex_theta, p->n_rindex_phi, p->rindex_theta0, p->delta_rindex_theta,
+                          p->rindex_phi0, p->delta_rindex_phi, nray_out);
+}
+int rays_b200_launch_fan_directions(int64_t n_in, const double *rvec_in, const double *nvec_in, int64_t *nray_out) {
+    if (n_in < 0 || (n_in > 0 && (!rvec_in || !nvec_in))) return set_err(RAYS_ERR_INVALID_CONFIG, "launch fan: bad input arrays");
+    std::vector<double> pos(rvec_in, rvec_in + 3 * n_in);
+    return run_launch_fan(4, n_in, pos, nvec_in, 1, 1, 0, 0, 0, 0, nray_out);
+}
+
+// ======================= deposition ==========================================================================
+int rays_b200_deposition(rays_deposition *dep, double *d_profile_out) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!dep || dep->n_bins < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad arguments");
+    const rays_cfg &c = g.dc.c;
+    const int nb = dep->n_bins;
+    if (g.dep_fused) {
+        if (nb != g.dep_bins) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: n_bins differs from the binned trace");
+    } else {
+        if (!g.have_traj) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: no stored trajectories; trace with storage or use rays_b200_trace_device_binned");
+        if (c.damping_model == RAYS_DAMP_NONE) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: needs a damping model");
+        if (c.equilib_model != RAYS_EQ_SLAB && c.equilib_model != RAYS_EQ_AXISYM_TOROID)
+            return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
+        CK(g.dep.reserve((size_t)nb));
+        g.dep_bins = nb; g.dep_min = dep->grid_min; g.dep_max = dep->grid_max;
+        CK(cudaMemsetAsync(g.dep.p, 0, (size_t)nb * sizeof(double), g.stream));
+        if (g.res_nray > 0) {
+            const unsigned grid = (unsigned)((g.res_nray + 127) / 128);
+            if (c.equilib_model == RAYS_EQ_SLAB)
+                deposition_kernel<RAYS_EQ_SLAB><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, g.dep.p, nb, dep->grid_min, dep->grid_max);
+            else
+                deposition_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, g.dep.p, nb, dep->grid_min, dep->grid_max);
+            CK(cudaGetLastError());
+        }
+    }
+    std::vector<double> h((size_t)nb);
+    CK(cudaMemcpyAsync(h.data(), g.dep.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (d_profile_out) CK(cudaMemcpyAsync(d_profile_out, g.dep.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    double q = 0.0;
+    for (int b = 0; b < nb; ++b) { if (dep->profile) dep->profile[b] = h[(size_t)b]; q += h[(size_t)b]; }
+    dep->Q_sum = q;
+    if (d_profile_out) {
+        CK(cudaMemcpyAsync(d_profile_out + nb, &q, sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    return 0;
+}
+
+// ======================= probes ==============================================================================
+static int run_probe(int which, int64_t n, const double *in, size_t in_per, double *out, size_t out_per, int32_t *code) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(g.device));
+    const TuOps *ops = tu_ops(g.dc.c.equilib_model, RAYS_ODE_RK4);
+    DevBuf<double> din, dout;
+    DevBuf<int> dcode;
+    CK(din.reserve((size_t)n * in_per)); CK(dout.reserve((size_t)n * out_per)); CK(dcode.reserve((size_t)n));
+    CK(cudaMemcpyAsync(din.p, in, (size_t)n * in_per * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    cudaError_t e;
+    if (which == 0) e = ops->probe_equilibrium(g.sel, n, din.p, dout.p, dcode.p, g.stream);
+    else if (which == 1) e = ops->probe_rhs(g.sel, n, din.p, dout.p, dcode.p, g.stream);
+    else e = ops->probe_check_save(g.sel, n, din.p, dout.p, dcode.p, g.stream);
+    CK(e);
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(code, dcode.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    din.release(); dout.release(); dcode.release();
+    return 0;
+}
+int rays_b200_probe_equilibrium(int64_t n, const double *rvec, double *out, int32_t *err) { return run_probe(0, n, rvec, 3, out, RAYS_EQ_OUT, err); }
+int rays_b200_probe_rhs(int64_t n, const double *v, double *dvds, int32_t *stop) {
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    return run_probe(1, n, v, (size_t)g.dc.c.nv, dvds, (size_t)g.dc.c.nv, stop);
+}
+int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_t *stop) {
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    return run_probe(2, n, v, (size_t)g.dc.c.nv, resid, 1, stop);
+}
+
+// ======================= measurement helpers =================================================================
+int rays_b200_fp64_peak(double *tflops, double *sm_mhz) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    CK(cudaSetDevice(g.device));
+    const int threads = 256, blocks = g.num_sms * 8, iters = 1 << 16;
+    DevBuf<double> out;
+    CK(out.reserve((size_t)threads * blocks));
+    fp64_peak_kernel<<<blocks, threads, 0, g.stream>>>(out.p, 1024, 1.0000001, 1e-9);   // warm-up
+    CK(cudaGetLastError());
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(g.ev0, g.stream));
+        fp64_peak_kernel<<<blocks, threads, 0, g.stream>>>(out.p, iters, 1.0000001, 1e-9);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(g.ev1, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    out.release();
+    if (tflops) *tflops = best;
+    if (sm_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+        *sm_mhz = khz / 1000.0;   // maximum SM clock; bench.py samples the clock under load with nvidia-smi
+    }
+    return 0;
+}
+
+// pinned host memory for result arrays (so the trajectory copy-out runs at full PCIe rate)
+int rays_b200_host_alloc(void **p, size_t bytes) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return 0;
+}
+int rays_b200_host_free(void *p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+}  // extern "C"
