@@ -323,6 +323,40 @@ void fill_flags(rays_results *res, const std::vector<int> &codes, long long firs
     for (size_t i = 0; i < codes.size(); ++i) rays_b200_stop_string(codes[i], res->ray_stop_flag + (size_t)(first + (long long)i) * RAYS_FLAG_LEN, RAYS_FLAG_LEN);
 }
 
+// D2H of trajectories in the reference layout, trimmed to the points actually written: rays are
+// taken in groups of 64, the copy width of a group is its longest ray rounded up to 32 points, and
+// neighbouring groups of equal width share one cudaMemcpy2DAsync.  (A fan whose longest ray hits
+// nstep_max would otherwise move every ray at full length.)
+int copy_trajectories(rays_results *res, const std::vector<int> &np, long long first, long long count, const double *tv, const double *tr,
+                      int npa, int nv, cudaStream_t st) {
+    const long long G = 64;
+    long long run0 = first;
+    int w0 = -1;
+    auto flush = [&](long long a, long long b, int w) -> cudaError_t {
+        if (b <= a || w <= 0) return cudaSuccess;
+        cudaError_t e = cudaSuccess;
+        if (res->ray_vec)
+            e = cudaMemcpy2DAsync(res->ray_vec + (size_t)a * res->npoints_alloc * nv, (size_t)res->npoints_alloc * nv * 8,
+                                  tv + (size_t)(a - first) * npa * nv, (size_t)npa * nv * 8, (size_t)w * nv * 8, (size_t)(b - a), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && res->residual)
+            e = cudaMemcpy2DAsync(res->residual + (size_t)a * res->npoints_alloc, (size_t)res->npoints_alloc * 8, tr + (size_t)(a - first) * npa,
+                                  (size_t)npa * 8, (size_t)w * 8, (size_t)(b - a), cudaMemcpyDeviceToHost, st);
+        return e;
+    };
+    for (long long gs = first; gs < first + count; gs += G) {
+        const long long ge = std::min(gs + G, first + count);
+        int m = 1;
+        for (long long i = gs; i < ge; ++i) m = std::max(m, np[(size_t)i]);
+        const int w = std::min(npa, (m + 31) / 32 * 32);
+        if (w != w0) {
+            CK(flush(run0, gs, w0));
+            run0 = gs; w0 = w;
+        }
+    }
+    CK(flush(run0, first + count, w0));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -588,15 +622,9 @@ int rays_b200_results_download(rays_results *res) {
     CK(cudaStreamSynchronize(g.stream));
     if (g.have_traj && n && (res->ray_vec || res->residual)) {
         if (res->npoints_alloc < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "npoints_alloc < 1");
-        int maxnp = 1;
-        for (long long i = 0; i < n; ++i) maxnp = std::max(maxnp, np[(size_t)i]);
-        if (maxnp > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
-        if (res->ray_vec)
-            CK(cudaMemcpy2DAsync(res->ray_vec, (size_t)res->npoints_alloc * nv * 8, g.ray_vec.p, (size_t)g.res_npa * nv * 8, (size_t)maxnp * nv * 8, (size_t)n,
-                                 cudaMemcpyDeviceToHost, g.stream));
-        if (res->residual)
-            CK(cudaMemcpy2DAsync(res->residual, (size_t)res->npoints_alloc * 8, g.residual.p, (size_t)g.res_npa * 8, (size_t)maxnp * 8, (size_t)n,
-                                 cudaMemcpyDeviceToHost, g.stream));
+        for (long long i = 0; i < n; ++i)
+            if (np[(size_t)i] > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
+        if ((rc = copy_trajectories(res, np, 0, n, g.ray_vec.p, g.residual.p, g.res_npa, nv, g.stream))) return rc;
         CK(cudaStreamSynchronize(g.stream));
     }
     fill_flags(res, codes, 0);
@@ -660,14 +688,7 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
         CK(cudaEventRecord(g.ev_batch[b], g.stream));
         if (want_traj) {
             CK(cudaEventSynchronize(g.ev_batch[b]));   // npoints of this batch are on the host: trim the copy
-            int maxnp = 1;
-            for (long long i = first; i < first + count; ++i) maxnp = std::max(maxnp, np[(size_t)i]);
-            if (res->ray_vec)
-                CK(cudaMemcpy2DAsync(res->ray_vec + (size_t)first * res->npoints_alloc * nv, (size_t)res->npoints_alloc * nv * 8, tv, (size_t)npa * nv * 8,
-                                     (size_t)maxnp * nv * 8, (size_t)count, cudaMemcpyDeviceToHost, g.copy_stream));
-            if (res->residual)
-                CK(cudaMemcpy2DAsync(res->residual + (size_t)first * res->npoints_alloc, (size_t)res->npoints_alloc * 8, tr, (size_t)npa * 8, (size_t)maxnp * 8,
-                                     (size_t)count, cudaMemcpyDeviceToHost, g.copy_stream));
+            if ((rc = copy_trajectories(res, np, first, count, tv, tr, npa, nv, g.copy_stream))) return rc;
             CK(cudaEventRecord(g.ev_copy[b], g.copy_stream));
         }
     }
