@@ -31,8 +31,8 @@ template <int EQ_, int NS_, int DERIV_, int DAMP_, int GRADS_> struct Traits {
 template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
     constexpr int NSM = NSpec<T::NS>::MAX;
     const rays_cfg &c = g_dc.c;
-    const double k0 = c.k0;
-    const double nvec[3] = {v[3] / k0, v[4] / k0, v[5] / k0};
+    const Rcp K0 = g_dc.rc_k0;
+    const double nvec[3] = {qdiv(v[3], K0), qdiv(v[4], K0), qdiv(v[5], K0)};
     Eq<NSM> e;
     equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
     if (e.err) return e.err;
@@ -45,20 +45,21 @@ template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
         if (pert_err) return pert_err;
     }
     if (dddw == 0.0) return RAYS_STOP_INFINITE_VG_RHS;
-    const double vg[3] = {-dddk[0] / dddw, -dddk[1] / dddw, -dddk[2] / dddw};
+    const Rcp W = rcp_of(dddw);
+    const double vg[3] = {qdiv(-dddk[0], W), qdiv(-dddk[1], W), qdiv(-dddk[2], W)};
     const double vg0 = sqrt(vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2]);
     double dsd;
     if (c.ray_param == RAYS_PARAM_ARCL) {
         if (dddk[0] != 0.0 || dddk[1] != 0.0 || dddk[2] != 0.0) {
             const double sg = copysign(1.0, dddw);
-            const double nrm = sqrt(dddk[0] * dddk[0] + dddk[1] * dddk[1] + dddk[2] * dddk[2]);
+            const Rcp nrm = rcp_of(sqrt(dddk[0] * dddk[0] + dddk[1] * dddk[1] + dddk[2] * dddk[2]));
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { dvds[i] = -sg * dddk[i] / nrm; dvds[3 + i] = sg * dddx[i] / nrm; }
+            for (int i = 0; i < 3; ++i) { dvds[i] = qdiv(-sg * dddk[i], nrm); dvds[3 + i] = qdiv(sg * dddx[i], nrm); }
             dsd = 1.0;
         } else return RAYS_STOP_RAY_STALLED;
     } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { dvds[i] = vg[i]; dvds[3 + i] = dddx[i] / dddw; }
+        for (int i = 0; i < 3; ++i) { dvds[i] = vg[i]; dvds[3 + i] = qdiv(dddx[i], W); }
         dsd = vg0;
     }
     dvds[6] = dsd;
@@ -75,7 +76,8 @@ template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
         }
     }
     if (T::grads()) {
-        const double u0 = vg[0] / vg0, u1 = vg[1] / vg0, u2 = vg[2] / vg0;
+        const Rcp V0 = rcp_of(vg0);
+        const double u0 = qdiv(vg[0], V0), u1 = qdiv(vg[1], V0), u2 = qdiv(vg[2], V0);
 #pragma unroll
         for (int j = 0; j < 3; ++j) dvds[nv0 + j] = dsd * u0 * e.g[0][j] + dsd * u1 * e.g[1][j] + dsd * u2 * e.g[2][j];
         dvds[nv0 + 3] = dsd * u0 * e.gradns[0][0] + dsd * u1 * e.gradns[1][0] + dsd * u2 * e.gradns[2][0];
@@ -92,7 +94,7 @@ template <class T> RD_INLINE void check_save(const double *v, double &resid, boo
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int ns = NSpec<T::NS>::n();
     const rays_cfg &c = g_dc.c;
-    const double k0 = c.k0;
+    const Rcp K0 = g_dc.rc_k0;
     Eq<NSM> e;
     equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
     if (e.err) {
@@ -104,7 +106,7 @@ template <class T> RD_INLINE void check_save(const double *v, double &resid, boo
     const double kv[3] = {v[3], v[4], v[5]};
     double k3, k1;
     kpar_kperp(kv, e.bunit, k3, k1);
-    const double nvec[3] = {kv[0] / k0, kv[1] / k0, kv[2] / k0};
+    const double nvec[3] = {qdiv(kv[0], K0), qdiv(kv[1], K0), qdiv(kv[2], K0)};
     resid = residual<NSM>(e, ns, k1, k3);
     if (resid > c.dispersion_resid_limit) { stop = true; flag = RAYS_STOP_DISP_RESIDUAL; }
     double dddx[3], dddk[3], dddw;
@@ -160,7 +162,7 @@ template <class T> RD_INLINE int RK4_ode(double *v, double &s, double sout) {
     }
     if (code) return code;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + ds * acc[i] / 6.0;
+    for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + qdiv(ds * acc[i], g_dc.rc_six);
     s = sout;
     return 0;
 }

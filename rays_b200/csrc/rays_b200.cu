@@ -482,6 +482,13 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     d.dn_omg_p2 = d.dn_omg_p * d.dn_omg_p;
     d.dn_omg_m2 = d.dn_omg_m * d.dn_omg_m;
     d.dn_omg_delta = c.omgrf * d.dn_delta;
+    auto mk = [](double v) { Rcp r; r.d = v; r.r = 1.0 / v; return r; };   // IEEE, correctly rounded
+    d.rc_k0 = mk(c.k0); d.rc_omgrf = mk(c.omgrf); d.rc_omgrf2 = mk(d.omgrf2); d.rc_clight = mk(c.clight); d.rc_six = mk(6.0);
+    for (int s = 0; s < RAYS_NSPECIES; ++s) { d.rc_ms[s] = mk(c.ms[s]); d.rc_eps0ms[s] = mk(d.eps0ms[s]); }
+    d.rc_rk = mk(d.sv_rk); d.rc_rk2 = mk(d.sv_rk2); d.rc_rmaj = mk(d.sv_rmaj); d.rc_rmaj2 = mk(d.sv_rmaj2); d.rc_psiB = mk(d.sv_psiB);
+    d.rc_Aphi_LUFS = mk(c.mirror.Aphi_LUFS);
+    d.rc_two_delta = mk(d.dn_two_delta); d.rc_omg_p = mk(d.dn_omg_p); d.rc_omg_m = mk(d.dn_omg_m); d.rc_omg_p2 = mk(d.dn_omg_p2);
+    d.rc_omg_m2 = mk(d.dn_omg_m2); d.rc_k0_p = mk(d.dn_k0_p); d.rc_k0_m = mk(d.dn_k0_m); d.rc_omg_delta = mk(d.dn_omg_delta);
     // kernel selection: the two-species specialisations cover electron + one ion without per-species damping slots
     g.sel.ray_deriv = c.ray_deriv;
     g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
