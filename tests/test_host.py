@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference's Fortran host: namelist reader, module initialisation, spline setup,
+netCDF-3 reader/writer, result file contract (no GPU needed)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import rays_b200 as rb
+from rays_b200 import _abi
+from _cases import init_case
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(built):
+    yield
+
+
+def test_constants_carry_single_precision_literals():
+    """pi, clight, e, me are float32 literals widened to double."""
+    cfg = init_case("slab_ECH_90GHz_case_1.in")
+    pi32 = float(np.float32(3.1415926535897932385))
+    clight = float(np.float32(2.997930e8))
+    assert cfg.clight == clight
+    assert cfg.omgrf == 2.0 * pi32 * 90.0e9
+    assert cfg.k0 == cfg.omgrf / clight
+    me, e = float(np.float32(9.1094e-31)), float(np.float32(1.6022e-19))
+    assert cfg.ms[0] == me and cfg.ms[1] == me * 3670.0 and cfg.qs[0] == -e
+    mu0 = pi32 * float(np.float32(4.e-7))
+    assert cfg.eps0 == 1.0 / (mu0 * (clight * clight))
+    assert cfg.total_damping_limit == 0.99            # namelist value parsed as a double
+
+
+def test_namelists_of_all_configs_parse():
+    nv = {"slab_ECH_90GHz_case_1.in": 7, "solovev_ECH_90GHz_plus_root.in": 12, "mpex/rays.in": 12, "solovev_fan_1M.in": 7,
+          "axisym_deposition_fan.in": 8}
+    for name, want in nv.items():
+        cfg = init_case(name)
+        assert cfg.nv == want and cfg.nspec == 1
+    cfg = init_case("mpex/rays.in")
+    m = cfg.mirror
+    assert (m.Br_spline.nx, m.Br_spline.ny) == (51, 201)
+    assert abs(m.r_LUFS - 0.12) < 1e-12 and abs(m.z_LUFS - 3.6) < 1e-12 and m.Aphi_LUFS != 0.0
+    assert cfg.ode_solver == _abi.ODE_RK4 and cfg.ds == 1e-12 and cfg.nstep_max == 500
+
+
+def test_unknown_namelist_variable_is_an_error(tmp_path):
+    txt = open(rb.config_path("slab_ECH_90GHz_case_1.in")).read().replace("frf=90.e9,", "frf=90.e9,\n  message_unit=11,")
+    p = tmp_path / "rays.in"
+    p.write_text(txt)
+    L = _abi.load()
+    assert L.rays_host_initialize(str(p).encode(), 0) != 0
+    assert b"message_unit" in L.rays_host_last_error().lower()
+
+
+def test_invalid_model_strings_fail_like_the_reference(tmp_path):
+    L = _abi.load()
+    for old, new in (("ode_solver_name='SG_ODE'", "ode_solver_name='EULER'"), ("equilib_model='slab'", "equilib_model='torus'"),
+                     ("dens_prof_model='linear'", "dens_prof_model='cubic'")):
+        txt = open(rb.config_path("slab_ECH_90GHz_case_1.in")).read()
+        assert old in txt
+        p = tmp_path / "bad.in"
+        p.write_text(txt.replace(old, new))
+        assert L.rays_host_initialize(str(p).encode(), 0) != 0
+
+
+def test_cubic_and_bicubic_spline_setup_interpolate():
+    """cspline / bcspline (not-a-knot): reproduce smooth functions to the accuracy test_pspline.f90 reports."""
+    L = _abi.load()
+    nx = 101
+    x = np.linspace(0.0, 2.0, nx)
+    f = np.zeros((nx, 4))
+    f[:, 0] = 1.0 + np.cos(10.0 * x)
+    assert L.rays_host_cspline(x.ctypes.data_as(_abi.c_double_p), nx, f.ctypes.data_as(_abi.c_double_p)) == 0
+    import _oracle as orc
+    s = _abi.Spline1D()
+    s.nx, s.x_grid, s.fspl = nx, x.ctypes.data_as(_abi.c_double_p), f.ctypes.data_as(_abi.c_double_p)
+    xs = np.linspace(0.0, 2.0, 1777)
+    fo, fpo = np.zeros_like(xs), np.zeros_like(xs)
+    orc.load().oracle_cspeval(C.byref(s), len(xs), xs.ctypes.data_as(_abi.c_double_p), fo.ctypes.data_as(_abi.c_double_p),
+                              fpo.ctypes.data_as(_abi.c_double_p))
+    assert np.max(np.abs(fo - (1.0 + np.cos(10.0 * xs)))) < 1e-4
+    assert np.max(np.abs(fpo + 10.0 * np.sin(10.0 * xs))) < 5e-2
+    # 2-D
+    nx, ny = 41, 61
+    xg, yg = np.linspace(0.1, 1.0, nx), np.linspace(-1.0, 1.0, ny)
+    F = np.zeros((ny, nx, 4, 4))
+    F[:, :, 0, 0] = np.sqrt(xg[None, :] ** 2 + yg[:, None] ** 2)
+    assert L.rays_host_bcspline(xg.ctypes.data_as(_abi.c_double_p), nx, yg.ctypes.data_as(_abi.c_double_p), ny,
+                                F.ctypes.data_as(_abi.c_double_p)) == 0
+    s2 = _abi.Spline2D()
+    s2.nx, s2.ny = nx, ny
+    s2.x_grid, s2.y_grid, s2.fspl = xg.ctypes.data_as(_abi.c_double_p), yg.ctypes.data_as(_abi.c_double_p), F.ctypes.data_as(_abi.c_double_p)
+    rng = np.random.default_rng(3)
+    px, py = rng.uniform(0.1, 1.0, 500), rng.uniform(-1, 1, 500)
+    f, fx, fy = np.zeros(500), np.zeros(500), np.zeros(500)
+    orc.load().oracle_bcspeval(C.byref(s2), 500, px.ctypes.data_as(_abi.c_double_p), py.ctypes.data_as(_abi.c_double_p),
+                               f.ctypes.data_as(_abi.c_double_p), fx.ctypes.data_as(_abi.c_double_p), fy.ctypes.data_as(_abi.c_double_p))
+    rr = np.sqrt(px ** 2 + py ** 2)
+    assert np.max(np.abs(f - rr)) < 2e-5 and np.max(np.abs(fx - px / rr)) < 2e-3 and np.max(np.abs(fy - py / rr)) < 2e-3
+
+
+def test_run_results_netcdf_contract(tmp_path):
+    """finalize_run writes run_results.<label>.nc with the reference's dims/vars/types
+    (ray_results_m.f90:171-249); scipy's classic-netCDF reader stands in for post_process_RAYS."""
+    import _oracle as orc
+    from _cases import oracle_fan
+    from scipy.io import netcdf_file
+    cfg = init_case("slab_ECH_90GHz_case_1.in")
+    r, n, w, _, _ = oracle_fan(cfg)
+    rb.set_fan(r, n, w)
+    # fill the host's ray_results_m arrays with an oracle trace (no GPU here), then write the file
+    res = _abi.Results()
+    L = _abi.load()
+    assert L.rays_host_results(C.byref(res)) == 0
+    fan, keep = rb.make_fan(r, n, w)
+    st = orc.load().oracle_trace(C.byref(cfg), C.byref(fan), C.byref(res), 0, None)
+    assert st == 0
+    rb.finalize_run(str(tmp_path))
+    f = netcdf_file(str(tmp_path / "run_results.run_1.nc"), "r", mmap=False)
+    assert f.dimensions["number_of_rays"] == 3 and f.dimensions["dim_v_vector"] == 7 and f.dimensions["max_number_of_points"] == 501
+    assert f.RAYS_run_label.decode().strip() == "run_1"
+    rv = f.variables["ray_vec"]
+    assert rv.shape == (3, 501, 7) and rv.data.dtype == np.dtype(">f8")
+    npnt = f.variables["npoints"].data
+    assert list(npnt) == [501, 501, 501]
+    got = np.array(rv.data)
+    want = np.ctypeslib.as_array(res.ray_vec, (3, 501, 7))
+    assert np.array_equal(got, want)
+    assert f.variables["residual"].shape == (3, 501)
+    assert f.variables["initial_ray_power"].data.dtype == np.dtype(">f4")
+    flag = b"".join(f.variables["ray_stop_flag"].data[0]).decode()
+    assert flag == " nstep > nstep_max".ljust(60)
+    assert f.variables["date_vector"].shape == (8,)
+    f.close()
+
+
+def test_mpex_field_file_reader_matches_scipy():
+    from scipy.io import netcdf_file
+    cfg = init_case("mpex/rays.in")
+    f = netcdf_file(rb.config_path("mpex/Brz_fields.MPEX_9_filaments_D3-6_ECH_2nd_harm.nc"), "r", mmap=False)
+    Br = np.array(f.variables["Br"].data, dtype=np.float64)        # (n_z, n_r)
+    nx, ny = cfg.mirror.Br_spline.nx, cfg.mirror.Br_spline.ny
+    fs = np.ctypeslib.as_array(cfg.mirror.Br_spline.fspl, (ny, nx, 4, 4))
+    assert np.array_equal(fs[:, :, 0, 0], Br)                       # spline knots carry the file's data
+    rg = np.ctypeslib.as_array(cfg.mirror.Br_spline.x_grid, (nx,))
+    assert np.allclose(rg, np.array(f.variables["r_grid"].data))
+    f.close()
