@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -15
+timeout 900 python bench.py --steps 2 --warmup 1 --no-e2e 2>&1 | tail -3

@@ -27,23 +27,26 @@ template <int EQ_, int NS_, int DERIV_, int DAMP_, int GRADS_> struct Traits {
     RD_INLINE static int nv() { return GENERIC ? g_dc.c.nv : NV; }
 };
 
-// ---- eqn_ray (eqn_ray.f90:1-236): returns 0 or the stop code ------------------------------------------
-template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
+// ---- eqn_ray (eqn_ray.f90:1-236), in three pieces so that the fused RK4 kernel can share one equilibrium
+// evaluation between check_save and the first stage: derivatives of D, then the ray equations.
+template <class T>
+RD_INLINE int ray_derivs(const Eq<NSpec<T::NS>::MAX> &e, const double *v, double dddx[3], double dddk[3], double &dddw) {
+    if (T::DERIV == RAYS_DERIV_COLD) {
+        const Rcp K0 = g_dc.rc_k0;
+        const double nvec[3] = {qdiv(v[3], K0), qdiv(v[4], K0), qdiv(v[5], K0)};
+        deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);
+        return 0;
+    }
+    int pert_err;
+    const double r0[3] = {v[0], v[1], v[2]}, kv[3] = {v[3], v[4], v[5]};
+    deriv_num<T::EQ, T::NS>(e, r0, kv, dddx, dddk, dddw, pert_err);
+    return pert_err;
+}
+// eqn_ray.f90:126-229: group velocity, dr/ds, dk/ds, arc length, damping and gradient diagnostics
+template <class T>
+RD_INLINE int ray_equations(const Eq<NSpec<T::NS>::MAX> &e, const double *v, const double dddx[3], const double dddk[3], double dddw, double *dvds) {
     constexpr int NSM = NSpec<T::NS>::MAX;
     const rays_cfg &c = g_dc.c;
-    const Rcp K0 = g_dc.rc_k0;
-    const double nvec[3] = {qdiv(v[3], K0), qdiv(v[4], K0), qdiv(v[5], K0)};
-    Eq<NSM> e;
-    equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
-    if (e.err) return e.err;
-    double dddx[3], dddk[3], dddw;
-    if (T::DERIV == RAYS_DERIV_COLD) deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);
-    else {
-        int pert_err;
-        const double r0[3] = {v[0], v[1], v[2]}, kv[3] = {v[3], v[4], v[5]};
-        deriv_num<T::EQ, T::NS>(e, r0, kv, dddx, dddk, dddw, pert_err);
-        if (pert_err) return pert_err;
-    }
     if (dddw == 0.0) return RAYS_STOP_INFINITE_VG_RHS;
     const Rcp W = rcp_of(dddw);
     const double vg[3] = {qdiv(-dddk[0], W), qdiv(-dddk[1], W), qdiv(-dddk[2], W)};
@@ -85,14 +88,40 @@ template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
     }
     return 0;
 }
+// eqn_ray: returns 0 or the stop code
+template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    Eq<NSM> e;
+    equilibrium<T::EQ, T::NS, true>(v[0], v[1], v[2], e);
+    if (e.err) return e.err;
+    double dddx[3], dddk[3], dddw;
+    const int pert_err = ray_derivs<T>(e, v, dddx, dddk, dddw);
+    if (pert_err) return pert_err;
+    return ray_equations<T>(e, v, dddx, dddk, dddw, dvds);
+}
 // out-of-line copy for the Shampine-Gordon stepper, which evaluates the RHS from three places
 template <class T> RD_NOINLINE int eqn_ray_call(const double *v, double *dvds) { return eqn_ray<T>(v, dvds); }
 
 // ---- check_save (check_save.f90:1-161): residual + stop tests at a saved point -------------------------
-// flag/stop follow ode_stop semantics: a flag may be set without stopping (equilibrium error, A.5 (X))
-template <class T> RD_INLINE void check_save(const double *v, double &resid, bool &stop, int &flag) {
+// flag/stop follow ode_stop semantics: a flag may be set without stopping (equilibrium error, A.5 (X)).
+// check_save_tests works on an equilibrium that is already evaluated; dddw_cold is dD/d(omega) of
+// deriv_cold at the point (check_save always differentiates with deriv_cold, check_save.f90:79-87).
+template <class T>
+RD_INLINE void check_save_resid(const Eq<NSpec<T::NS>::MAX> &e, const double *v, double &resid, bool &stop, int &flag) {
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int ns = NSpec<T::NS>::n();
+    const double kv[3] = {v[3], v[4], v[5]};
+    double k3, k1;
+    kpar_kperp(kv, e.bunit, k3, k1);
+    resid = residual<NSM>(e, ns, k1, k3);
+    if (resid > g_dc.c.dispersion_resid_limit) { stop = true; flag = RAYS_STOP_DISP_RESIDUAL; }
+}
+template <class T> RD_INLINE void check_save_tail(const double *v, double dddw_cold, bool &stop, int &flag) {
+    if (!(fabs(dddw_cold) > DBL_MIN)) { stop = true; flag = RAYS_STOP_INFINITE_VG_CHECK; }
+    if (T::damp() && v[7] > g_dc.c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+}
+template <class T> RD_INLINE void check_save(const double *v, double &resid, bool &stop, int &flag) {
+    constexpr int NSM = NSpec<T::NS>::MAX;
     const rays_cfg &c = g_dc.c;
     const Rcp K0 = g_dc.rc_k0;
     Eq<NSM> e;
@@ -103,16 +132,11 @@ template <class T> RD_INLINE void check_save(const double *v, double &resid, boo
         if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
         return;
     }
-    const double kv[3] = {v[3], v[4], v[5]};
-    double k3, k1;
-    kpar_kperp(kv, e.bunit, k3, k1);
-    const double nvec[3] = {qdiv(kv[0], K0), qdiv(kv[1], K0), qdiv(kv[2], K0)};
-    resid = residual<NSM>(e, ns, k1, k3);
-    if (resid > c.dispersion_resid_limit) { stop = true; flag = RAYS_STOP_DISP_RESIDUAL; }
+    check_save_resid<T>(e, v, resid, stop, flag);
+    const double nvec[3] = {qdiv(v[3], K0), qdiv(v[4], K0), qdiv(v[5], K0)};
     double dddx[3], dddk[3], dddw;
-    deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);   // always cold (check_save.f90:79-87)
-    if (!(fabs(dddw) > DBL_MIN)) { stop = true; flag = RAYS_STOP_INFINITE_VG_CHECK; }
-    if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+    deriv_cold<T::NS>(e, nvec, dddx, dddk, dddw);
+    check_save_tail<T>(v, dddw, stop, flag);
 }
 
 // ---- initialize_ode_vector (initialize_ode_vector.f90:1-57) ---------------------------------------------
@@ -680,6 +704,178 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
         }
     }
     // ---- per-warp totals -> global counters
+    unsigned long long st = my_steps, rh = my_rhs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
+    if (lane == 0) { atomicAdd(a.counters, st); atomicAdd(a.counters + 1, rh); }
+}
+
+// ---- fused RK4 trace kernel ---------------------------------------------------------------------------------
+// One loop iteration = one ray-step of every active lane.  check_save of the point a step produced is
+// deferred to the top of the next iteration, where the point is also the first RK4 stage: the two share one
+// equilibrium evaluation (and, for ray_deriv_name='cold', one deriv_cold), which is bit-identical to the
+// reference's two evaluations at the same point.  The four stages run through ONE copy of the equilibrium /
+// derivative code (a real loop), which keeps the hot loop inside the instruction cache: the straight-line
+// version was fetch-bound (ncu: 4.5 issue slots lost to "no instruction" per issued instruction).
+// Sequence per iteration, in the reference's order (ray_tracing.f90:116-245):
+//   check_save(v) -> [stop: point not saved] -> save point, nstep++ -> s = sout, sout += ds -> s_max / nstep_max
+//   tests -> RK4 stages -> v advanced (or ray stopped by the RHS with v untouched).
+template <class T>
+__global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs a) {
+    constexpr int NV = T::NV;
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    const int nv = T::nv();
+    const rays_cfg &c = g_dc.c;
+    const unsigned lane = threadIdx.x & 31;
+    double v[NV];
+    double s = 0.0, sout = 0.0;
+    double resid_prev = 0.0, resid_last = 0.0, resid_max = 0.0;
+    double dep_x = 0.0, dep_Q = 0.0, pwr = 0.0;
+    long long iray = -1;
+    int nstep = 0, flag = 0;
+    bool active = false, exhausted = false, first = false;
+    unsigned long long my_steps = 0;
+    unsigned my_rhs = 0;
+    const bool binning = a.dep_bins != nullptr && T::damp();
+
+    for (;;) {
+        // ---- refill from the work queue (one atomic per warp)
+        const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+        if (want) {
+            unsigned long long base = 0;
+            const int leader = __ffs(want) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!active && !exhausted) {
+                const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+                if (idx >= a.nray) exhausted = true;
+                else {
+                    iray = idx;
+                    nstep = 0; s = 0.0; sout = 0.0; flag = 0;
+                    resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
+                    initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                    pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
+                    if (a.ray_vec) {
+                        double *dst = a.ray_vec + (size_t)iray * a.npoints_alloc * nv;
+                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                    }
+                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc] = 0.0;
+                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                    active = true; first = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            continue;
+        }
+        if (active) {
+            const double ds = c.ds;    // RK4_ode: ds = sout - s with sout = s + ds formed below; see note (*)
+            double w[NV], acc[NV], f[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { w[i] = v[i]; acc[i] = 0.0; f[i] = 0.0; }
+            int code = 0;          // RHS stop code (ray ends, v untouched)
+            bool stop = false;     // stop raised by check_save or the loop-top tests
+            bool did_not_start = false;
+            double h = 0.0;        // sout - s of this step
+#pragma unroll 1
+            for (int stage = 0; stage < 4; ++stage) {
+                Eq<NSM> e;
+                equilibrium<T::EQ, T::NS, true>(w[0], w[1], w[2], e);
+                double dddx[3], dddk[3], dddw = 0.0;
+                bool have_derivs = false;
+                if (stage == 0) {
+                    // ---- check_save(v) (check_save.f90:1-161)
+                    double resid = 0.0;
+                    if (e.err) {
+                        flag = e.err;
+                        if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+                    } else {
+                        check_save_resid<T>(e, v, resid, stop, flag);
+                        double dddw_cold;
+                        if (T::DERIV == RAYS_DERIV_COLD) {
+                            ray_derivs<T>(e, v, dddx, dddk, dddw);     // shared with the first stage below
+                            have_derivs = true;
+                            dddw_cold = dddw;
+                        } else {
+                            const Rcp K0 = g_dc.rc_k0;
+                            const double nvec[3] = {qdiv(v[3], K0), qdiv(v[4], K0), qdiv(v[5], K0)};
+                            double tx[3], tk[3];
+                            deriv_cold<T::NS>(e, nvec, tx, tk, dddw_cold);
+                        }
+                        check_save_tail<T>(v, dddw_cold, stop, flag);
+                    }
+                    if (stop) { did_not_start = first; break; }
+                    if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
+                        nstep = nstep + 1;
+                        if (a.ray_vec) {
+                            double *dst = a.ray_vec + ((size_t)iray * a.npoints_alloc + nstep) * nv;
+                            if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                        }
+                        if (a.residual) a.residual[(size_t)iray * a.npoints_alloc + nstep] = resid;
+                        resid_prev = resid_last;
+                        resid_last = resid;
+                        if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
+                        if (binning) {
+                            const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
+                            bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
+                            dep_x = xn; dep_Q = Qn;
+                        }
+                        ++my_steps;
+                    } else if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
+                    first = false;
+                    // ---- top of the trajectory loop (ray_tracing.f90:118-172)
+                    s = sout;
+                    sout = sout + ds;
+                    if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; break; }
+                    if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; break; }
+                    h = sout - s;   // RK4_ode_m.f90:74
+                }
+                // ---- eqn_ray at w (eqn_ray.f90:87-229)
+                if (e.err) { code = e.err; break; }
+                if (!have_derivs) {
+                    code = ray_derivs<T>(e, w, dddx, dddk, dddw);
+                    if (code) break;
+                }
+                code = ray_equations<T>(e, w, dddx, dddk, dddw, f);
+                if (code) break;
+                const double ca = (stage == 1 || stage == 2) ? 2.0 : 1.0;
+                const double cw = stage == 2 ? 1.0 : 0.5;
+#pragma unroll
+                for (int i = 0; i < NV; ++i)
+                    if (i < nv) {
+                        acc[i] = stage == 0 ? f[i] : acc[i] + ca * f[i];
+                        w[i] = v[i] + h * f[i] * cw;
+                    }
+                my_rhs += 1;
+            }
+            if (!stop && code == 0) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + qdiv(h * acc[i], g_dc.rc_six);
+                s = sout;
+            } else {
+                if (code) flag = code;
+                a.stop_code[iray] = flag;
+                if (did_not_start) {   // only npoints, flag and the first point are set (ray_tracing.f90:101-112)
+                    a.npoints[iray] = 1;
+                    if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
+                    if (a.end_residuals) a.end_residuals[iray] = 0.0;
+                    if (a.max_residuals) a.max_residuals[iray] = 0.0;
+                    if (a.end_ray_parameter) a.end_ray_parameter[iray] = 0.0;
+                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = 0.0;
+                    if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = 0.0;
+                } else {               // summary block (ray_tracing.f90:252-260)
+                    a.npoints[iray] = nstep + 1;
+                    if (a.initial_ray_power) a.initial_ray_power[iray] = pwr;
+                    if (a.end_residuals) a.end_residuals[iray] = nstep >= 1 ? resid_prev : 0.0;
+                    if (a.max_residuals) a.max_residuals[iray] = nstep >= 1 ? resid_max : -DBL_MAX;
+                    if (a.end_ray_parameter) a.end_ray_parameter[iray] = v[6];
+                    if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
+                }
+                active = false;
+            }
+        }
+    }
     unsigned long long st = my_steps, rh = my_rhs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }

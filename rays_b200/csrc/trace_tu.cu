@@ -21,11 +21,19 @@ cudaError_t tu_upload(const DevCfg *dc, cudaStream_t st) {
 template <class T> cudaError_t launch_trace(const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, const char *nm) {
     if (name) *name = nm;
     if (bps) {
+#if RAYS_TU_ODE == 1
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
+#else
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_kernel<T, kODE>, kTraceBlock, 0);
+#endif
         if (e != cudaSuccess) return e;
     }
     if (grid <= 0) return cudaSuccess;
+#if RAYS_TU_ODE == 1
+    trace_rk4_kernel<T><<<grid, kTraceBlock, 0, st>>>(a);
+#else
     trace_kernel<T, kODE><<<grid, kTraceBlock, 0, st>>>(a);
+#endif
     return cudaGetLastError();
 }
 
