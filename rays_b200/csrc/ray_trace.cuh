@@ -513,6 +513,12 @@ struct TraceArgs {
     double *ray_vec;                // [nray][npoints_alloc][nv] or NULL (no trajectory storage)
     double *residual;               // [nray][npoints_alloc] or NULL
     int npoints_alloc;
+    // streaming copy-out: when host_ray_vec/host_residual are set (device-accessible pinned host memory in
+    // the reference layout, row pitch host_npoints_alloc), ray_vec/residual are per-LANE staging rows
+    // ([grid*block][npoints_alloc][nv]) and the warp copies each finished ray to the host as it ends
+    double *host_ray_vec, *host_residual;
+    int host_npoints_alloc;
+    long long host_ray0;            // index of this launch's first ray in the host arrays
     int *npoints;                   // [nray]
     int *stop_code;                 // [nray]
     double *initial_ray_power, *end_residuals, *max_residuals, *end_ray_parameter;  // [nray]
@@ -591,6 +597,33 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 
 constexpr int kTraceBlock = 128;
 
+// Warp-cooperative copy-out of the rays that ended in this iteration: every lane of the warp moves a
+// slice of each finished ray's staged trajectory (HBM/L2) to the caller's arrays in pinned host memory,
+// 256-byte coalesced stores over PCIe, overlapped with the integration of the other rays.
+RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long iray, int npts, size_t row, int nv, unsigned lane) {
+    unsigned m = __ballot_sync(0xffffffffu, finished);
+    if (m == 0u || a.host_ray_vec == nullptr && a.host_residual == nullptr) return;
+    __syncwarp();   // orders the finished lanes' trajectory stores before the other lanes' loads
+    while (m) {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        const long long ir = __shfl_sync(0xffffffffu, iray, l);
+        const int np = __shfl_sync(0xffffffffu, npts, l);
+        const unsigned long long rw = __shfl_sync(0xffffffffu, (unsigned long long)row, l);
+        if (a.host_ray_vec) {
+            const double *src = a.ray_vec + (size_t)rw * a.npoints_alloc * nv;
+            double *dst = a.host_ray_vec + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc * nv;
+            const int n = np * nv;
+            for (int i = (int)lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+        }
+        if (a.host_residual) {
+            const double *src = a.residual + (size_t)rw * a.npoints_alloc;
+            double *dst = a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc;
+            for (int i = (int)lane; i < np; i += 32) dst[i] = __ldcg(src + i);
+        }
+    }
+}
+
 template <class T, int ODE_>
 __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
@@ -608,6 +641,11 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
     const bool binning = a.dep_bins != nullptr && T::damp();
+    const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t row = 0;
+    bool fin = false;      // this lane's ray ended in the current iteration
+    int fin_np = 0;
 
     for (;;) {
         // ---- refill: lanes without a ray take the next indices from the queue (one atomic per warp)
@@ -622,21 +660,23 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                 if (idx >= a.nray) exhausted = true;
                 else {
                     iray = idx;
+                    row = streaming ? slot : (size_t)iray;
                     nstep = 0; s = 0.0; sout = 0.0; flag = 0;
                     rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_ode_solver (SG_ode_m.f90:73-85)
                     resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
                     initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
                     pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
                     if (a.ray_vec) {
-                        double *dst = a.ray_vec + (size_t)iray * a.npoints_alloc * nv;
+                        double *dst = a.ray_vec + row * a.npoints_alloc * nv;
                         if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                     }
-                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc] = 0.0;
+                    if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
                     if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
                     double resid = 0.0;
                     bool stop = false;
                     check_save<T>(v, resid, stop, flag);
                     if (stop) {   // "did not start": only npoints, flag and the first point are set (:101-112)
+                        fin = true; fin_np = 1;
                         a.npoints[iray] = 1;
                         a.stop_code[iray] = flag;
                         if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
@@ -652,6 +692,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                 }
             }
         }
+        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }   // "did not start" rays
         if (__ballot_sync(0xffffffffu, active) == 0u) {
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
@@ -676,10 +717,10 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                 if (!stop) {
                     nstep = nstep + 1;
                     if (a.ray_vec) {
-                        double *dst = a.ray_vec + ((size_t)iray * a.npoints_alloc + nstep) * nv;
+                        double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
                         if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                     }
-                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc + nstep] = resid;
+                    if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
                     resid_prev = resid_last;
                     resid_last = resid;
                     if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
@@ -700,8 +741,10 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                 if (a.end_ray_parameter) a.end_ray_parameter[iray] = v[6];
                 if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
                 active = false;
+                fin = true; fin_np = nstep + 1;
             }
         }
+        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }
     }
     // ---- per-warp totals -> global counters
     unsigned long long st = my_steps, rh = my_rhs;
@@ -737,6 +780,11 @@ __global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs 
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
     const bool binning = a.dep_bins != nullptr && T::damp();
+    const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
+    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t row = 0;
+    bool fin = false;      // this lane's ray ended in the current iteration
+    int fin_np = 0;
 
     for (;;) {
         // ---- refill from the work queue (one atomic per warp)
@@ -751,15 +799,16 @@ __global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs 
                 if (idx >= a.nray) exhausted = true;
                 else {
                     iray = idx;
+                    row = streaming ? slot : (size_t)iray;
                     nstep = 0; s = 0.0; sout = 0.0; flag = 0;
                     resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
                     initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
                     pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
                     if (a.ray_vec) {
-                        double *dst = a.ray_vec + (size_t)iray * a.npoints_alloc * nv;
+                        double *dst = a.ray_vec + row * a.npoints_alloc * nv;
                         if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                     }
-                    if (a.residual) a.residual[(size_t)iray * a.npoints_alloc] = 0.0;
+                    if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
                     if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
                     active = true; first = true;
                 }
@@ -809,10 +858,10 @@ __global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs 
                     if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
                         nstep = nstep + 1;
                         if (a.ray_vec) {
-                            double *dst = a.ray_vec + ((size_t)iray * a.npoints_alloc + nstep) * nv;
+                            double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
                             if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                         }
-                        if (a.residual) a.residual[(size_t)iray * a.npoints_alloc + nstep] = resid;
+                        if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
                         resid_prev = resid_last;
                         resid_last = resid;
                         if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
@@ -873,8 +922,10 @@ __global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs 
                     if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
                 }
                 active = false;
+                fin = true; fin_np = did_not_start ? 1 : nstep + 1;
             }
         }
+        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }
     }
     unsigned long long st = my_steps, rh = my_rhs;
 #pragma unroll

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -255,7 +256,9 @@ int ensure_results(long long nray, int nv, int npa, bool traj) {
 
 // launch the trace kernel over rays [first, first+count) of the device fan into result slots [first..)
 // trajectories go to traj_base (indexed from 0 for ray `first`) when non-null
-int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned) {
+struct HostOut { double *ray_vec = nullptr, *residual = nullptr; int npa = 0; };   // device-accessible pinned host arrays
+
+int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned, const HostOut *host = nullptr) {
     const rays_cfg &c = g.dc.c;
     const TuOps *ops = tu_ops(c.equilib_model, c.ode_solver);
     if (!ops) return set_err(RAYS_ERR_INVALID_CONFIG, "no kernel for this equilibrium/ode pair");
@@ -285,6 +288,13 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     if (bps < 1) bps = 1;
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;
     int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
+    if (host) {   // streaming copy-out: per-lane staging rows, finished rays go straight to the caller's arrays
+        const size_t lanes = (size_t)grid * kTraceBlock;
+        if (host->ray_vec) { CK(g.ray_vec.reserve(lanes * g.res_npa * g.res_nv)); a.ray_vec = g.ray_vec.p; a.host_ray_vec = host->ray_vec; }
+        if (host->residual) { CK(g.residual.reserve(lanes * g.res_npa)); a.residual = g.residual.p; a.host_residual = host->residual; }
+        a.host_npoints_alloc = host->npa;
+        a.host_ray0 = first;
+    }
     CK(cudaMemsetAsync(g.queue.p, 0, sizeof(unsigned long long), g.stream));
     CK(ops->trace(g.sel, a, grid, g.stream, nullptr, nullptr));
     g.last_kernel = name; g.last_grid = grid; g.last_bps = bps;
@@ -320,7 +330,12 @@ int copy_small_results(rays_results *res, long long first, long long count) {
 
 void fill_flags(rays_results *res, const std::vector<int> &codes, long long first) {
     if (!res->ray_stop_flag) return;
-    for (size_t i = 0; i < codes.size(); ++i) rays_b200_stop_string(codes[i], res->ray_stop_flag + (size_t)(first + (long long)i) * RAYS_FLAG_LEN, RAYS_FLAG_LEN);
+    char table[RAYS_STOP_CODE_MAX][RAYS_FLAG_LEN];
+    for (int c = 0; c < RAYS_STOP_CODE_MAX; ++c) rays_b200_stop_string(c, table[c], RAYS_FLAG_LEN);
+    for (size_t i = 0; i < codes.size(); ++i) {
+        const int c = (codes[i] >= 0 && codes[i] < RAYS_STOP_CODE_MAX) ? codes[i] : 0;
+        std::memcpy(res->ray_stop_flag + (size_t)(first + (long long)i) * RAYS_FLAG_LEN, table[c], RAYS_FLAG_LEN);
+    }
 }
 
 // D2H of trajectories in the reference layout, trimmed to the points actually written: rays are
@@ -641,6 +656,27 @@ int rays_b200_results_download(rays_results *res) {
     return 0;
 }
 
+// Is [p, p+bytes) page-locked host memory the device can address?  Arrays from rays_b200_host_alloc (or
+// registered by the caller) are used as they are; small pageable arrays (<= 1 GiB) are registered for the
+// duration of the call; larger pageable arrays take the batched fallback, which only touches the pages
+// that receive data.
+static double *device_view_of_host(double *p, size_t bytes, std::vector<void *> &temp_registered) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeUnregistered) {
+        const char *env = getenv("RAYS_B200_REGISTER_HOST");
+        if ((env && env[0] == '0') || bytes > (size_t(1) << 30)) return nullptr;
+        if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        temp_registered.push_back((void *)p);
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    cudaPointerAttributes at2{};   // the whole range must be page-locked
+    if (cudaPointerGetAttributes(&at2, (char *)p + bytes - 1) != cudaSuccess || at2.type != cudaMemoryTypeHost) { cudaGetLastError(); return nullptr; }
+    return (double *)at.devicePointer;
+}
+
 // trace_rays with HOST buffers (ray_tracing.f90:1-290): H2D of the fan, trace in batches sized to HBM with
 // two trajectory buffers so that the copy-out of batch b overlaps the integration of batch b+1, results
 // land in the caller's arrays in the reference layout.
@@ -660,7 +696,41 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
     if ((rc = rays_b200_fan_upload(fan))) return rc;
     const long long n = g.nray;
     const int nv = c.nv;
-    // batch size: two trajectory buffers within ~70% of free HBM
+    // Preferred path: the result arrays are (or can be made) page-locked: finished rays are copied out by
+    // the trace kernel itself, overlapped with the integration; HBM holds only one staging row per lane.
+    HostOut hv;
+    bool streaming = false;
+    std::vector<void *> temp_registered;
+    struct Unreg { std::vector<void *> &v; ~Unreg() { for (void *q : v) cudaHostUnregister(q); } } unreg{temp_registered};
+    if (want_traj && n > 0) {
+        hv.npa = res->npoints_alloc;
+        hv.ray_vec = device_view_of_host(res->ray_vec, (size_t)res->nray * res->npoints_alloc * nv * 8, temp_registered);
+        hv.residual = device_view_of_host(res->residual, (size_t)res->nray * res->npoints_alloc * 8, temp_registered);
+        streaming = (res->ray_vec == nullptr || hv.ray_vec) && (res->residual == nullptr || hv.residual);
+    }
+    if (streaming) {
+        if ((rc = ensure_results(n, nv, npa, false))) return rc;
+        g.have_traj = false;
+        g.last_launches = 0;
+        CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
+        if ((rc = launch_trace(0, n, nullptr, nullptr, false, &hv))) return rc;
+        std::vector<int> codes((size_t)n);
+        CK(cudaMemcpyAsync(codes.data(), g.stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        if ((rc = copy_small_results(res, 0, n))) return rc;
+        CK(cudaEventRecord(g.ev1, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        g.last_ms = ms;
+        if ((rc = fetch_counters())) return rc;
+        fill_flags(res, codes, 0);
+        res->total_trace_time = g.last_ms * 1e-3;
+        res->total_ray_steps = g.last_steps;
+        if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = res->total_trace_time / (double)n;
+        g.dep_fused = false;
+        return 0;
+    }
+    // Fallback (pageable arrays that cannot be registered): batches sized to HBM, two trajectory buffers
     long long batch = std::max<long long>(n, 1);
     if (want_traj && n > 0) {
         size_t free_b = 0, total_b = 0;
