@@ -1,0 +1,261 @@
+! rays_b200_m.f90 -- ISO_C_BINDING face of librays_b200.so (include/rays_b200.h) and the drop-in
+! replacement of   subroutine trace_rays   (RAYS_project/RAYS_lib/ray_tracing.f90:1-290).
+!
+! SOURCE ONLY: this image has no Fortran compiler, so this file has never been compiled here.  It is the
+! binding a RAYS maintainer adds to RAYS_lib (see INTEGRATION.md): remove ray_tracing.f90 from
+! RAYS_lib/CMakeLists.txt, add this file, link librays_b200.so.  Everything else of the host program --
+! namelist input, the ray_init_m launchers, module selection, write_results_NC, post_process_RAYS -- is
+! unchanged: trace_rays still has no arguments and still fills the ray_results_m module arrays.
+!
+! The derived types below are bind(C) mirrors of the structs in include/rays_b200.h; field order and
+! kinds must not be changed (rays_b200_struct_sizes lets the host verify the layout at start-up).
+
+module rays_b200_m
+
+    use, intrinsic :: iso_c_binding
+    implicit none
+
+    integer, parameter :: RAYS_NSPECIES = 6, RAYS_FLAG_LEN = 60
+
+    type, bind(C) :: rays_spline1d
+        integer(c_int32_t) :: nx, pad_
+        type(c_ptr) :: x_grid, fspl
+    end type
+    type, bind(C) :: rays_spline2d
+        integer(c_int32_t) :: nx, ny
+        type(c_ptr) :: x_grid, y_grid, fspl
+    end type
+    type, bind(C) :: rays_slab_eq
+        real(c_double) :: xmin, xmax, ymin, ymax, zmin, zmax, rmaj, rmin, x0
+        integer(c_int32_t) :: bx_prof_model, by_prof_model, bz_prof_model, dens_prof_model
+        real(c_double) :: bx0, by0, bz0, LBy_shear_scale, LBz_scale, dBzdx, Ln_scale, dndx, alphan1, alphan2, n_min
+        integer(c_int32_t) :: t_prof_model(RAYS_NSPECIES)
+        real(c_double) :: LT_scale, dtdx, alphat1(RAYS_NSPECIES), alphat2(RAYS_NSPECIES), T_min(RAYS_NSPECIES)
+    end type
+    type, bind(C) :: rays_solovev_eq
+        real(c_double) :: rmaj, kappa, bphi0, iota0, outer_bound, psiB, inner_bound, vert_bound, r_Zmax
+        real(c_double) :: box_rmin, box_rmax, box_zmin, box_zmax
+        integer(c_int32_t) :: dens_prof_model, t_prof_model(RAYS_NSPECIES), pad_
+        real(c_double) :: alphan1, alphan2, alphat1(RAYS_NSPECIES), alphat2(RAYS_NSPECIES)
+    end type
+    type, bind(C) :: rays_axisym_eq
+        integer(c_int32_t) :: magnetics_model, density_prof_model, temperature_prof_model(RAYS_NSPECIES)
+        real(c_double) :: r_axis, z_axis, box_rmin, box_rmax, box_zmin, box_zmax
+        real(c_double) :: inner_bound, outer_bound, upper_bound, lower_bound
+        real(c_double) :: plasma_psi_limit, alphan1, alphan2, d_scrape_off, T_scrape_off
+        real(c_double) :: alphat1(RAYS_NSPECIES), alphat2(RAYS_NSPECIES)
+        real(c_double) :: sm_rmaj, sm_kappa, sm_bphi0, sm_iota0, sm_psiB
+        real(c_double) :: sm_box_rmin, sm_box_rmax, sm_box_zmin, sm_box_zmax
+    end type
+    type, bind(C) :: rays_mirror_eq
+        integer(c_int32_t) :: density_prof_model, temperature_prof_model(RAYS_NSPECIES), pad_
+        real(c_double) :: box_rmax, box_zmin, box_zmax, r_LUFS, z_LUFS, Aphi_LUFS
+        real(c_double) :: plasma_AphiN_limit, alphan1, alphan2, AphiN0_d, delta_d, d_scrape_off, T_scrape_off
+        real(c_double) :: alphat1(RAYS_NSPECIES), alphat2(RAYS_NSPECIES), AphiN0_t(RAYS_NSPECIES), delta_t(RAYS_NSPECIES)
+        type(rays_spline2d) :: Br_spline, Bz_spline, Aphi_spline
+    end type
+    type, bind(C) :: rays_cfg
+        real(c_double) :: clight, eps0
+        real(c_double) :: omgrf, k0, dispersion_resid_limit
+        integer(c_int32_t) :: ray_param, wave_mode, k0_sign
+        integer(c_int32_t) :: nspec
+        real(c_double) :: qs(RAYS_NSPECIES), ms(RAYS_NSPECIES), n0s(RAYS_NSPECIES), t0s(RAYS_NSPECIES), eta(RAYS_NSPECIES)
+        integer(c_int32_t) :: ode_solver, ray_deriv, nv, nstep_max
+        real(c_double) :: ds, s_max, rel_err0, abs_err0, SG_error_limit
+        integer(c_int32_t) :: damping_model, multi_spec_damping
+        real(c_double) :: total_damping_limit
+        integer(c_int32_t) :: integrate_eq_gradients, equilib_model
+        type(rays_slab_eq) :: slab
+        type(rays_solovev_eq) :: solovev
+        type(rays_axisym_eq) :: axisym
+        type(rays_mirror_eq) :: mirror
+        type(rays_spline1d) :: zfun_re
+    end type
+    type, bind(C) :: rays_fan
+        integer(c_int64_t) :: nray
+        type(c_ptr) :: rvec0, rindex_vec0, ray_pwr_wt
+    end type
+    type, bind(C) :: rays_results
+        integer(c_int64_t) :: nray
+        integer(c_int32_t) :: nv, npoints_alloc
+        type(c_ptr) :: ray_vec, residual, npoints, ray_stop_code, ray_stop_flag, initial_ray_power, ray_trace_time
+        type(c_ptr) :: end_residuals, max_residuals, end_ray_parameter, start_ray_vec, end_ray_vec
+        real(c_double) :: total_trace_time
+        integer(c_int64_t) :: total_ray_steps
+    end type
+
+    interface
+        integer(c_int) function rays_b200_init(device) bind(C, name='rays_b200_init')
+            import :: c_int
+            integer(c_int), value :: device
+        end function
+        integer(c_int) function rays_b200_finalize() bind(C, name='rays_b200_finalize')
+            import :: c_int
+        end function
+        integer(c_int) function rays_b200_trace(cfg, fan, res) bind(C, name='rays_b200_trace')
+            import :: c_int, rays_cfg, rays_fan, rays_results
+            type(rays_cfg), intent(in) :: cfg
+            type(rays_fan), intent(in) :: fan
+            type(rays_results), intent(inout) :: res
+        end function
+        type(c_ptr) function rays_b200_last_error() bind(C, name='rays_b200_last_error')
+            import :: c_ptr
+        end function
+        integer(c_int) function rays_b200_host_alloc(p, bytes) bind(C, name='rays_b200_host_alloc')
+            import :: c_int, c_ptr, c_size_t
+            type(c_ptr), intent(out) :: p
+            integer(c_size_t), value :: bytes
+        end function
+        integer(c_int) function rays_b200_struct_sizes(out, n) bind(C, name='rays_b200_struct_sizes')
+            import :: c_int, c_int32_t
+            integer(c_int32_t), intent(out) :: out(*)
+            integer(c_int), value :: n
+        end function
+    end interface
+
+contains
+
+    integer function prof_code(name)
+        character(len=*), intent(in) :: name
+        select case (trim(name))
+            case ('zero');       prof_code = 0
+            case ('constant');   prof_code = 1
+            case ('linear');     prof_code = 2
+            case ('linear_2');   prof_code = 3
+            case ('parabolic');  prof_code = 4
+            case ('Gaussian');   prof_code = 5
+            case ('hyperbolic'); prof_code = 6
+            case default;        prof_code = -1
+        end select
+    end function prof_code
+
+end module rays_b200_m
+
+!*************************************************************************************************
+
+ subroutine trace_rays
+!   Drop-in replacement of RAYS_lib/ray_tracing.f90: packs the module state the reference's ray loop
+!   reads (SURVEY.md 8b "inputs to marshal"), calls rays_b200_trace, and leaves the results in the
+!   ray_results_m module arrays exactly as the OpenMP loop did.
+
+    use, intrinsic :: iso_c_binding
+    use rays_b200_m
+    use constants_m, only : rkind, clight, eps0
+    use diagnostics_m, only : message, text_message, integrate_eq_gradients
+    use species_m, only : nspec, qs, ms, n0s, t0s, eta
+    use rf_m, only : omgrf, k0, ray_param, wave_mode, k0_sign, dispersion_resid_limit
+    use damping_m, only : damping_model, multi_spec_damping, total_damping_limit
+    use ode_m, only : ode_solver_name, ray_deriv_name, nv, ds, s_max, nstep_max
+    use SG_ode_m, only : rel_err0, abs_err0, SG_error_limit
+    use equilibrium_m, only : equilib_model
+    use ray_init_m, only : nray, rvec0, rindex_vec0, ray_pwr_wt
+    use ray_results_m, only : ray_vec, residual, npoints, ray_stop_flag, initial_ray_power, ray_trace_time, &
+        & end_residuals, max_residuals, end_ray_parameter, start_ray_vec, end_ray_vec, total_trace_time
+    use zfunctions_m, only : x_grid, fsplRe, initialize_spline_coeffs, zfun_initialized => initialized
+
+    implicit none
+
+    type(rays_cfg), target :: cfg
+    type(rays_fan) :: fan
+    type(rays_results) :: res
+    integer(c_int32_t), allocatable, target :: stop_code(:)
+    integer :: rc
+    logical, save :: device_ready = .false.
+
+    if (.not. device_ready) then
+        rc = rays_b200_init(0_c_int)              ! one process per GPU; the launcher sets CUDA_VISIBLE_DEVICES
+        if (rc /= 0) call fail('rays_b200_init')
+        device_ready = .true.
+    end if
+
+!   constants_m, rf_m, species_m (values computed by the Fortran host carry its own rounding)
+    cfg%clight = clight;  cfg%eps0 = eps0
+    cfg%omgrf = omgrf;    cfg%k0 = k0;  cfg%dispersion_resid_limit = dispersion_resid_limit
+    cfg%ray_param = merge(1, 2, trim(ray_param) == 'arcl')
+    select case (trim(wave_mode))
+        case ('plus');  cfg%wave_mode = 1
+        case ('minus'); cfg%wave_mode = 2
+        case ('fast');  cfg%wave_mode = 3
+        case ('slow');  cfg%wave_mode = 4
+    end select
+    cfg%k0_sign = k0_sign
+    cfg%nspec = nspec
+    cfg%qs = qs(0:5);  cfg%ms = ms(0:5);  cfg%n0s = n0s(0:5);  cfg%t0s = t0s(0:5);  cfg%eta = eta(0:5)
+!   ode_m, SG_ode_m
+    cfg%ode_solver = merge(2, 1, trim(ode_solver_name) == 'SG_ODE')
+    cfg%ray_deriv = merge(2, 1, trim(ray_deriv_name) == 'numerical')
+    cfg%nv = nv;  cfg%nstep_max = nstep_max;  cfg%ds = ds;  cfg%s_max = s_max
+    cfg%rel_err0 = rel_err0;  cfg%abs_err0 = abs_err0;  cfg%SG_error_limit = SG_error_limit
+!   damping_m, diagnostics_m
+    cfg%damping_model = merge(0, 1, trim(damping_model) == 'no_damp')
+    cfg%multi_spec_damping = merge(1, 0, multi_spec_damping)
+    cfg%total_damping_limit = total_damping_limit
+    cfg%integrate_eq_gradients = merge(1, 0, integrate_eq_gradients)
+    if (cfg%damping_model /= 0) then
+        if (.not. zfun_initialized) call initialize_spline_coeffs
+        cfg%zfun_re%nx = size(x_grid);  cfg%zfun_re%x_grid = c_loc(x_grid);  cfg%zfun_re%fspl = c_loc(fsplRe)
+    end if
+!   equilibrium_m: the selected model's module data (pack_* are one block of assignments per model, e.g.
+!   cfg%solovev%rmaj = rmaj ... cfg%solovev%psiB = psiB from solovev_eq_m; for multiple_mirror the three
+!   cube_spline_function_2D objects give nx, ny, c_loc(x grid), c_loc(y grid), c_loc(fspl))
+    select case (trim(equilib_model))
+        case ('slab');            cfg%equilib_model = 1;  call pack_slab_eq(cfg%slab)
+        case ('solovev');         cfg%equilib_model = 2;  call pack_solovev_eq(cfg%solovev)
+        case ('axisym_toroid');   cfg%equilib_model = 3;  call pack_axisym_toroid_eq(cfg%axisym)
+        case ('multiple_mirror'); cfg%equilib_model = 4;  call pack_multiple_mirror_eq(cfg%mirror)
+    end select
+
+!   ray_init_m: the launch fan, as the launcher modules left it (rvec0(3,nray) is xyz-contiguous per ray)
+    fan%nray = nray
+    fan%rvec0 = c_loc(rvec0);  fan%rindex_vec0 = c_loc(rindex_vec0);  fan%ray_pwr_wt = c_loc(ray_pwr_wt)
+
+!   ray_results_m: caller-owned arrays in their Fortran layout ray_vec(nv, nstep_max+1, nray)
+    allocate(stop_code(nray))
+    res%nray = nray;  res%nv = nv;  res%npoints_alloc = nstep_max + 1
+    res%ray_vec = c_loc(ray_vec);  res%residual = c_loc(residual);  res%npoints = c_loc(npoints)
+    res%ray_stop_code = c_loc(stop_code);  res%ray_stop_flag = c_loc(ray_stop_flag)
+    res%initial_ray_power = c_loc(initial_ray_power);  res%ray_trace_time = c_loc(ray_trace_time)
+    res%end_residuals = c_loc(end_residuals);  res%max_residuals = c_loc(max_residuals)
+    res%end_ray_parameter = c_loc(end_ray_parameter)
+    res%start_ray_vec = c_loc(start_ray_vec);  res%end_ray_vec = c_loc(end_ray_vec)
+
+    rc = rays_b200_trace(cfg, fan, res)
+    if (rc /= 0) call fail('rays_b200_trace')
+
+    total_trace_time = res%total_trace_time
+    call message('Wall time ray tracing', total_trace_time, 0)
+    deallocate(stop_code)
+    return
+
+ contains
+
+    subroutine pack_solovev_eq(q)
+!   solovev_eq_m module data (RAYS_lib/solovev_eq_m.f90:17-45) -> rays_solovev_eq.  pack_slab_eq,
+!   pack_axisym_toroid_eq (+ solovev_magnetics_m) and pack_multiple_mirror_eq (+ the three
+!   cube_spline_function_2D objects of mirror_magnetics_spline_interp_m) follow the same pattern:
+!   one assignment per field of the struct, strings resolved with prof_code (table in INTEGRATION.md).
+        use solovev_eq_m, only : rmaj, kappa, bphi0, iota0, outer_bound, psiB, inner_bound, vert_bound, r_Zmax, &
+            & box_rmin, box_rmax, box_zmin, box_zmax, dens_prof_model, alphan1, alphan2, t_prof_model, alphat1, alphat2
+        type(rays_solovev_eq), intent(out) :: q
+        integer :: is
+        q%rmaj = rmaj;  q%kappa = kappa;  q%bphi0 = bphi0;  q%iota0 = iota0;  q%outer_bound = outer_bound;  q%psiB = psiB
+        q%inner_bound = inner_bound;  q%vert_bound = vert_bound;  q%r_Zmax = r_Zmax
+        q%box_rmin = box_rmin;  q%box_rmax = box_rmax;  q%box_zmin = box_zmin;  q%box_zmax = box_zmax
+        q%dens_prof_model = prof_code(dens_prof_model)
+        q%alphan1 = alphan1;  q%alphan2 = alphan2
+        q%t_prof_model = 0;  q%alphat1 = 0.;  q%alphat2 = 0.
+        do is = 0, nspec
+            q%t_prof_model(is+1) = prof_code(t_prof_model(is))
+            q%alphat1(is+1) = alphat1(is);  q%alphat2(is+1) = alphat2(is)
+        end do
+    end subroutine pack_solovev_eq
+
+    subroutine fail(where)
+        character(len=*), intent(in) :: where
+        character(kind=c_char), pointer :: msg(:)
+        call c_f_pointer(rays_b200_last_error(), msg, [256])
+        write(0,*) where, ' failed: ', msg(1:index(transfer(msg, repeat(' ', 256)), c_null_char) - 1)
+        stop 1
+    end subroutine fail
+
+ end subroutine trace_rays

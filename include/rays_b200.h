@@ -308,6 +308,12 @@ int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_
 /* DFMA-only microbenchmark: measured fp64 FMA throughput of this GPU in TFLOP/s (2 flop/FMA)
  * and the SM clock (MHz) NVML/driver reported under load (0 if unavailable). */
 int rays_b200_fp64_peak(double *tflops, double *sm_mhz);
+/* Self-test of the kernels' exact arithmetic helpers (correctly rounded reciprocal and square root without
+ * range checks, quotient by reciprocal + FMA correction) against IEEE 1.0/d, sqrt(x), x/d on n pseudo-random
+ * operand pairs on the device; mismatch[0..2] receive the number of differing results of each (must be 0),
+ * mismatch[3] the count of the one documented exception: the reciprocal of a divisor whose 52-bit significand
+ * is all ones is 1 ulp off (probability 2^-52 per reciprocal on real data). */
+int rays_b200_selftest_arith(int64_t n, uint64_t seed, int64_t *mismatch);
 /* page-locked host memory for the result arrays (allocate_ray_results, ray_results_m.f90:132-142):
  * lets the trajectory copy-out of rays_b200_trace run at PCIe rate; pageable arrays work too */
 int rays_b200_host_alloc(void **p, size_t bytes);

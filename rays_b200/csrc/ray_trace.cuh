@@ -50,7 +50,7 @@ RD_INLINE int ray_equations(const Eq<NSpec<T::NS>::MAX> &e, const double *v, con
     if (dddw == 0.0) return RAYS_STOP_INFINITE_VG_RHS;
     const Rcp W = rcp_of(dddw);
     const double vg[3] = {qdiv(-dddk[0], W), qdiv(-dddk[1], W), qdiv(-dddk[2], W)};
-    const double vg0 = sqrt(vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2]);
+    const double vg0 = sqrt_rn(vg[0] * vg[0] + vg[1] * vg[1] + vg[2] * vg[2]);
     double dsd;
     if (c.ray_param == RAYS_PARAM_ARCL) {
         if (dddk[0] != 0.0 || dddk[1] != 0.0 || dddk[2] != 0.0) {
@@ -763,8 +763,11 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
 // Sequence per iteration, in the reference's order (ray_tracing.f90:116-245):
 //   check_save(v) -> [stop: point not saved] -> save point, nstep++ -> s = sout, sout += ds -> s_max / nstep_max
 //   tests -> RK4 stages -> v advanced (or ray stopped by the RHS with v untouched).
+#ifndef RAYS_RK4_MIN_CTAS
+#define RAYS_RK4_MIN_CTAS 4   // measured on the 1M-ray bench fan: 2 -> 284 ms, 3 -> 238, 4 -> 234, 5 -> 246, 6 -> 269
+#endif
 template <class T>
-__global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int nv = T::nv();
@@ -931,6 +934,38 @@ __global__ void __launch_bounds__(kTraceBlock) trace_rk4_kernel(const TraceArgs 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
     if (lane == 0) { atomicAdd(a.counters, st); atomicAdd(a.counters + 1, rh); }
+}
+
+// ---- arithmetic self-test: rcp_rn / sqrt_rn / qdiv against IEEE 1.0/d, sqrt(x), x/d on pseudo-random operands
+static __global__ void selftest_arith_kernel(unsigned long long seed, int per_thread, unsigned long long *mismatch) {
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned long long bad_rcp = 0, bad_sqrt = 0, bad_div = 0;
+    for (int it = 0; it < per_thread; ++it) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long ma = s;
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long mb = s;
+        const int mode = it & 7;
+        int ea = (int)((ma >> 52) % 400) - 200, eb = (int)((mb >> 52) % 400) - 200;
+        if (mode == 0) { mb |= 0xFFF0000000000ULL; ma |= 0xFF00000000000ULL; ea = eb = 0; }
+        else if (mode == 1) { mb = 0xFFFFFFFFFFFFFULL - (mb & 0xFFFFF); ma = 0xFFFFFFFFFFFFFULL - (ma & 0xFFFFFF); ea = eb = 0; }
+        else if (mode == 2) { mb &= 0xFFFULL; }
+        const double a = __longlong_as_double((long long)(((unsigned long long)(1023 + ea) << 52) | (ma & 0xFFFFFFFFFFFFFULL)));
+        double b = __longlong_as_double((long long)(((unsigned long long)(1023 + eb) << 52) | (mb & 0xFFFFFFFFFFFFFULL)));
+        if (mb & (1ULL << 60)) b = -b;
+        const double r = rcp_rn(b);
+        // Known exception of the final correction step (Markstein): a divisor whose 52-bit significand is
+        // all ones (probability 2^-52 for real data; CUDA's __drcp_rn routes that case to its slow path).
+        // Such operands are counted separately (mismatch[3]) and excluded from the three exact counts.
+        if ((mb & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL) { if (r != 1.0 / b) atomicAdd(mismatch + 3, 1ULL); continue; }
+        if (r != 1.0 / b) ++bad_rcp;
+        if (sqrt_rn(a) != sqrt(a)) ++bad_sqrt;
+        Rcp rc; rc.d = b; rc.r = r;
+        if (qdiv(a, rc) != a / b) ++bad_div;
+    }
+    if (bad_rcp) atomicAdd(mismatch, bad_rcp);
+    if (bad_sqrt) atomicAdd(mismatch + 1, bad_sqrt);
+    if (bad_div) atomicAdd(mismatch + 2, bad_div);
 }
 
 // ---- one-point probes (unit parity tests through the C ABI) -----------------------------------------------

@@ -504,6 +504,14 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     d.rc_Aphi_LUFS = mk(c.mirror.Aphi_LUFS);
     d.rc_two_delta = mk(d.dn_two_delta); d.rc_omg_p = mk(d.dn_omg_p); d.rc_omg_m = mk(d.dn_omg_m); d.rc_omg_p2 = mk(d.dn_omg_p2);
     d.rc_omg_m2 = mk(d.dn_omg_m2); d.rc_k0_p = mk(d.dn_k0_p); d.rc_k0_m = mk(d.dn_k0_m); d.rc_omg_delta = mk(d.dn_omg_delta);
+    {   // are the temperatures read by anything on this run's path?
+        bool need = c.damping_model != RAYS_DAMP_NONE || c.integrate_eq_gradients != 0;
+        for (int s = 0; s <= c.nspec; ++s) {
+            if (c.t0s[s] < 0.0) need = true;                                                    // 'negative_temp' must still fire
+            if (c.equilib_model == RAYS_EQ_SOLOVEV && c.solovev.t_prof_model[s] == RAYS_PROF_CONSTANT) need = true;   // (R) resets the density
+        }
+        d.need_temp = need ? 1 : 0;
+    }
     // kernel selection: the two-species specialisations cover electron + one ion without per-species damping slots
     g.sel.ray_deriv = c.ray_deriv;
     g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
@@ -986,6 +994,27 @@ int rays_b200_fp64_peak(double *tflops, double *sm_mhz) {
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
         *sm_mhz = khz / 1000.0;   // maximum SM clock; bench.py samples the clock under load with nvidia-smi
     }
+    return 0;
+}
+
+// rcp_rn / sqrt_rn / qdiv of the kernels against IEEE 1.0/d, sqrt(x), x/d on n pseudo-random operand pairs
+// (a quarter of them adversarial); mismatch[0..2] = counts for reciprocal, square root, quotient (must be 0);
+// mismatch[3] = reciprocals of all-ones-significand divisors that are 1 ulp off (the documented exception)
+int rays_b200_selftest_arith(int64_t n, uint64_t seed, int64_t *mismatch) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    CK(cudaSetDevice(g.device));
+    DevBuf<unsigned long long> d;
+    CK(d.reserve(4));
+    CK(cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), g.stream));
+    const int threads = 256, blocks = g.num_sms * 4;
+    const int per_thread = (int)std::max<int64_t>(1, n / ((int64_t)threads * blocks));
+    selftest_arith_kernel<<<blocks, threads, 0, g.stream>>>(seed, per_thread, d.p);
+    CK(cudaGetLastError());
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    d.release();
+    for (int i = 0; i < 4; ++i) mismatch[i] = (int64_t)h[i];
     return 0;
 }
 

@@ -191,3 +191,14 @@ def test_probe_rhs_and_check_save(deriv):
     gr, gc = rb.probe_check_save(v)
     orr, oc = orc.probe_check_save(cfg, v)
     assert np.array_equal(gc, oc) and np.array_equal(gr, orr)
+
+
+def test_exact_arithmetic_helpers_on_device():
+    """rcp_rn / sqrt_rn / qdiv (ray_physics.cuh) == IEEE 1.0/d, sqrt(x), x/d on 2^30 operand pairs."""
+    import ctypes as C
+    from rays_b200 import _abi
+    L = _abi.load()
+    mm = (C.c_int64 * 4)()
+    assert L.rays_b200_selftest_arith(1 << 30, 20260101, mm) == 0
+    assert list(mm)[:3] == [0, 0, 0], list(mm)
+    assert mm[3] < 1000      # all-ones-significand divisors (forced by the adversarial modes): the documented exception
