@@ -239,14 +239,14 @@ def main():
     # ---- end-to-end arm: host buffers through rays_b200_trace ------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        res = rb.ResultArrays.__new__(rb.ResultArrays)
         pinned = []
 
         def host_array(shape, dtype=np.float64):
+            """page-locked array from the library's allocator (allocate_ray_results); pageable if that fails"""
             nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
             p = C.c_void_p()
             if L.rays_b200_host_alloc(C.byref(p), max(nbytes, 8)) != 0:
-                return np.zeros(shape, dtype=dtype)          # pageable fallback
+                return np.zeros(shape, dtype=dtype)
             pinned.append(p)
             buf = (C.c_char * max(nbytes, 8)).from_address(p.value)
             a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
@@ -256,11 +256,12 @@ def main():
         out.nray = nray
         out.ray_vec = host_array((nray, npa, nv))
         out.residual = host_array((nray, npa))
-        out.npoints = np.zeros(nray, dtype=np.int32); out.ray_stop_code = np.zeros(nray, dtype=np.int32)
+        out.npoints = host_array((nray,), np.int32)
+        out.ray_stop_code = host_array((nray,), np.int32)
         out._flags = C.create_string_buffer(nray * _abi.FLAG_LEN)
         for nm in ("initial_ray_power", "ray_trace_time", "end_residuals", "max_residuals", "end_ray_parameter"):
-            setattr(out, nm, np.zeros(nray))
-        out.start_ray_vec, out.end_ray_vec = np.zeros((nray, nv)), np.zeros((nray, nv))
+            setattr(out, nm, host_array((nray,)))
+        out.start_ray_vec, out.end_ray_vec = host_array((nray, nv)), host_array((nray, nv))
         c = out.c
         c.nray, c.nv, c.npoints_alloc = nray, nv, npa
         dp, ip = (lambda a: a.ctypes.data_as(_abi.c_double_p)), (lambda a: a.ctypes.data_as(_abi.c_int32_p))
@@ -268,23 +269,28 @@ def main():
         c.ray_stop_flag = C.cast(out._flags, C.c_char_p)
         c.initial_ray_power, c.ray_trace_time, c.end_residuals = dp(out.initial_ray_power), dp(out.ray_trace_time), dp(out.end_residuals)
         c.max_residuals, c.end_ray_parameter, c.start_ray_vec, c.end_ray_vec = dp(out.max_residuals), dp(out.end_ray_parameter), dp(out.start_ray_vec), dp(out.end_ray_vec)
-        fan, keep = rb.make_fan(rvec0, nvec0, wt)
+        h_r, h_n, h_w = host_array((nray, 3)), host_array((nray, 3)), host_array((nray,))
+        h_r[...], h_n[...], h_w[...] = rvec0, nvec0, wt
+        fan, keep = rb.make_fan(h_r, h_n, h_w)
         for _ in range(max(1, min(args.warmup, 2))):
             assert L.rays_b200_trace(C.byref(cfg), C.byref(fan), C.byref(c)) == 0, L.rays_b200_last_error()
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_steps = 0
+        e2e_steps, e2e_dev_ms = 0, 0.0
         for _ in range(args.steps):
             assert L.rays_b200_trace(C.byref(cfg), C.byref(fan), C.byref(c)) == 0, L.rays_b200_last_error()
             e2e_steps += int(c.total_ray_steps)
-            launches += rb.last_trace_stats()["n_launches"]
+            stt = rb.last_trace_stats()
+            launches += stt["n_launches"]
+            e2e_dev_ms += stt["kernel_ms"]
         torch.cuda.synchronize(); barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e_all = sum_over_ranks(float(e2e_steps))
         npts = out.npoints.astype(np.int64)
         d2h = float(np.sum(npts) * (nv + 1) * 8 + nray * (2 * 4 + 4 * 8 + 2 * nv * 8))
         e2e = {"value": e2e_all / dt, "unit": "ray-steps/s", "h2d_bytes_per_step": float(nray * 7 * 8), "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * dt / args.steps, "note": "d2h counts the saved points + summaries; the copy is trimmed per 64-ray group"}
+               "ms_per_step": 1e3 * dt / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
+               "note": "host fan in (pinned), trajectories + summaries out in the reference layout (pinned); finished rays are copied out by the trace kernel while others integrate; d2h counts saved points + summaries; device_ms = H2D + kernel + summary D2H by CUDA events"}
         # spot check: the end-to-end trajectories equal the device-resident run's summaries
         assert int(np.sum(npts - 1)) == ray_steps_per_fan
         for p in pinned:

@@ -597,6 +597,21 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 
 constexpr int kTraceBlock = 128;
 
+// one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the
+// 256-byte coalesced stores, so that the copy is bandwidth- rather than latency-bound (a 13 KB ray takes ~7
+// round trips instead of ~50; the latency-bound version cost the warp about one ray-step per finished ray)
+RD_INLINE void copy_row_to_host(double *__restrict__ dst, const double *__restrict__ src, int n, unsigned lane) {
+    int i = (int)lane;
+    for (; i + 32 * 7 < n; i += 32 * 8) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = __ldcg(src + i + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[i + 32 * k] = t[k];
+    }
+    for (; i < n; i += 32) dst[i] = __ldcg(src + i);
+}
+
 // Warp-cooperative copy-out of the rays that ended in this iteration: every lane of the warp moves a
 // slice of each finished ray's staged trajectory (HBM/L2) to the caller's arrays in pinned host memory,
 // 256-byte coalesced stores over PCIe, overlapped with the integration of the other rays.
@@ -613,13 +628,12 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
         if (a.host_ray_vec) {
             const double *src = a.ray_vec + (size_t)rw * a.npoints_alloc * nv;
             double *dst = a.host_ray_vec + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc * nv;
-            const int n = np * nv;
-            for (int i = (int)lane; i < n; i += 32) dst[i] = __ldcg(src + i);
+            copy_row_to_host(dst, src, np * nv, lane);
         }
         if (a.host_residual) {
             const double *src = a.residual + (size_t)rw * a.npoints_alloc;
             double *dst = a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc;
-            for (int i = (int)lane; i < np; i += 32) dst[i] = __ldcg(src + i);
+            copy_row_to_host(dst, src, np, lane);
         }
     }
 }
