@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rays", type=int, default=12288, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--ode", default="", help="measurement aid: override ode_solver_name (RK4_ODE | SG_ODE)")
+    ap.add_argument("--deriv", default="", help="measurement aid: override ray_deriv_name (cold | numerical)")
     return ap.parse_args()
 
 
@@ -62,6 +64,35 @@ def workload_namelist(rank: int, rays: int) -> str:
     p = os.path.join(d, "rays.in")
     open(p, "w").write(text)
     return p
+
+
+def host_threads() -> int:
+    """threads for the CPU arms: every core this process may run on (torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def host_memory_budget(world_local: int) -> float:
+    """bytes of host memory one rank may lock for result arrays: half of min(cgroup limit, MemAvailable) / ranks"""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = float(ln.split()[1]) * 1024.0
+    except Exception:
+        pass
+    for f in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(f).read().strip()
+            if v != "max":
+                avail = min(avail, float(v)) if avail else float(v)
+        except Exception:
+            pass
+    if not avail:
+        avail = 64e9
+    return 0.5 * avail / max(world_local, 1)
 
 
 class ClockSampler(threading.Thread):
@@ -114,16 +145,16 @@ def run_reference(args, rank, world):
     stride = max(1, r.shape[0] // args.cpu_rays)
     idx = np.arange(0, r.shape[0], stride)
     rs, ns_, ws = r[idx].copy(), n[idx].copy(), w[idx].copy()
+    cores = host_threads()
     for _ in range(max(args.warmup, 1) if args.steps > 1 else 1):
-        orc.trace(cfg, rs[:256], ns_[:256], ws[:256], store=False)
+        orc.trace(cfg, rs[:256], ns_[:256], ws[:256], store=False, nthreads=cores)
     t0 = time.perf_counter()
     steps = 0
     for _ in range(args.steps):
-        o, st, _ = orc.trace(cfg, rs, ns_, ws, store=True)
+        o, st, _ = orc.trace(cfg, rs, ns_, ws, store=True, nthreads=cores)
         steps += o.total_ray_steps
     dt = time.perf_counter() - t0
     val = steps / dt
-    cores = orc.num_threads()
     sample = f"{len(idx)} rays (every {stride}th of the {r.shape[0]}-ray fan), {steps // args.steps} ray-steps per step"
     print(json.dumps({
         "impl": "reference", "metric": "ray_steps_per_sec", "value": val, "unit": "ray-steps/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -178,6 +209,8 @@ def main():
     # ---- initialize(read_input): namelist -> module state -> launch fan built on the device ------------
     path = workload_namelist(rank, args.rays)
     rb.initialize(path, ray_init=True, device=local_rank)
+    if args.ode or args.deriv:
+        rb.set_ode(ode_solver_name=args.ode, ray_deriv_name=args.deriv, rel_err0=1e-6, abs_err0=1e-6, SG_error_limit=0.1)
     cfg = rb.host_cfg()
     rvec0, nvec0, wt = rb.get_fan()
     nray = rvec0.shape[0]
@@ -252,18 +285,26 @@ def main():
             a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
             a[...] = 0
             return a
+        # The reference's result arrays are dense: ray_vec(nv, nstep_max+1, nray) = 58.8 GB + residual 8.4 GB for
+        # this fan.  When that exceeds this rank's share of host memory the host traces the fan in equal batches
+        # of rays, re-using the same arrays (as a host that writes each batch out before the next would).
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        budget = host_memory_budget(local_world)
+        per_ray = npa * (nv + 1) * 8.0
+        n_batches = max(1, int(np.ceil(nray * per_ray / budget)))
+        nb_rays = (nray + n_batches - 1) // n_batches
         out = rb.ResultArrays(0, nv, npa, store=False)
-        out.nray = nray
-        out.ray_vec = host_array((nray, npa, nv))
-        out.residual = host_array((nray, npa))
-        out.npoints = host_array((nray,), np.int32)
-        out.ray_stop_code = host_array((nray,), np.int32)
-        out._flags = C.create_string_buffer(nray * _abi.FLAG_LEN)
+        out.nray = nb_rays
+        out.ray_vec = host_array((nb_rays, npa, nv))
+        out.residual = host_array((nb_rays, npa))
+        out.npoints = host_array((nb_rays,), np.int32)
+        out.ray_stop_code = host_array((nb_rays,), np.int32)
+        out._flags = C.create_string_buffer(nb_rays * _abi.FLAG_LEN)
         for nm in ("initial_ray_power", "ray_trace_time", "end_residuals", "max_residuals", "end_ray_parameter"):
-            setattr(out, nm, host_array((nray,)))
-        out.start_ray_vec, out.end_ray_vec = host_array((nray, nv)), host_array((nray, nv))
+            setattr(out, nm, host_array((nb_rays,)))
+        out.start_ray_vec, out.end_ray_vec = host_array((nb_rays, nv)), host_array((nb_rays, nv))
         c = out.c
-        c.nray, c.nv, c.npoints_alloc = nray, nv, npa
+        c.nray, c.nv, c.npoints_alloc = nb_rays, nv, npa
         dp, ip = (lambda a: a.ctypes.data_as(_abi.c_double_p)), (lambda a: a.ctypes.data_as(_abi.c_int32_p))
         c.ray_vec, c.residual, c.npoints, c.ray_stop_code = dp(out.ray_vec), dp(out.residual), ip(out.npoints), ip(out.ray_stop_code)
         c.ray_stop_flag = C.cast(out._flags, C.c_char_p)
@@ -271,28 +312,39 @@ def main():
         c.max_residuals, c.end_ray_parameter, c.start_ray_vec, c.end_ray_vec = dp(out.max_residuals), dp(out.end_ray_parameter), dp(out.start_ray_vec), dp(out.end_ray_vec)
         h_r, h_n, h_w = host_array((nray, 3)), host_array((nray, 3)), host_array((nray,))
         h_r[...], h_n[...], h_w[...] = rvec0, nvec0, wt
-        fan, keep = rb.make_fan(h_r, h_n, h_w)
+        fans = []
+        for b in range(n_batches):
+            lo, hi = b * nb_rays, min(nray, (b + 1) * nb_rays)
+            fans.append(rb.make_fan(h_r[lo:hi], h_n[lo:hi], h_w[lo:hi]))
+
+        def e2e_step():
+            steps_, ms_, nl_, pts_ = 0, 0.0, 0, 0
+            for fan, _keep in fans:
+                assert L.rays_b200_trace(C.byref(cfg), C.byref(fan), C.byref(c)) == 0, L.rays_b200_last_error()
+                steps_ += int(c.total_ray_steps)
+                stt = rb.last_trace_stats()
+                nl_ += stt["n_launches"]
+                ms_ += stt["kernel_ms"]
+                pts_ += int(np.sum(out.npoints[: int(fan.nray)], dtype=np.int64))
+            return steps_, ms_, nl_, pts_
         for _ in range(max(1, min(args.warmup, 2))):
-            assert L.rays_b200_trace(C.byref(cfg), C.byref(fan), C.byref(c)) == 0, L.rays_b200_last_error()
+            e2e_step()
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_steps, e2e_dev_ms = 0, 0.0
+        e2e_steps, e2e_dev_ms, npts_sum = 0, 0.0, 0
         for _ in range(args.steps):
-            assert L.rays_b200_trace(C.byref(cfg), C.byref(fan), C.byref(c)) == 0, L.rays_b200_last_error()
-            e2e_steps += int(c.total_ray_steps)
-            stt = rb.last_trace_stats()
-            launches += stt["n_launches"]
-            e2e_dev_ms += stt["kernel_ms"]
+            a_, b_, c_, d_ = e2e_step()
+            e2e_steps += a_; e2e_dev_ms += b_; launches += c_; npts_sum = d_
         torch.cuda.synchronize(); barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e_all = sum_over_ranks(float(e2e_steps))
-        npts = out.npoints.astype(np.int64)
-        d2h = float(np.sum(npts) * (nv + 1) * 8 + nray * (2 * 4 + 4 * 8 + 2 * nv * 8))
+        d2h = float(npts_sum * (nv + 1) * 8 + nray * (2 * 4 + 4 * 8 + 2 * nv * 8))
         e2e = {"value": e2e_all / dt, "unit": "ray-steps/s", "h2d_bytes_per_step": float(nray * 7 * 8), "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * dt / args.steps, "device_ms_per_step": e2e_dev_ms / args.steps,
                "note": "host fan in (pinned), trajectories + summaries out in the reference layout (pinned); finished rays are copied out by the trace kernel while others integrate; d2h counts saved points + summaries; device_ms = H2D + kernel + summary D2H by CUDA events"}
-        # spot check: the end-to-end trajectories equal the device-resident run's summaries
-        assert int(np.sum(npts - 1)) == ray_steps_per_fan
+        # spot check: the end-to-end run saved exactly the points the device-resident run counted
+        assert npts_sum - nray == ray_steps_per_fan, (npts_sum, nray, ray_steps_per_fan)
+        e2e["host_batches"] = n_batches
         for p in pinned:
             L.rays_b200_host_free(p)
 
@@ -303,9 +355,9 @@ def main():
         stride = max(1, nray // args.cpu_rays)
         idx = np.arange(0, nray, stride)
         t0 = time.perf_counter()
-        o, stt, _ = orc.trace(cfg, rvec0[idx], nvec0[idx], wt[idx], store=True)
+        o, stt, _ = orc.trace(cfg, rvec0[idx], nvec0[idx], wt[idx], store=True, nthreads=host_threads())
         dt = time.perf_counter() - t0
-        cpu = {"value": o.total_ray_steps / dt, "unit": "ray-steps/s", "cores": orc.num_threads(), "kind": "port",
+        cpu = {"value": o.total_ray_steps / dt, "unit": "ray-steps/s", "cores": host_threads(), "kind": "port",
                "sample": f"{len(idx)} rays (every {stride}th of the fan), {o.total_ray_steps} ray-steps, {dt:.1f} s; C++ restatement of the Fortran path, OpenMP over rays"}
 
     if rank == 0:
@@ -313,7 +365,8 @@ def main():
             "metric": "ray_steps_per_sec", "value": value, "unit": "ray-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": nray, "ray_steps_per_fan": int(ray_steps_per_fan), "ode": "RK4", "ray_deriv": "numerical",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": nray, "ray_steps_per_fan": int(ray_steps_per_fan),
+                       "ode": "SG" if cfg.ode_solver == 2 else "RK4", "ray_deriv": "numerical" if cfg.ray_deriv == 2 else "cold",
                        "ds": 5e-11, "nstep_max": 1000, "nv": nv, "sharding": "one fan per GPU, no collective during integration",
                        "l2": "256 MiB buffer written between timed iterations; trajectory output (>= 14 GB per fan) exceeds L2"},
             "wall_time_per_fan_s": dev_ms_max * 1e-3 / args.steps,
