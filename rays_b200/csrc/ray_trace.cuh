@@ -99,8 +99,6 @@ template <class T> RD_INLINE int eqn_ray(const double *v, double *dvds) {
     if (pert_err) return pert_err;
     return ray_equations<T>(e, v, dddx, dddk, dddw, dvds);
 }
-// out-of-line copy for the Shampine-Gordon stepper, which evaluates the RHS from three places
-template <class T> RD_NOINLINE int eqn_ray_call(const double *v, double *dvds) { return eqn_ray<T>(v, dvds); }
 
 // ---- check_save (check_save.f90:1-161): residual + stop tests at a saved point -------------------------
 // flag/stop follow ode_stop semantics: a flag may be set without stopping (equilibrium error, A.5 (X)).
@@ -202,6 +200,9 @@ template <int NV> struct SGWork {
     double x, h, hold;
     bool start, phase1, nornd;
     int ns, k, kold;
+    // values the reference keeps in locals of `step` across its derivative evaluations
+    double round, absh, xold, erk, erkm1;
+    int ifail, knew;
 };
 __device__ const double kSGgstr[14] = {  // ode_RAYS.f90:776-779 (single-precision literals)
     0.0, (double)0.50e+00f, (double)0.0833e+00f, (double)0.0417e+00f, (double)0.0264e+00f, (double)0.0188e+00f,
@@ -209,159 +210,180 @@ __device__ const double kSGgstr[14] = {  // ode_RAYS.f90:776-779 (single-precisi
     (double)0.00592e+00f, (double)0.00524e+00f, (double)0.00468e+00f};
 __device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0, 1024.0, 2048.0, 4096.0, 8192.0};
 
-// step (ode_RAYS.f90:595-1234); returns a stop code from the RHS or 0
-template <class T> __device__ int sg_step(int neqn, SGWork<T::NV> &W, double &eps, bool &crash, unsigned &nrhs) {
-    double &x = W.x, &h = W.h, &hold = W.hold;
-    double *y = W.yy, *wt = W.wt, *p = W.p, *yp = W.yp;
-    double(*phi)[T::NV] = W.phi;
-    double *alpha = W.alpha, *beta = W.beta, *sig = W.sig, *v = W.v, *w = W.w, *g = W.g, *psi = W.psi;
-    int &k = W.k, &kold = W.kold, &ns = W.ns;
+// step (ode_RAYS.f90:595-1234) is cut at its three right-hand-side evaluations so that a warp evaluates the
+// RHS of all its lanes at ONE place per loop iteration, whatever phase of the integrator each lane is in
+// (the straight transcription called eqn_ray from three divergent sites and ran at 1 % of the FP64 peak).
+// The arithmetic of every piece is the reference's, statement by statement.
+enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3 };
+
+// step, first block (:840-852): tests for too small a step / tolerance; returns true on crash
+template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps) {
     const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
-    crash = true;
-    if (fabs(h) < fouru * fabs(x)) { h = copysign(fouru * fabs(x), h); return 0; }
+    if (fabs(W.h) < fouru * fabs(W.x)) { W.h = copysign(fouru * fabs(W.x), W.h); return true; }
     const double p5eps = 0.5 * eps;
     double sum = 0.0;
-    for (int l = 0; l < neqn; ++l) { const double q = y[l] / wt[l]; sum = sum + q * q; }
-    const double round = twou * sqrt(sum);
-    if (p5eps < round) { eps = 2.0 * round * (1.0 + fouru); return 0; }
-    crash = false;
-    g[1] = 1.0; g[2] = 0.5; sig[1] = 1.0;
-    double absh;
-    if (W.start) {
-        const int code = eqn_ray_call<T>(y, yp); ++nrhs;
-        if (code) return code;
-        double tot = 0.0;
-        for (int l = 0; l < neqn; ++l) {
-            phi[1][l] = yp[l]; phi[2][l] = 0.0;
-            const double q = yp[l] / wt[l]; tot = tot + q * q;
-        }
-        const double total = sqrt(tot);
-        absh = fabs(h);
-        if (eps < 16.0 * total * h * h) absh = 0.25 * sqrt(eps / total);
-        h = copysign(fmax(absh, fouru * fabs(x)), h);
-        hold = 0.0;
-        k = 1; kold = 0;
-        W.start = false; W.phase1 = true; W.nornd = true;
-        if (p5eps <= 100.0 * round) {
-            W.nornd = false;
-            for (int l = 0; l < neqn; ++l) phi[15][l] = 0.0;
-        }
+    for (int l = 0; l < neqn; ++l) { const double q = W.yy[l] / W.wt[l]; sum = sum + q * q; }
+    W.round = twou * sqrt(sum);
+    if (p5eps < W.round) { eps = 2.0 * W.round * (1.0 + fouru); return true; }
+    W.g[1] = 1.0; W.g[2] = 0.5; W.sig[1] = 1.0;
+    W.ifail = 0;
+    return false;
+}
+// step, start block after the first derivative evaluation (:858-885)
+template <int NV> RD_INLINE void sg_after_start(int neqn, SGWork<NV> &W, double eps) {
+    const double fouru = 4.0 * DBL_EPSILON;
+    const double p5eps = 0.5 * eps;
+    double tot = 0.0;
+    for (int l = 0; l < neqn; ++l) {
+        W.phi[1][l] = W.yp[l]; W.phi[2][l] = 0.0;
+        const double q = W.yp[l] / W.wt[l]; tot = tot + q * q;
     }
-    int ifail = 0;
-    int kp1, kp2, km1, km2, knew;
-    double erkm2, erkm1, erk, err, xold;
-    for (;;) {
-        kp1 = k + 1; kp2 = k + 2; km1 = k - 1; km2 = k - 2;
-        if (h != hold) ns = 0;
-        if (ns <= kold) ns = ns + 1;
-        const int nsp1 = ns + 1;
-        if (ns <= k) {
-            beta[ns] = 1.0;
-            alpha[ns] = 1.0 / (double)ns;
-            double temp1 = h * (double)ns;
-            sig[nsp1] = 1.0;
-            for (int i = nsp1; i <= k; ++i) {
-                const double temp2 = psi[i - 1];
-                psi[i - 1] = temp1;
-                beta[i] = beta[i - 1] * psi[i - 1] / temp2;
-                temp1 = temp2 + h;
-                alpha[i] = h / temp1;
-                sig[i + 1] = (double)i * alpha[i] * sig[i];
-            }
-            psi[k] = temp1;
-            if (ns <= 1) {
-                for (int iq = 1; iq <= k; ++iq) { v[iq] = 1.0 / (double)(iq * (iq + 1)); w[iq] = v[iq]; }
-            } else {
-                if (kold < k) {
-                    v[k] = 1.0 / (double)(k * kp1);
-                    for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
-                }
-                for (int iq = 1; iq <= kp1 - ns; ++iq) { v[iq] = v[iq] - alpha[ns] * v[iq + 1]; w[iq] = v[iq]; }
-                g[nsp1] = w[1];
-            }
-            for (int i = ns + 2; i <= kp1; ++i) {
-                for (int iq = 1; iq <= kp2 - i; ++iq) w[iq] = w[iq] - alpha[i - 1] * w[iq + 1];
-                g[i] = w[1];
-            }
+    const double total = sqrt(tot);
+    double absh = fabs(W.h);
+    if (eps < 16.0 * total * W.h * W.h) absh = 0.25 * sqrt(eps / total);
+    W.h = copysign(fmax(absh, fouru * fabs(W.x)), W.h);
+    W.hold = 0.0;
+    W.k = 1; W.kold = 0;
+    W.start = false; W.phase1 = true; W.nornd = true;
+    if (p5eps <= 100.0 * W.round) {
+        W.nornd = false;
+        for (int l = 0; l < neqn; ++l) W.phi[15][l] = 0.0;
+    }
+}
+// step, blocks 1 and 2 (:896-1015): coefficients for this step size/order, then the predicted solution p at x + h
+template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
+    double *alpha = W.alpha, *beta = W.beta, *sig = W.sig, *v = W.v, *w = W.w, *g = W.g, *psi = W.psi;
+    double(*phi)[NV] = W.phi;
+    const int k = W.k, kold = W.kold;
+    int ns = W.ns;
+    const double h = W.h;
+    const int kp1 = k + 1, kp2 = k + 2;
+    if (h != W.hold) ns = 0;
+    if (ns <= kold) ns = ns + 1;
+    const int nsp1 = ns + 1;
+    if (ns <= k) {
+        beta[ns] = 1.0;
+        alpha[ns] = 1.0 / (double)ns;
+        double temp1 = h * (double)ns;
+        sig[nsp1] = 1.0;
+        for (int i = nsp1; i <= k; ++i) {
+            const double temp2 = psi[i - 1];
+            psi[i - 1] = temp1;
+            beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+            temp1 = temp2 + h;
+            alpha[i] = h / temp1;
+            sig[i + 1] = (double)i * alpha[i] * sig[i];
         }
-        for (int i = nsp1; i <= k; ++i)
-            for (int l = 0; l < neqn; ++l) phi[i][l] = beta[i] * phi[i][l];
-        for (int l = 0; l < neqn; ++l) { phi[kp2][l] = phi[kp1][l]; phi[kp1][l] = 0.0; p[l] = 0.0; }
-        for (int j = 1; j <= k; ++j) {
-            const int i = kp1 - j;
-            for (int l = 0; l < neqn; ++l) {
-                p[l] = p[l] + phi[i][l] * g[i];
-                phi[i][l] = phi[i][l] + phi[i + 1][l];
-            }
-        }
-        if (!W.nornd) {
-            for (int l = 0; l < neqn; ++l) {
-                const double tau = h * p[l] - phi[15][l];
-                p[l] = y[l] + tau;
-                phi[16][l] = (p[l] - y[l]) - tau;
-            }
+        psi[k] = temp1;
+        if (ns <= 1) {
+            for (int iq = 1; iq <= k; ++iq) { v[iq] = 1.0 / (double)(iq * (iq + 1)); w[iq] = v[iq]; }
         } else {
-            for (int l = 0; l < neqn; ++l) p[l] = y[l] + h * p[l];
+            if (kold < k) {
+                v[k] = 1.0 / (double)(k * kp1);
+                for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
+            }
+            for (int iq = 1; iq <= kp1 - ns; ++iq) { v[iq] = v[iq] - alpha[ns] * v[iq + 1]; w[iq] = v[iq]; }
+            g[nsp1] = w[1];
         }
-        xold = x;
-        x = x + h;
-        absh = fabs(h);
-        {
-            const int code = eqn_ray_call<T>(p, yp); ++nrhs;
-            if (code) return code;
-        }
-        erkm2 = 0.0; erkm1 = 0.0; erk = 0.0;
-        for (int l = 0; l < neqn; ++l) {
-            if (0 < km2) { const double q = (phi[km1][l] + yp[l] - phi[1][l]) / wt[l]; erkm2 = erkm2 + q * q; }
-            if (0 <= km2) { const double q = (phi[k][l] + yp[l] - phi[1][l]) / wt[l]; erkm1 = erkm1 + q * q; }
-            const double q = (yp[l] - phi[1][l]) / wt[l];
-            erk = erk + q * q;
-        }
-        if (0 < km2) erkm2 = absh * sig[km1] * kSGgstr[km2] * sqrt(erkm2);
-        if (0 <= km2) erkm1 = absh * sig[k] * kSGgstr[km1] * sqrt(erkm1);
-        err = absh * sqrt(erk) * (g[k] - g[kp1]);
-        erk = absh * sqrt(erk) * sig[kp1] * kSGgstr[k];
-        knew = k;
-        if (0 < km2) {
-            if (fmax(erkm1, erkm2) <= erk) knew = km1;
-        } else if (0 == km2) {
-            if (erkm1 <= 0.5 * erk) knew = km1;
-        }
-        if (err <= eps) break;
-        // step failed: restore x, phi, psi; halve (or more) the step
-        W.phase1 = false;
-        x = xold;
-        for (int i = 1; i <= k; ++i)
-            for (int l = 0; l < neqn; ++l) phi[i][l] = (phi[i][l] - phi[i + 1][l]) / beta[i];
-        for (int i = 2; i <= k; ++i) psi[i - 1] = psi[i] - h;
-        ifail = ifail + 1;
-        double temp2 = 0.5;
-        if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sqrt(p5eps / erk); }
-        if (3 <= ifail) knew = 1;
-        h = temp2 * h;
-        k = knew;
-        if (fabs(h) < fouru * fabs(x)) {
-            crash = true;
-            h = copysign(fouru * fabs(x), h);
-            eps = eps + eps;
-            return 0;
+        for (int i = ns + 2; i <= kp1; ++i) {
+            for (int iq = 1; iq <= kp2 - i; ++iq) w[iq] = w[iq] - alpha[i - 1] * w[iq + 1];
+            g[i] = w[1];
         }
     }
-    kold = k;
-    hold = h;
+    W.ns = ns;
+    for (int i = nsp1; i <= k; ++i)
+        for (int l = 0; l < neqn; ++l) phi[i][l] = beta[i] * phi[i][l];
+    for (int l = 0; l < neqn; ++l) { phi[kp2][l] = phi[kp1][l]; phi[kp1][l] = 0.0; W.p[l] = 0.0; }
+    for (int j = 1; j <= k; ++j) {
+        const int i = kp1 - j;
+        for (int l = 0; l < neqn; ++l) {
+            W.p[l] = W.p[l] + phi[i][l] * g[i];
+            phi[i][l] = phi[i][l] + phi[i + 1][l];
+        }
+    }
     if (!W.nornd) {
         for (int l = 0; l < neqn; ++l) {
-            const double rho = h * g[kp1] * (yp[l] - phi[1][l]) - phi[16][l];
-            y[l] = p[l] + rho;
-            phi[15][l] = (y[l] - p[l]) - rho;
+            const double tau = h * W.p[l] - phi[15][l];
+            W.p[l] = W.yy[l] + tau;
+            phi[16][l] = (W.p[l] - W.yy[l]) - tau;
         }
     } else {
-        for (int l = 0; l < neqn; ++l) y[l] = p[l] + h * g[kp1] * (yp[l] - phi[1][l]);
+        for (int l = 0; l < neqn; ++l) W.p[l] = W.yy[l] + h * W.p[l];
     }
-    {
-        const int code = eqn_ray_call<T>(y, yp); ++nrhs;
-        if (code) return code;
+    W.xold = W.x;
+    W.x = W.x + h;
+    W.absh = fabs(h);
+}
+// step, after the derivative at the predicted point (:1022-1110): error estimates, accept or fail.
+// returns 0 = accepted (corrected solution formed in yy, evaluate the derivative there next),
+//         1 = failed, retry with the reduced step, 2 = crash (step size too small: eps doubled)
+template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double &eps) {
+    const double fouru = 4.0 * DBL_EPSILON;
+    double(*phi)[NV] = W.phi;
+    const double *yp = W.yp, *wt = W.wt, *sig = W.sig, *g = W.g;
+    const int k = W.k, kp1 = k + 1, km1 = k - 1, km2 = k - 2;
+    const double absh = W.absh, p5eps = 0.5 * eps;
+    double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
+    for (int l = 0; l < neqn; ++l) {
+        if (0 < km2) { const double q = (phi[km1][l] + yp[l] - phi[1][l]) / wt[l]; erkm2 = erkm2 + q * q; }
+        if (0 <= km2) { const double q = (phi[k][l] + yp[l] - phi[1][l]) / wt[l]; erkm1 = erkm1 + q * q; }
+        const double q = (yp[l] - phi[1][l]) / wt[l];
+        erk = erk + q * q;
     }
+    if (0 < km2) erkm2 = absh * sig[km1] * kSGgstr[km2] * sqrt(erkm2);
+    if (0 <= km2) erkm1 = absh * sig[k] * kSGgstr[km1] * sqrt(erkm1);
+    const double err = absh * sqrt(erk) * (g[k] - g[kp1]);
+    erk = absh * sqrt(erk) * sig[kp1] * kSGgstr[k];
+    int knew = k;
+    if (0 < km2) {
+        if (fmax(erkm1, erkm2) <= erk) knew = km1;
+    } else if (0 == km2) {
+        if (erkm1 <= 0.5 * erk) knew = km1;
+    }
+    W.knew = knew; W.erk = erk; W.erkm1 = erkm1;
+    if (err <= eps) {   // accepted: correct (:1123-1141)
+        const double h = W.h;
+        W.kold = k;
+        W.hold = h;
+        if (!W.nornd) {
+            for (int l = 0; l < neqn; ++l) {
+                const double rho = h * g[kp1] * (yp[l] - phi[1][l]) - phi[16][l];
+                W.yy[l] = W.p[l] + rho;
+                phi[15][l] = (W.yy[l] - W.p[l]) - rho;
+            }
+        } else {
+            for (int l = 0; l < neqn; ++l) W.yy[l] = W.p[l] + h * g[kp1] * (yp[l] - phi[1][l]);
+        }
+        return 0;
+    }
+    // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
+    W.phase1 = false;
+    W.x = W.xold;
+    for (int i = 1; i <= k; ++i)
+        for (int l = 0; l < neqn; ++l) phi[i][l] = (phi[i][l] - phi[i + 1][l]) / W.beta[i];
+    for (int i = 2; i <= k; ++i) W.psi[i - 1] = W.psi[i] - W.h;
+    W.ifail = W.ifail + 1;
+    double temp2 = 0.5;
+    if (3 < W.ifail) { if (p5eps < 0.25 * erk) temp2 = sqrt(p5eps / erk); }
+    if (3 <= W.ifail) knew = 1;
+    W.h = temp2 * W.h;
+    W.k = knew;
+    if (fabs(W.h) < fouru * fabs(W.x)) {
+        W.h = copysign(fouru * fabs(W.x), W.h);
+        eps = eps + eps;
+        return 2;
+    }
+    return 1;
+}
+// step, after the derivative at the corrected point (:1147-1231): update differences, choose order and step
+template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, double eps) {
+    const double fouru = 4.0 * DBL_EPSILON;
+    double(*phi)[NV] = W.phi;
+    const double *yp = W.yp, *wt = W.wt;
+    int k = W.k;
+    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.knew, ns = W.ns;
+    const double absh = W.absh, p5eps = 0.5 * eps, h = W.h, erkm1 = W.erkm1;
+    double erk = W.erk;
     for (int l = 0; l < neqn; ++l) {
         phi[kp1][l] = yp[l] - phi[1][l];
         phi[kp2][l] = phi[kp1][l] - phi[kp2][l];
@@ -393,16 +415,16 @@ template <class T> __device__ int sg_step(int neqn, SGWork<T::NV> &W, double &ep
                 const double temp2 = (double)(k + 1);
                 const double r = pow(p5eps / erk, 1.0 / temp2);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
-                hnew = copysign(fmax(hnew, fouru * fabs(x)), h);
+                hnew = copysign(fmax(hnew, fouru * fabs(W.x)), h);
             }
         }
     }
-    h = hnew;
-    return 0;
+    W.k = k;
+    W.h = hnew;
 }
 
 // intrp (ode_RAYS.f90:1235-1362); ypout is not used by the caller
-template <int NV> __device__ void sg_intrp(int neqn, const SGWork<NV> &W, double xout, double *yout) {
+template <int NV> RD_INLINE void sg_intrp(int neqn, const SGWork<NV> &W, double xout, double *yout) {
     double g[14], rho[14], w[14];
     const double hi = xout - W.x;
     const int ki = W.kold + 1;
@@ -424,84 +446,6 @@ template <int NV> __device__ void sg_intrp(int neqn, const SGWork<NV> &W, double
         for (int l = 0; l < neqn; ++l) yout[l] = yout[l] + g[i] * W.phi[i][l];
     }
     for (int l = 0; l < neqn; ++l) yout[l] = W.yy[l] + hi * yout[l];
-}
-
-// ode + de with iflag = 1 on entry (ode_RAYS.f90:1-593).  Returns iflag; `code` is the RHS stop code.
-template <class T>
-__device__ int sg_de(int neqn, double *y, double &t, double tout, double &relerr, double &abserr, int &code, int &flag, unsigned &nrhs) {
-    SGWork<T::NV> W;
-    const int maxnum = 500;
-    const double fouru = 4.0 * DBL_EPSILON;
-    code = 0;
-    if (t == tout) { flag = RAYS_STOP_SG_T_EQ_TOUT; return 6; }
-    if (relerr < 0.0 || abserr < 0.0) { flag = RAYS_STOP_SG_BAD_TOL; return 6; }
-    double eps = fmax(relerr, abserr);
-    if (eps <= 0.0) { flag = RAYS_STOP_SG_EPS_LE_0; return 6; }
-    int iflag = 1;
-    const double del = tout - t;
-    const double absdel = fabs(del);
-    const double tend = t + 10.0 * del;
-    int nostep = 0, kle4 = 0;
-    bool stiff = false;
-    const double releps = relerr / eps;
-    const double abseps = abserr / eps;
-    W.start = true;
-    W.x = t;
-    for (int l = 0; l < neqn; ++l) W.yy[l] = y[l];
-    W.h = copysign(fmax(fabs(tout - W.x), fouru * fabs(W.x)), tout - W.x);
-    W.ns = 0; W.k = 0; W.kold = 0; W.hold = 0.0; W.phase1 = false; W.nornd = true;
-    for (;;) {
-        if (absdel <= fabs(W.x - t)) {
-            sg_intrp<T::NV>(neqn, W, tout, y);
-            iflag = 2;
-            t = tout;
-            break;
-        }
-        if (maxnum <= nostep) {
-            iflag = 4;
-            flag = RAYS_STOP_SG_MAXNUM;
-            if (stiff) { iflag = 5; flag = RAYS_STOP_SG_STIFF; }
-            for (int l = 0; l < neqn; ++l) y[l] = W.yy[l];
-            t = W.x;
-            break;
-        }
-        W.h = copysign(fmin(fabs(W.h), fabs(tend - W.x)), W.h);
-        for (int l = 0; l < neqn; ++l) W.wt[l] = releps * fabs(W.yy[l]) + abseps;
-        bool crash;
-        code = sg_step<T>(neqn, W, eps, crash, nrhs);
-        if (code) { flag = code; return iflag; }
-        if (crash) {
-            iflag = 3;
-            relerr = eps * releps;
-            abserr = eps * abseps;
-            for (int l = 0; l < neqn; ++l) y[l] = W.yy[l];
-            t = W.x;
-            break;
-        }
-        nostep = nostep + 1;
-        kle4 = kle4 + 1;
-        if (4 < W.kold) kle4 = 0;
-        if (50 <= kle4) stiff = true;
-    }
-    return iflag;
-}
-
-// SG_ode driver (SG_ode_m.f90:89-159): returns true if the ray stops; flag carries the reason
-template <class T>
-__device__ bool SG_ode(double *v, double &s, double &sout, double &rel_err, double &abs_err, int &flag, unsigned &nrhs) {
-    const int nv = T::nv();
-    for (;;) {
-        int code;
-        const int iflag = sg_de<T>(nv, v, s, sout, rel_err, abs_err, code, flag, nrhs);
-        if (code) { sout = s; return true; }
-        if (iflag == 2) return false;
-        if (iflag == 3) {
-            const double total_error = fabs(rel_err) + fabs(abs_err);
-            if (total_error > g_dc.c.SG_error_limit) { flag = RAYS_STOP_ODE_TOTAL_ERROR; return true; }
-            continue;
-        }
-        return true;  // error return: flag already set by de
-    }
 }
 
 // ---- the trace kernel ------------------------------------------------------------------------------------
@@ -638,45 +582,60 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
     }
 }
 
-template <class T, int ODE_>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
+// ---- Shampine-Gordon trace kernel ---------------------------------------------------------------------------
+// SG_ode (SG_ode_m.f90:89-159) -> ode/de (ode_RAYS.f90:1-593) -> step/intrp as a per-lane state machine.
+// One loop iteration evaluates at most one right-hand side per lane, at a single convergence point of the
+// warp; the integrator bookkeeping between two evaluations is lane-private.  `work`/`iwork` are automatic in
+// SG_ode and iflag = 1 on every call, so each ds segment restarts the integrator at order 1:
+// the history W lives in per-thread local memory and is re-initialised per segment.
+template <class T>
+__global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
+    constexpr int NSM = NSpec<T::NS>::MAX;
     const int nv = T::nv();
     const rays_cfg &c = g_dc.c;
     const unsigned lane = threadIdx.x & 31;
-    // per-lane ray state
+    const int maxnum = 500;
+    const double fouru = 4.0 * DBL_EPSILON;
+    // ray state
     double v[NV];
     double s = 0.0, sout = 0.0, rel_err = 0.0, abs_err = 0.0;
     double resid_prev = 0.0, resid_last = 0.0, resid_max = 0.0;
     double dep_x = 0.0, dep_Q = 0.0, pwr = 0.0;
     long long iray = -1;
     int nstep = 0, flag = 0;
-    bool active = false, exhausted = false;
+    int st = SG_IDLE;
+    bool exhausted = false, first = false;
+    // de state of the current segment
+    SGWork<NV> W;
+    double eps = 0.0, absdel = 0.0, tend = 0.0, releps = 0.0, abseps = 0.0, t = 0.0;
+    int nostep = 0, kle4 = 0;
+    bool stiff = false;
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
     const bool binning = a.dep_bins != nullptr && T::damp();
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
     const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t row = 0;
-    bool fin = false;      // this lane's ray ended in the current iteration
+    bool fin = false;
     int fin_np = 0;
 
     for (;;) {
-        // ---- refill: lanes without a ray take the next indices from the queue (one atomic per warp)
-        const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
+        // ---- refill from the work queue (one atomic per warp)
+        const unsigned want = __ballot_sync(0xffffffffu, st == SG_IDLE && !exhausted);
         if (want) {
             unsigned long long base = 0;
             const int leader = __ffs(want) - 1;
             if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(want));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (!active && !exhausted) {
+            if (st == SG_IDLE && !exhausted) {
                 const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
                 if (idx >= a.nray) exhausted = true;
                 else {
                     iray = idx;
                     row = streaming ? slot : (size_t)iray;
                     nstep = 0; s = 0.0; sout = 0.0; flag = 0;
-                    rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_ode_solver (SG_ode_m.f90:73-85)
+                    rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
                     resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
                     initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
                     pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
@@ -686,49 +645,23 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                     }
                     if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
                     if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                    double resid = 0.0;
-                    bool stop = false;
-                    check_save<T>(v, resid, stop, flag);
-                    if (stop) {   // "did not start": only npoints, flag and the first point are set (:101-112)
-                        fin = true; fin_np = 1;
-                        a.npoints[iray] = 1;
-                        a.stop_code[iray] = flag;
-                        if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
-                        if (a.end_residuals) a.end_residuals[iray] = 0.0;
-                        if (a.max_residuals) a.max_residuals[iray] = 0.0;
-                        if (a.end_ray_parameter) a.end_ray_parameter[iray] = 0.0;
-                        if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = 0.0;
-                        if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = 0.0;
-                    } else {
-                        active = true;
-                        if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
-                    }
+                    st = SG_CHECK; first = true;
                 }
             }
         }
-        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }   // "did not start" rays
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
+        if (__ballot_sync(0xffffffffu, st != SG_IDLE) == 0u) {
             if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
             continue;
         }
-        // ---- one pass of the trajectory loop body (ray_tracing.f90:116-245) for every active lane
-        if (active) {
-            bool stop = false;
-            s = sout;
-            sout = sout + c.ds;
-            if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
-            else if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; nstep = c.nstep_max; }
+        bool stop = false, did_not_start = false;
+
+        // ---- check_save of a new point + top of the trajectory loop (convergent: same code for every lane in SG_CHECK)
+        if (st == SG_CHECK) {
+            double resid = 0.0;
+            check_save<T>(v, resid, stop, flag);
+            if (stop) did_not_start = first;
             else {
-                if (ODE_ == RAYS_ODE_RK4) {
-                    const int code = RK4_ode<T>(v, s, sout);
-                    my_rhs += 4;
-                    if (code) { stop = true; flag = code; }
-                } else {
-                    stop = SG_ode<T>(v, s, sout, rel_err, abs_err, flag, my_rhs);
-                }
-                double resid = 0.0;
-                if (!stop) check_save<T>(v, resid, stop, flag);
-                if (!stop) {
+                if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
                     nstep = nstep + 1;
                     if (a.ray_vec) {
                         double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
@@ -744,27 +677,130 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const TraceArgs a) {
                         dep_x = xn; dep_Q = Qn;
                     }
                     ++my_steps;
+                } else if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
+                first = false;
+                s = sout;
+                sout = sout + c.ds;
+                if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
+                else if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; }
+                else st = SG_DE_BEGIN;
+            }
+        }
+
+        // ---- lane-private integrator bookkeeping up to the next derivative evaluation
+        int req = 0;               // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy
+        bool need_predict = false, de_top = false, crashed = false;
+        if (!stop) {
+            if (st == SG_DE_BEGIN) {   // ode/de entry with iflag = 1 (ode_RAYS.f90:425-505)
+                t = s;
+                if (t == sout) { stop = true; flag = RAYS_STOP_SG_T_EQ_TOUT; }
+                else if (rel_err < 0.0 || abs_err < 0.0) { stop = true; flag = RAYS_STOP_SG_BAD_TOL; }
+                else {
+                    eps = fmax(rel_err, abs_err);
+                    if (eps <= 0.0) { stop = true; flag = RAYS_STOP_SG_EPS_LE_0; }
+                    else {
+                        const double del = sout - t;
+                        absdel = fabs(del);
+                        tend = t + 10.0 * del;
+                        nostep = 0; kle4 = 0; stiff = false;
+                        releps = rel_err / eps;
+                        abseps = abs_err / eps;
+                        W.start = true;
+                        W.x = t;
+                        for (int l = 0; l < nv; ++l) W.yy[l] = v[l];
+                        W.h = copysign(fmax(fabs(sout - W.x), fouru * fabs(W.x)), sout - W.x);
+                        W.ns = 0; W.k = 0; W.kold = 0; W.hold = 0.0; W.phase1 = false; W.nornd = true;
+                        de_top = true;
+                    }
+                }
+            } else if (st == SG_AFTER_R1) {
+                sg_after_start<NV>(nv, W, eps);
+                need_predict = true;
+            } else if (st == SG_AFTER_R2) {
+                const int r = sg_after_predict<NV>(nv, W, eps);
+                if (r == 0) req = 3;
+                else if (r == 1) need_predict = true;
+                else crashed = true;
+            } else if (st == SG_AFTER_R3) {
+                sg_after_correct<NV>(nv, W, eps);
+                nostep = nostep + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
+                kle4 = kle4 + 1;
+                if (4 < W.kold) kle4 = 0;
+                if (50 <= kle4) stiff = true;
+                de_top = true;
+            }
+            if (de_top) {   // top of de's loop (ode_RAYS.f90:509-562)
+                if (absdel <= fabs(W.x - t)) {           // past the output point: interpolate, segment done (iflag = 2)
+                    sg_intrp<NV>(nv, W, sout, v);
+                    s = sout;
+                    st = SG_CHECK;
+                } else if (maxnum <= nostep) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
+                    flag = stiff ? RAYS_STOP_SG_STIFF : RAYS_STOP_SG_MAXNUM;
+                    for (int l = 0; l < nv; ++l) v[l] = W.yy[l];
+                    s = W.x;
+                    stop = true;
+                } else {
+                    W.h = copysign(fmin(fabs(W.h), fabs(tend - W.x)), W.h);
+                    for (int l = 0; l < nv; ++l) W.wt[l] = releps * fabs(W.yy[l]) + abseps;
+                    if (sg_block0<NV>(nv, W, eps)) crashed = true;
+                    else if (W.start) req = 1;
+                    else need_predict = true;
                 }
             }
-            if (stop) {   // summary block (ray_tracing.f90:252-260)
+            if (crashed) {   // iflag = 3: tolerances raised (ode_RAYS.f90:566-575), then SG_ode's test (SG_ode_m.f90:138-149)
+                rel_err = eps * releps;
+                abs_err = eps * abseps;
+                for (int l = 0; l < nv; ++l) v[l] = W.yy[l];
+                s = W.x;
+                const double total_error = fabs(rel_err) + fabs(abs_err);
+                if (total_error > c.SG_error_limit) { flag = RAYS_STOP_ODE_TOTAL_ERROR; stop = true; }
+                else st = SG_DE_BEGIN;           // SG_ode loops: ode again from the current s to sout
+            }
+        }
+        // ---- predictor (convergent for every lane that needs it, whatever state it came from)
+        if (need_predict && !stop) { sg_predict<NV>(nv, W); req = 2; }
+        // ---- derivative evaluation: ONE site for the whole warp
+        if (req && !stop) {
+            const double *u = req == 2 ? W.p : W.yy;
+            double uu[NV], ff[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { uu[i] = i < nv ? u[i] : 0.0; ff[i] = 0.0; }
+            const int code = eqn_ray<T>(uu, ff);
+            my_rhs += 1;
+            if (code) { flag = code; sout = s; stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
+            else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) if (i < nv) W.yp[i] = ff[i];
+                st = req == 1 ? SG_AFTER_R1 : (req == 2 ? SG_AFTER_R2 : SG_AFTER_R3);
+            }
+        }
+        if (stop) {
+            a.stop_code[iray] = flag;
+            if (did_not_start) {   // only npoints, flag and the first point are set (ray_tracing.f90:101-112)
+                a.npoints[iray] = 1;
+                if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
+                if (a.end_residuals) a.end_residuals[iray] = 0.0;
+                if (a.max_residuals) a.max_residuals[iray] = 0.0;
+                if (a.end_ray_parameter) a.end_ray_parameter[iray] = 0.0;
+                if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = 0.0;
+                if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = 0.0;
+            } else {               // summary block (ray_tracing.f90:252-260)
                 a.npoints[iray] = nstep + 1;
-                a.stop_code[iray] = flag;
                 if (a.initial_ray_power) a.initial_ray_power[iray] = pwr;
-                if (a.end_residuals) a.end_residuals[iray] = nstep >= 1 ? resid_prev : 0.0;       // residual(nstep), (X) nstep = 0
-                if (a.max_residuals) a.max_residuals[iray] = nstep >= 1 ? resid_max : -DBL_MAX;   // maxval of an empty array
+                if (a.end_residuals) a.end_residuals[iray] = nstep >= 1 ? resid_prev : 0.0;
+                if (a.max_residuals) a.max_residuals[iray] = nstep >= 1 ? resid_max : -DBL_MAX;
                 if (a.end_ray_parameter) a.end_ray_parameter[iray] = v[6];
                 if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
-                active = false;
-                fin = true; fin_np = nstep + 1;
             }
+            st = SG_IDLE;
+            fin = true; fin_np = did_not_start ? 1 : nstep + 1;
         }
         if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }
     }
-    // ---- per-warp totals -> global counters
-    unsigned long long st = my_steps, rh = my_rhs;
+    unsigned long long stt = my_steps, rh = my_rhs;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
-    if (lane == 0) { atomicAdd(a.counters, st); atomicAdd(a.counters + 1, rh); }
+    for (int o = 16; o > 0; o >>= 1) { stt += __shfl_down_sync(0xffffffffu, stt, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
+    if (lane == 0) { atomicAdd(a.counters, stt); atomicAdd(a.counters + 1, rh); }
 }
 
 // ---- fused RK4 trace kernel ---------------------------------------------------------------------------------

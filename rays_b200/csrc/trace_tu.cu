@@ -24,7 +24,7 @@ template <class T> cudaError_t launch_trace(const TraceArgs &a, int grid, cudaSt
 #if RAYS_TU_ODE == 1
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
 #else
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_kernel<T, kODE>, kTraceBlock, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0);
 #endif
         if (e != cudaSuccess) return e;
     }
@@ -32,7 +32,7 @@ template <class T> cudaError_t launch_trace(const TraceArgs &a, int grid, cudaSt
 #if RAYS_TU_ODE == 1
     trace_rk4_kernel<T><<<grid, kTraceBlock, 0, st>>>(a);
 #else
-    trace_kernel<T, kODE><<<grid, kTraceBlock, 0, st>>>(a);
+    trace_sg_kernel<T><<<grid, kTraceBlock, 0, st>>>(a);
 #endif
     return cudaGetLastError();
 }
