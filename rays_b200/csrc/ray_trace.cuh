@@ -214,7 +214,7 @@ __device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.
 // RHS of all its lanes at ONE place per loop iteration, whatever phase of the integrator each lane is in
 // (the straight transcription called eqn_ray from three divergent sites and ran at 1 % of the FP64 peak).
 // The arithmetic of every piece is the reference's, statement by statement.
-enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3 };
+enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_CHECK, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3 };
 
 // step, first block (:840-852): tests for too small a step / tolerance; returns true on crash
 template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps) {
@@ -222,6 +222,7 @@ template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps)
     if (fabs(W.h) < fouru * fabs(W.x)) { W.h = copysign(fouru * fabs(W.x), W.h); return true; }
     const double p5eps = 0.5 * eps;
     double sum = 0.0;
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) { const double q = W.yy[l] / W.wt[l]; sum = sum + q * q; }
     W.round = twou * sqrt(sum);
     if (p5eps < W.round) { eps = 2.0 * W.round * (1.0 + fouru); return true; }
@@ -234,6 +235,7 @@ template <int NV> RD_INLINE void sg_after_start(int neqn, SGWork<NV> &W, double 
     const double fouru = 4.0 * DBL_EPSILON;
     const double p5eps = 0.5 * eps;
     double tot = 0.0;
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) {
         W.phi[1][l] = W.yp[l]; W.phi[2][l] = 0.0;
         const double q = W.yp[l] / W.wt[l]; tot = tot + q * q;
@@ -247,6 +249,7 @@ template <int NV> RD_INLINE void sg_after_start(int neqn, SGWork<NV> &W, double 
     W.start = false; W.phase1 = true; W.nornd = true;
     if (p5eps <= 100.0 * W.round) {
         W.nornd = false;
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) W.phi[15][l] = 0.0;
     }
 }
@@ -266,6 +269,7 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
         alpha[ns] = 1.0 / (double)ns;
         double temp1 = h * (double)ns;
         sig[nsp1] = 1.0;
+        #pragma unroll 1
         for (int i = nsp1; i <= k; ++i) {
             const double temp2 = psi[i - 1];
             psi[i - 1] = temp1;
@@ -276,38 +280,50 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
         }
         psi[k] = temp1;
         if (ns <= 1) {
+            #pragma unroll 1
             for (int iq = 1; iq <= k; ++iq) { v[iq] = 1.0 / (double)(iq * (iq + 1)); w[iq] = v[iq]; }
         } else {
             if (kold < k) {
                 v[k] = 1.0 / (double)(k * kp1);
+                #pragma unroll 1
                 for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
             }
+            #pragma unroll 1
             for (int iq = 1; iq <= kp1 - ns; ++iq) { v[iq] = v[iq] - alpha[ns] * v[iq + 1]; w[iq] = v[iq]; }
             g[nsp1] = w[1];
         }
+        #pragma unroll 1
         for (int i = ns + 2; i <= kp1; ++i) {
+            #pragma unroll 1
             for (int iq = 1; iq <= kp2 - i; ++iq) w[iq] = w[iq] - alpha[i - 1] * w[iq + 1];
             g[i] = w[1];
         }
     }
     W.ns = ns;
+    #pragma unroll 1
     for (int i = nsp1; i <= k; ++i)
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) phi[i][l] = beta[i] * phi[i][l];
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) { phi[kp2][l] = phi[kp1][l]; phi[kp1][l] = 0.0; W.p[l] = 0.0; }
+    #pragma unroll 1
     for (int j = 1; j <= k; ++j) {
         const int i = kp1 - j;
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) {
             W.p[l] = W.p[l] + phi[i][l] * g[i];
             phi[i][l] = phi[i][l] + phi[i + 1][l];
         }
     }
     if (!W.nornd) {
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) {
             const double tau = h * W.p[l] - phi[15][l];
             W.p[l] = W.yy[l] + tau;
             phi[16][l] = (W.p[l] - W.yy[l]) - tau;
         }
     } else {
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) W.p[l] = W.yy[l] + h * W.p[l];
     }
     W.xold = W.x;
@@ -324,6 +340,7 @@ template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double
     const int k = W.k, kp1 = k + 1, km1 = k - 1, km2 = k - 2;
     const double absh = W.absh, p5eps = 0.5 * eps;
     double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) {
         if (0 < km2) { const double q = (phi[km1][l] + yp[l] - phi[1][l]) / wt[l]; erkm2 = erkm2 + q * q; }
         if (0 <= km2) { const double q = (phi[k][l] + yp[l] - phi[1][l]) / wt[l]; erkm1 = erkm1 + q * q; }
@@ -346,12 +363,14 @@ template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double
         W.kold = k;
         W.hold = h;
         if (!W.nornd) {
+            #pragma unroll 1
             for (int l = 0; l < neqn; ++l) {
                 const double rho = h * g[kp1] * (yp[l] - phi[1][l]) - phi[16][l];
                 W.yy[l] = W.p[l] + rho;
                 phi[15][l] = (W.yy[l] - W.p[l]) - rho;
             }
         } else {
+            #pragma unroll 1
             for (int l = 0; l < neqn; ++l) W.yy[l] = W.p[l] + h * g[kp1] * (yp[l] - phi[1][l]);
         }
         return 0;
@@ -359,8 +378,11 @@ template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double
     // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
     W.phase1 = false;
     W.x = W.xold;
+    #pragma unroll 1
     for (int i = 1; i <= k; ++i)
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) phi[i][l] = (phi[i][l] - phi[i + 1][l]) / W.beta[i];
+    #pragma unroll 1
     for (int i = 2; i <= k; ++i) W.psi[i - 1] = W.psi[i] - W.h;
     W.ifail = W.ifail + 1;
     double temp2 = 0.5;
@@ -384,11 +406,14 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
     const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.knew, ns = W.ns;
     const double absh = W.absh, p5eps = 0.5 * eps, h = W.h, erkm1 = W.erkm1;
     double erk = W.erk;
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) {
         phi[kp1][l] = yp[l] - phi[1][l];
         phi[kp2][l] = phi[kp1][l] - phi[kp2][l];
     }
+    #pragma unroll 1
     for (int i = 1; i <= k; ++i)
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) phi[i][l] = phi[i][l] + phi[kp1][l];
     double erkp1 = 0.0;
     if (knew == km1 || k == 12) W.phase1 = false;
@@ -397,6 +422,7 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
     } else if (knew == km1) {
         k = km1; erk = erkm1;
     } else if (kp1 <= ns) {
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) { const double q = phi[kp2][l] / wt[l]; erkp1 = erkp1 + q * q; }
         erkp1 = absh * kSGgstr[kp1] * sqrt(erkp1);
         if (k == 1) {
@@ -428,23 +454,30 @@ template <int NV> RD_INLINE void sg_intrp(int neqn, const SGWork<NV> &W, double 
     double g[14], rho[14], w[14];
     const double hi = xout - W.x;
     const int ki = W.kold + 1;
+    #pragma unroll 1
     for (int i = 1; i <= ki; ++i) w[i] = 1.0 / (double)i;
     g[1] = 1.0; rho[1] = 1.0;
     double term = 0.0;
+    #pragma unroll 1
     for (int j = 2; j <= ki; ++j) {
         const double psijm1 = W.psi[j - 1];
         const double gamma = (hi + term) / psijm1;
         const double eta = hi / psijm1;
+        #pragma unroll 1
         for (int i = 1; i <= ki + 1 - j; ++i) w[i] = gamma * w[i] - eta * w[i + 1];
         g[j] = w[1];
         rho[j] = gamma * rho[j - 1];
         term = psijm1;
     }
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) yout[l] = 0.0;
+    #pragma unroll 1
     for (int j = 1; j <= ki; ++j) {
         const int i = ki + 1 - j;
+        #pragma unroll 1
         for (int l = 0; l < neqn; ++l) yout[l] = yout[l] + g[i] * W.phi[i][l];
     }
+    #pragma unroll 1
     for (int l = 0; l < neqn; ++l) yout[l] = W.yy[l] + hi * yout[l];
 }
 
@@ -619,6 +652,8 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
     size_t row = 0;
     bool fin = false;
     int fin_np = 0;
+    bool have_f1 = false;     // W.yp holds the derivative at v evaluated together with check_save
+    int f1_code = 0;
 
     for (;;) {
         // ---- refill from the work queue (one atomic per warp)
@@ -645,7 +680,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                     }
                     if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
                     if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                    st = SG_CHECK; first = true;
+                    st = SG_CHECK; first = true; have_f1 = false;
                 }
             }
         }
@@ -655,43 +690,15 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
         }
         bool stop = false, did_not_start = false;
 
-        // ---- check_save of a new point + top of the trajectory loop (convergent: same code for every lane in SG_CHECK)
-        if (st == SG_CHECK) {
-            double resid = 0.0;
-            check_save<T>(v, resid, stop, flag);
-            if (stop) did_not_start = first;
-            else {
-                if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
-                    nstep = nstep + 1;
-                    if (a.ray_vec) {
-                        double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
-                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
-                    }
-                    if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
-                    resid_prev = resid_last;
-                    resid_last = resid;
-                    if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
-                    if (binning) {
-                        const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
-                        bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
-                        dep_x = xn; dep_Q = Qn;
-                    }
-                    ++my_steps;
-                } else if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
-                first = false;
-                s = sout;
-                sout = sout + c.ds;
-                if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
-                else if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; }
-                else st = SG_DE_BEGIN;
-            }
-        }
-
+        // Lanes run free: each is in its own integrator phase (measured lane utilisation 34 %).  Re-synchronising the
+        // warp at segment boundaries was tried and is 2x slower: segments differ too much in internal step count.
         // ---- lane-private integrator bookkeeping up to the next derivative evaluation
-        int req = 0;               // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy
+        int req = 0;               // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
+                                   // 4: check_save of the new point v + the start derivative of the next segment there
         bool need_predict = false, de_top = false, crashed = false;
         if (!stop) {
-            if (st == SG_DE_BEGIN) {   // ode/de entry with iflag = 1 (ode_RAYS.f90:425-505)
+            if (st == SG_CHECK) req = 4;
+            else if (st == SG_DE_BEGIN || st == SG_AFTER_CHECK) {   // ode/de entry with iflag = 1 (ode_RAYS.f90:425-505)
                 t = s;
                 if (t == sout) { stop = true; flag = RAYS_STOP_SG_T_EQ_TOUT; }
                 else if (rel_err < 0.0 || abs_err < 0.0) { stop = true; flag = RAYS_STOP_SG_BAD_TOL; }
@@ -734,6 +741,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                     sg_intrp<NV>(nv, W, sout, v);
                     s = sout;
                     st = SG_CHECK;
+                    req = 4;
                 } else if (maxnum <= nostep) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
                     flag = stiff ? RAYS_STOP_SG_STIFF : RAYS_STOP_SG_MAXNUM;
                     for (int l = 0; l < nv; ++l) v[l] = W.yy[l];
@@ -743,8 +751,14 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                     W.h = copysign(fmin(fabs(W.h), fabs(tend - W.x)), W.h);
                     for (int l = 0; l < nv; ++l) W.wt[l] = releps * fabs(W.yy[l]) + abseps;
                     if (sg_block0<NV>(nv, W, eps)) crashed = true;
-                    else if (W.start) req = 1;
-                    else need_predict = true;
+                    else if (W.start) {
+                        if (have_f1) {   // the start derivative was evaluated together with check_save at this very point
+                            have_f1 = false;
+                            my_rhs += 1;
+                            if (f1_code) { flag = f1_code; sout = s; stop = true; }
+                            else { sg_after_start<NV>(nv, W, eps); need_predict = true; }
+                        } else req = 1;
+                    } else need_predict = true;
                 }
             }
             if (crashed) {   // iflag = 3: tolerances raised (ode_RAYS.f90:566-575), then SG_ode's test (SG_ode_m.f90:138-149)
@@ -759,19 +773,84 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
         }
         // ---- predictor (convergent for every lane that needs it, whatever state it came from)
         if (need_predict && !stop) { sg_predict<NV>(nv, W); req = 2; }
-        // ---- derivative evaluation: ONE site for the whole warp
+        // ---- equilibrium + derivative evaluation: ONE site for the whole warp.  A lane with req = 4 also runs
+        // check_save on the same equilibrium (the reference evaluates it twice at this point: check_save.f90:38
+        // and eqn_ray.f90:87 of the next segment's first derivative), saves the point and runs the loop-top tests.
         if (req && !stop) {
-            const double *u = req == 2 ? W.p : W.yy;
+            const double *u = req == 2 ? W.p : (req == 4 ? v : W.yy);
             double uu[NV], ff[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) { uu[i] = i < nv ? u[i] : 0.0; ff[i] = 0.0; }
-            const int code = eqn_ray<T>(uu, ff);
-            my_rhs += 1;
-            if (code) { flag = code; sout = s; stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
-            else {
+            Eq<NSM> e;
+            equilibrium<T::EQ, T::NS, true>(uu[0], uu[1], uu[2], e);
+            double dddx[3], dddk[3], dddw = 0.0;
+            bool have_derivs = false;
+            if (req == 4) {
+                double resid = 0.0;
+                if (e.err) {
+                    flag = e.err;
+                    if (T::damp() && v[7] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+                } else {
+                    check_save_resid<T>(e, uu, resid, stop, flag);
+                    double dddw_cold;
+                    if (T::DERIV == RAYS_DERIV_COLD) {
+                        ray_derivs<T>(e, uu, dddx, dddk, dddw);
+                        have_derivs = true;
+                        dddw_cold = dddw;
+                    } else {
+                        const Rcp K0 = g_dc.rc_k0;
+                        const double nvec[3] = {qdiv(uu[3], K0), qdiv(uu[4], K0), qdiv(uu[5], K0)};
+                        double tx[3], tk[3];
+                        deriv_cold<T::NS>(e, nvec, tx, tk, dddw_cold);
+                    }
+                    check_save_tail<T>(uu, dddw_cold, stop, flag);
+                }
+                if (stop) did_not_start = first;
+                else {
+                    if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
+                        nstep = nstep + 1;
+                        if (a.ray_vec) {
+                            double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
+                            if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                        }
+                        if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
+                        resid_prev = resid_last;
+                        resid_last = resid;
+                        if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
+                        if (binning) {
+                            const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
+                            bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
+                            dep_x = xn; dep_Q = Qn;
+                        }
+                        ++my_steps;
+                    } else if (binning) { dep_x = dep_abscissa<T::EQ>(v); dep_Q = v[7] * pwr; }
+                    first = false;
+                    s = sout;                       // top of the trajectory loop (ray_tracing.f90:118-172)
+                    sout = sout + c.ds;
+                    if (sout > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
+                    else if (nstep + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; }
+                }
+            }
+            if (!stop) {
+                int code = e.err;
+                if (!code && !have_derivs) code = ray_derivs<T>(e, uu, dddx, dddk, dddw);
+                if (!code) code = ray_equations<T>(e, uu, dddx, dddk, dddw, ff);
+                if (req == 4) {          // keep it for the start of the next segment (consumed after de's entry tests)
+                    have_f1 = true; f1_code = code;
+                    if (!code) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i) if (i < nv) W.yp[i] = ff[i];
-                st = req == 1 ? SG_AFTER_R1 : (req == 2 ? SG_AFTER_R2 : SG_AFTER_R3);
+                        for (int i = 0; i < NV; ++i) if (i < nv) W.yp[i] = ff[i];
+                    }
+                    st = SG_AFTER_CHECK;
+                } else {
+                    my_rhs += 1;
+                    if (code) { flag = code; sout = s; stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
+                    else {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) if (i < nv) W.yp[i] = ff[i];
+                        st = req == 1 ? SG_AFTER_R1 : (req == 2 ? SG_AFTER_R2 : SG_AFTER_R3);
+                    }
+                }
             }
         }
         if (stop) {
