@@ -21,6 +21,23 @@ def init_case(name: str, **ode):
     return rb.host_cfg()
 
 
+def init_case_text(name: str, edits, tmpdir, **ode):
+    """like init_case, but with (old, new) text substitutions applied to the namelist first"""
+    import os
+    txt = open(rb.config_path(name)).read()
+    for old, new in edits:
+        assert old in txt, old
+        txt = txt.replace(old, new)
+    p = os.path.join(str(tmpdir), "rays.in")
+    open(p, "w").write(txt)
+    L = _abi.load()
+    rc = L.rays_host_initialize(p.encode(), 0)
+    assert rc == 0, L.rays_host_last_error()
+    if ode:
+        rb.set_ode(**ode)
+    return rb.host_cfg()
+
+
 def launch_params():
     L = _abi.load()
     sl, so, ax = _abi.SlabLaunch(), _abi.SolovevLaunch(), _abi.AxisymLaunch()

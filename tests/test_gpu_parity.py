@@ -9,7 +9,7 @@ import pytest
 
 import rays_b200 as rb
 import _oracle as orc
-from _cases import init_case, oracle_fan, vec_rel_err
+from _cases import init_case, init_case_text, oracle_fan, vec_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -202,3 +202,110 @@ def test_exact_arithmetic_helpers_on_device():
     assert L.rays_b200_selftest_arith(1 << 30, 20260101, mm) == 0
     assert list(mm)[:3] == [0, 0, 0], list(mm)
     assert mm[3] < 1000      # all-ones-significand divisors (forced by the adversarial modes): the documented exception
+
+
+# ---- generic kernels: species counts other than electron + one ion, per-species damping slots -----------
+THREE_SPECIES = [(" spec_name(1) = 'deuterium',", " spec_name(1) = 'deuterium',\n spec_name(2) = 'tritium',\n spec_model(2) = 'cold',\n t0s_eV(2)=1.0e2 ,\n eta(2)=0.5"),
+                 (" eta(1)=1.", " eta(1)=0.5"), ("t_prof_model=2*'zero'", "t_prof_model=3*'zero'")]
+ELECTRONS_ONLY = [(" eta(1)=1.", " eta(1)=0."), (" neutrality", " neutrality")]
+
+
+@pytest.mark.parametrize("deriv", ["cold", "numerical"])
+def test_three_species_generic_kernel_bitwise(deriv, tmp_path):
+    cfg = init_case_text("solovev_ECH_90GHz_plus_root.in", THREE_SPECIES, tmp_path, ode_solver_name="RK4_ODE", ray_deriv_name=deriv,
+                         nstep_max=200, ds=5e-11)
+    assert cfg.nspec == 2
+    r, n, w, _, _ = oracle_fan(cfg, n_theta_launch=3, theta_launch0=-0.3, dtheta_launch=0.3, n_rindex_theta=3, rindex_theta0=-0.2,
+                               delta_rindex_theta=0.2, n_rindex_phi=8, rindex_phi0=0.05, delta_rindex_phi=0.05)
+    assert r.shape[0] > 32
+    g, o = _run_both(cfg, r, n, w)
+    assert "generic" in rb.last_trace_stats()["kernel"]
+    _compare_traces(g, o, cfg, 1e-10, bitwise=True)
+
+
+def test_three_species_generic_sg(tmp_path):
+    cfg = init_case_text("solovev_ECH_90GHz_plus_root.in", THREE_SPECIES, tmp_path, nstep_max=100, ds=5e-11, rel_err0=1e-6, abs_err0=1e-6,
+                         SG_error_limit=0.1)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_phi=8, rindex_phi0=0.05, delta_rindex_phi=0.05)
+    g, o = _run_both(cfg, r, n, w)
+    assert "generic" in rb.last_trace_stats()["kernel"]
+    _compare_traces(g, o, cfg, 1e-6, bitwise=False)
+
+
+def test_multi_species_damping_generic_kernel(tmp_path):
+    cfg = init_case_text("axisym_deposition_fan.in", [("multi_spec_damping = .false.", "multi_spec_damping = .true.")], tmp_path, nstep_max=300)
+    assert cfg.nv == 10 and cfg.multi_spec_damping == 1
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=4, delta_rindex_theta=0.1, n_rindex_phi=8, delta_rindex_phi=0.04)
+    g, o = _run_both(cfg, r, n, w)
+    assert "generic" in rb.last_trace_stats()["kernel"]
+    _compare_traces(g, o, cfg, 1e-10, bitwise=False)
+    fin = np.isfinite(o.end_ray_vec).all(axis=1)
+    assert np.allclose(g.end_ray_vec[fin, 8], o.end_ray_vec[fin, 8], rtol=1e-10, atol=1e-14)      # electron slot = total
+    assert np.all(o.end_ray_vec[fin, 9] == 0.0) and np.all(g.end_ray_vec[fin, 9] == 0.0)           # ions absorb nothing in this model
+
+
+def test_launch_fans_on_device_match_the_oracle():
+    """row f1: the device launch-fan kernels + order-preserving compaction against the oracle's launchers"""
+    from _cases import launch_params
+    cfg = init_case("solovev_fan_1M.in")
+    _, so, _ = launch_params()
+    so.n_r_launch, so.n_theta_launch, so.n_rindex_theta, so.n_rindex_phi = 3, 5, 16, 16
+    so.rindex_phi0, so.delta_rindex_phi = 0.05, 0.08       # the upper end of the grid is evanescent: candidates get dropped
+    ro, no, wo = orc.launch_fan(cfg, "solovev", so, 4096)
+    rb.set_config(cfg)
+    k = rb.launch_fan("solovev", so)
+    assert k == ro.shape[0] and 0 < k <= 3 * 5 * 256
+    rg, ng, wg = rb.fan_download(k)
+    assert np.array_equal(rg, ro) and np.array_equal(ng, no) and np.array_equal(wg, wo)
+    # slab
+    cfg = init_case("slab_ECH_90GHz_case_1.in")
+    sl, _, _ = launch_params()
+    sl.n_kz_launch, sl.delta_rindex_z0, sl.n_ky_launch, sl.delta_rindex_y0, sl.n_x_launch, sl.dx_launch = 40, 0.03, 5, 0.1, 3, 0.05
+    ro, no, wo = orc.launch_fan(cfg, "slab", sl, 4096)
+    rb.set_config(cfg)
+    k = rb.launch_fan("slab", sl)
+    assert k == ro.shape[0] and 0 < k < 600
+    rg, ng, wg = rb.fan_download(k)
+    assert np.array_equal(rg, ro) and np.array_equal(ng, no) and np.array_equal(wg, wo)
+    # axisym
+    cfg = init_case("axisym_deposition_fan.in")
+    _, _, ax = launch_params()
+    ax.n_rindex_theta, ax.n_rindex_phi, ax.delta_rindex_theta, ax.delta_rindex_phi = 24, 24, 0.03, 0.05
+    ro, no, wo = orc.launch_fan(cfg, "axisym", ax, 4096)
+    rb.set_config(cfg)
+    k = rb.launch_fan("axisym", ax)
+    assert k == ro.shape[0]
+    rg, ng, wg = rb.fan_download(k)
+    assert np.array_equal(rg, ro) and np.array_equal(ng, no) and np.array_equal(wg, wo)
+    # file_input / n(theta): acos + cos are libm -> rounding-level agreement
+    cfg = init_case("mpex/rays.in")
+    r11, n11, w11, _, _ = oracle_fan(cfg)
+    import ctypes as C
+    from rays_b200 import _abi
+    L = _abi.load()
+    rin, nin = _abi.c_double_p(), _abi.c_double_p()
+    kk = L.rays_host_directions_in(C.byref(rin), C.byref(nin))
+    rb.set_config(cfg)
+    k = rb.launch_fan_directions(np.ctypeslib.as_array(rin, (kk, 3)).copy(), np.ctypeslib.as_array(nin, (kk, 3)).copy())
+    assert k == 11
+    rg, ng, _ = rb.fan_download(k)
+    assert np.array_equal(rg, r11) and np.allclose(ng, n11, rtol=1e-13, atol=0)
+
+
+def test_host_mirror_program_flow(tmp_path):
+    """initialize(read_input) -> trace_rays -> finalize_run through the host mirror, fan built on the device"""
+    from scipy.io import netcdf_file
+    rb.initialize(rb.config_path("mpex/rays.in"), ray_init=True, device=0)
+    rb.trace_rays()
+    res = rb.results()
+    assert res["nray"] == 11 and all(f.strip() == "nstep > nstep_max" for f in res["ray_stop_flag"])
+    cfg = rb.host_cfg()
+    r, n, w = rb.get_fan()
+    o, st, _ = orc.trace(cfg, r, n, w)
+    assert np.array_equal(res["npoints"], o.npoints)
+    assert vec_rel_err(res["ray_vec"][:, :, 0:3], o.ray_vec[:, :, 0:3]) <= 1e-10
+    rb.finalize_run(str(tmp_path))
+    f = netcdf_file(str(tmp_path / "run_results.2nd_harm_11_rays_nx.nc"), "r", mmap=False)
+    assert f.variables["ray_vec"].shape == (11, 501, 12)
+    assert np.array_equal(np.array(f.variables["ray_vec"].data), res["ray_vec"])
+    f.close()
