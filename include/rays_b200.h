@@ -254,6 +254,9 @@ int rays_b200_last_trace_stats(double *kernel_ms, int64_t *ray_steps, int32_t *n
 /* RHS evaluations of the last trace (SG accounting), the kernel specialisation that ran, its grid and
  * resident CTAs per SM (for profiles/ and bench.py) */
 int rays_b200_last_trace_info(int64_t *rhs_evals, char *kernel_name, int name_len, int32_t *grid, int32_t *blocks_per_sm);
+/* Kernel time of the last trace (ms, CUDA events): the first pass over the fan and the resume passes over the
+ * rays the first pass suspended (time slicing packs the long rays into full warps), and the number of passes */
+int rays_b200_last_trace_breakdown(double *first_pass_ms, double *resume_pass_ms, int32_t *n_passes);
 /* sharding helper: keep rays iray with iray % world == rank */
 int rays_b200_fan_shard(int rank, int world);
 

@@ -253,8 +253,11 @@ def last_trace_stats() -> dict:
     rhs, grid, bps = C.c_int64(0), C.c_int32(0), C.c_int32(0)
     name = C.create_string_buffer(96)
     L.rays_b200_last_trace_info(C.byref(rhs), name, 96, C.byref(grid), C.byref(bps))
+    first, resume, npass = C.c_double(0), C.c_double(0), C.c_int32(0)
+    L.rays_b200_last_trace_breakdown(C.byref(first), C.byref(resume), C.byref(npass))
     return dict(kernel_ms=ms.value, ray_steps=steps.value, n_launches=nl.value, rhs_evals=rhs.value, kernel=name.value.decode(),
-                grid=grid.value, blocks_per_sm=bps.value)
+                grid=grid.value, blocks_per_sm=bps.value, first_pass_ms=first.value, resume_pass_ms=resume.value, n_passes=npass.value,
+                trace_kernel_ms=first.value + resume.value)
 
 
 def results_download(nray: int, nv: int, npoints_alloc: int, store: bool = True) -> ResultArrays:

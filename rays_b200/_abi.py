@@ -131,7 +131,7 @@ ABI_SYMBOLS = [
     "rays_b200_fan_download", "rays_b200_deposition", "rays_b200_trace_device_binned",
     "rays_b200_probe_equilibrium", "rays_b200_probe_rhs", "rays_b200_probe_check_save",
     "rays_b200_fp64_peak", "rays_b200_host_alloc", "rays_b200_host_free", "rays_b200_stream", "rays_b200_version",
-    "rays_b200_struct_sizes", "rays_b200_selftest_arith",
+    "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown",
 ]
 HOST_SYMBOLS = [
     "rays_host_initialize", "rays_host_trace_rays", "rays_host_finalize_run", "rays_host_deallocate", "rays_host_last_error",
@@ -180,6 +180,7 @@ def load() -> C.CDLL:
         "rays_b200_fp64_peak": (i, [P(dbl), P(dbl)]), "rays_b200_host_alloc": (i, [P(vp), C.c_size_t]), "rays_b200_host_free": (i, [vp]),
         "rays_b200_stream": (vp, []), "rays_b200_version": (i, []), "rays_b200_struct_sizes": (i, [P(C.c_int32), i]),
         "rays_b200_selftest_arith": (i, [i64, C.c_uint64, P(i64)]),
+        "rays_b200_last_trace_breakdown": (i, [P(dbl), P(dbl), P(C.c_int32)]),
         "rays_host_initialize": (i, [cp, i]), "rays_host_trace_rays": (i, []), "rays_host_finalize_run": (i, [cp]),
         "rays_host_deallocate": (i, []), "rays_host_last_error": (cp, []), "rays_host_cfg": (P(Cfg), []),
         "rays_host_nspec": (i, []), "rays_host_run_label": (cp, []), "rays_host_ray_init_model": (cp, []),

@@ -500,6 +500,17 @@ struct TraceArgs {
     int *stop_code;                 // [nray]
     double *initial_ray_power, *end_residuals, *max_residuals, *end_ray_parameter;  // [nray]
     double *start_ray_vec, *end_ray_vec;   // [nray][nv]
+    const int *order;               // optional: queue position -> ray index (resume list / explicit schedule)
+    // Time slicing.  Ray lengths are very unequal (3.4 % of the bench fan runs 5x the mean) and the long rays
+    // are scattered over all warps, so after the queue empties every warp would crawl on with one or two live
+    // lanes (measured: 19 % of all lane slots idle).  With slice_steps > 0 a ray that has taken that many steps
+    // in this launch is suspended: its state goes to cont_state[iray], its index to cont_list; the host then
+    // launches the kernel again over that list (resume = 1), where the survivors are packed into full warps.
+    int slice_steps;
+    int resume;
+    double *cont_state;             // [nray][kContStride]
+    int *cont_list;
+    unsigned long long *cont_count;
     unsigned long long *queue;      // next ray index to hand out
     unsigned long long *counters;   // [0] ray-steps, [1] RHS evaluations
     // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_bins == NULL disables it
@@ -573,6 +584,7 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 }
 
 constexpr int kTraceBlock = 128;
+constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, resid_prev/last/max, dep_x, dep_Q, rel_err, abs_err
 
 // one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the
 // 256-byte coalesced stores, so that the copy is bandwidth- rather than latency-bound (a 13 KB ray takes ~7
@@ -589,10 +601,29 @@ RD_INLINE void copy_row_to_host(double *__restrict__ dst, const double *__restri
     for (; i < n; i += 32) dst[i] = __ldcg(src + i);
 }
 
+// suspended-ray record (time slicing): everything a lane needs to carry on with the ray in a later launch
+struct RayCarry { double s, sout, resid_prev, resid_last, resid_max, dep_x, dep_Q, rel_err, abs_err; int nstep, flag; };
+RD_INLINE void suspend_ray(const TraceArgs &a, long long iray, const double *v, int nv, const RayCarry &c) {
+    double *r = a.cont_state + (size_t)iray * kContStride;
+    for (int i = 0; i < nv; ++i) r[i] = v[i];
+    double *q = r + RAYS_NV_MAX;
+    q[0] = c.s; q[1] = c.sout; q[2] = (double)c.nstep; q[3] = (double)c.flag; q[4] = c.resid_prev; q[5] = c.resid_last;
+    q[6] = c.resid_max; q[7] = c.dep_x; q[8] = c.dep_Q; q[9] = c.rel_err; q[10] = c.abs_err;
+    const unsigned long long pos = atomicAdd(a.cont_count, 1ULL);
+    a.cont_list[pos] = (int)iray;
+}
+RD_INLINE void resume_ray(const TraceArgs &a, long long iray, double *v, int nv, RayCarry &c) {
+    const double *r = a.cont_state + (size_t)iray * kContStride;
+    for (int i = 0; i < nv; ++i) v[i] = r[i];
+    const double *q = r + RAYS_NV_MAX;
+    c.s = q[0]; c.sout = q[1]; c.nstep = (int)q[2]; c.flag = (int)q[3]; c.resid_prev = q[4]; c.resid_last = q[5];
+    c.resid_max = q[6]; c.dep_x = q[7]; c.dep_Q = q[8]; c.rel_err = q[9]; c.abs_err = q[10];
+}
+
 // Warp-cooperative copy-out of the rays that ended in this iteration: every lane of the warp moves a
 // slice of each finished ray's staged trajectory (HBM/L2) to the caller's arrays in pinned host memory,
 // 256-byte coalesced stores over PCIe, overlapped with the integration of the other rays.
-RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long iray, int npts, size_t row, int nv, unsigned lane) {
+RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long iray, int npts, int p0, size_t row, int nv, unsigned lane) {
     unsigned m = __ballot_sync(0xffffffffu, finished);
     if (m == 0u || a.host_ray_vec == nullptr && a.host_residual == nullptr) return;
     __syncwarp();   // orders the finished lanes' trajectory stores before the other lanes' loads
@@ -600,16 +631,17 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
         const int l = __ffs(m) - 1;
         m &= m - 1;
         const long long ir = __shfl_sync(0xffffffffu, iray, l);
-        const int np = __shfl_sync(0xffffffffu, npts, l);
+        const int np = __shfl_sync(0xffffffffu, npts, l);          // points staged in this lane's row ...
+        const int pf = __shfl_sync(0xffffffffu, p0, l);            // ... the first of which is point pf of the ray
         const unsigned long long rw = __shfl_sync(0xffffffffu, (unsigned long long)row, l);
         if (a.host_ray_vec) {
             const double *src = a.ray_vec + (size_t)rw * a.npoints_alloc * nv;
-            double *dst = a.host_ray_vec + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc * nv;
+            double *dst = a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv;
             copy_row_to_host(dst, src, np * nv, lane);
         }
         if (a.host_residual) {
             const double *src = a.residual + (size_t)rw * a.npoints_alloc;
-            double *dst = a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc;
+            double *dst = a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf;
             copy_row_to_host(dst, src, np, lane);
         }
     }
@@ -652,6 +684,8 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
     size_t row = 0;
     bool fin = false;
     int fin_np = 0;
+    int p0 = 0;          // index (within the ray) of the first point staged in this lane's row (streaming + resume)
+    int slice_n = 0;     // steps this ray has taken in this launch
     bool have_f1 = false;     // W.yp holds the derivative at v evaluated together with check_save
     int f1_code = 0;
 
@@ -667,20 +701,30 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                 const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
                 if (idx >= a.nray) exhausted = true;
                 else {
-                    iray = idx;
+                    iray = a.order ? (long long)a.order[idx] : idx;
                     row = streaming ? slot : (size_t)iray;
-                    nstep = 0; s = 0.0; sout = 0.0; flag = 0;
-                    rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
-                    resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
-                    initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
                     pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
-                    if (a.ray_vec) {
-                        double *dst = a.ray_vec + row * a.npoints_alloc * nv;
-                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                    slice_n = 0; have_f1 = false; st = SG_CHECK;
+                    if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
+                        RayCarry k;
+                        resume_ray(a, iray, v, nv, k);
+                        s = k.s; sout = k.sout; nstep = k.nstep; flag = k.flag; resid_prev = k.resid_prev; resid_last = k.resid_last;
+                        resid_max = k.resid_max; dep_x = k.dep_x; dep_Q = k.dep_Q; rel_err = k.rel_err; abs_err = k.abs_err;
+                        first = false;
+                        p0 = streaming ? nstep + 1 : 0;
+                    } else {
+                        nstep = 0; s = 0.0; sout = 0.0; flag = 0; p0 = 0;
+                        rel_err = c.rel_err0; abs_err = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
+                        resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
+                        initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                        if (a.ray_vec) {
+                            double *dst = a.ray_vec + row * a.npoints_alloc * nv;
+                            if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                        }
+                        if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
+                        if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                        first = true;
                     }
-                    if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
-                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                    st = SG_CHECK; first = true; have_f1 = false;
                 }
             }
         }
@@ -741,7 +785,13 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                     sg_intrp<NV>(nv, W, sout, v);
                     s = sout;
                     st = SG_CHECK;
-                    req = 4;
+                    ++slice_n;
+                    if (a.slice_steps > 0 && slice_n >= a.slice_steps) {   // suspend: packed into full warps by the next launch
+                        RayCarry k{s, sout, resid_prev, resid_last, resid_max, dep_x, dep_Q, rel_err, abs_err, nstep, flag};
+                        suspend_ray(a, iray, v, nv, k);
+                        st = SG_IDLE;
+                        fin = true; fin_np = nstep + 1 - p0;
+                    } else req = 4;
                 } else if (maxnum <= nostep) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
                     flag = stiff ? RAYS_STOP_SG_STIFF : RAYS_STOP_SG_MAXNUM;
                     for (int l = 0; l < nv; ++l) v[l] = W.yy[l];
@@ -810,10 +860,10 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                     if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
                         nstep = nstep + 1;
                         if (a.ray_vec) {
-                            double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
+                            double *dst = a.ray_vec + (row * a.npoints_alloc + (nstep - p0)) * nv;
                             if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                         }
-                        if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
+                        if (a.residual) a.residual[row * a.npoints_alloc + (nstep - p0)] = resid;
                         resid_prev = resid_last;
                         resid_last = resid;
                         if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
@@ -872,9 +922,9 @@ __global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a
                 if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
             }
             st = SG_IDLE;
-            fin = true; fin_np = did_not_start ? 1 : nstep + 1;
+            fin = true; fin_np = did_not_start ? 1 : nstep + 1 - p0;
         }
-        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }
+        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, p0, row, nv, lane); fin = false; }
     }
     unsigned long long stt = my_steps, rh = my_rhs;
 #pragma unroll
@@ -915,8 +965,10 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kern
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
     const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t row = 0;
-    bool fin = false;      // this lane's ray ended in the current iteration
+    bool fin = false;      // this lane's ray ended (or was suspended) in the current iteration
     int fin_np = 0;
+    int p0 = 0;          // index (within the ray) of the first point staged in this lane's row (streaming + resume)
+    int slice_n = 0;     // steps this ray has taken in this launch
 
     for (;;) {
         // ---- refill from the work queue (one atomic per warp)
@@ -930,19 +982,29 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kern
                 const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
                 if (idx >= a.nray) exhausted = true;
                 else {
-                    iray = idx;
+                    iray = a.order ? (long long)a.order[idx] : idx;
                     row = streaming ? slot : (size_t)iray;
-                    nstep = 0; s = 0.0; sout = 0.0; flag = 0;
-                    resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
-                    initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
                     pwr = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
-                    if (a.ray_vec) {
-                        double *dst = a.ray_vec + row * a.npoints_alloc * nv;
-                        if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                    slice_n = 0; active = true;
+                    if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
+                        RayCarry k;
+                        resume_ray(a, iray, v, nv, k);
+                        s = k.s; sout = k.sout; nstep = k.nstep; flag = k.flag; resid_prev = k.resid_prev; resid_last = k.resid_last;
+                        resid_max = k.resid_max; dep_x = k.dep_x; dep_Q = k.dep_Q;
+                        first = false;
+                        p0 = streaming ? nstep + 1 : 0;
+                    } else {
+                        nstep = 0; s = 0.0; sout = 0.0; flag = 0; p0 = 0;
+                        resid_prev = 0.0; resid_last = 0.0; resid_max = 0.0;
+                        initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                        if (a.ray_vec) {
+                            double *dst = a.ray_vec + row * a.npoints_alloc * nv;
+                            if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                        }
+                        if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
+                        if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                        first = true;
                     }
-                    if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
-                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                    active = true; first = true;
                 }
             }
         }
@@ -990,10 +1052,10 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kern
                     if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
                         nstep = nstep + 1;
                         if (a.ray_vec) {
-                            double *dst = a.ray_vec + (row * a.npoints_alloc + nstep) * nv;
+                            double *dst = a.ray_vec + (row * a.npoints_alloc + (nstep - p0)) * nv;
                             if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                         }
-                        if (a.residual) a.residual[row * a.npoints_alloc + nstep] = resid;
+                        if (a.residual) a.residual[row * a.npoints_alloc + (nstep - p0)] = resid;
                         resid_prev = resid_last;
                         resid_last = resid;
                         if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
@@ -1034,6 +1096,13 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kern
 #pragma unroll
                 for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + qdiv(h * acc[i], g_dc.rc_six);
                 s = sout;
+                ++slice_n;
+                if (a.slice_steps > 0 && slice_n >= a.slice_steps) {   // suspend: packed into full warps by the next launch
+                    RayCarry k{s, sout, resid_prev, resid_last, resid_max, dep_x, dep_Q, 0.0, 0.0, nstep, flag};
+                    suspend_ray(a, iray, v, nv, k);
+                    active = false;
+                    fin = true; fin_np = nstep + 1 - p0;
+                }
             } else {
                 if (code) flag = code;
                 a.stop_code[iray] = flag;
@@ -1054,10 +1123,10 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kern
                     if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = v[i];
                 }
                 active = false;
-                fin = true; fin_np = did_not_start ? 1 : nstep + 1;
+                fin = true; fin_np = did_not_start ? 1 : nstep + 1 - p0;
             }
         }
-        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, row, nv, lane); fin = false; }
+        if (streaming) { flush_finished_rays(a, fin, iray, fin_np, p0, row, nv, lane); fin = false; }
     }
     unsigned long long st = my_steps, rh = my_rhs;
 #pragma unroll

@@ -78,6 +78,16 @@ struct Ctx {
     DevBuf<double> ray_vec, residual, pwr, endres, maxres, endpar, startv, endv;
     DevBuf<int> npoints, stop;
     DevBuf<unsigned long long> queue;   // [0] queue, [1] ray-steps, [2] RHS evaluations
+    // time slicing: suspended-ray records and the two resume lists
+    DevBuf<double> cont_state;
+    DevBuf<int> cont_list[2];
+    double last_first_ms = 0, last_resume_ms = 0;
+    int last_phases = 0;
+    cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
+    bool main_pending = false, main_is_resume = false;
+    int cached_bps = 0;
+    const char *cached_name = "";
+    const void *cached_ops = nullptr;
     // deposition
     DevBuf<double> dep;
     int dep_bins = 0;
@@ -245,7 +255,7 @@ int ensure_results(long long nray, int nv, int npa, bool traj) {
     CK(g.endpar.reserve((size_t)nray));
     CK(g.startv.reserve((size_t)nray * nv));
     CK(g.endv.reserve((size_t)nray * nv));
-    CK(g.queue.reserve(4));
+    CK(g.queue.reserve(8));
     if (traj) {
         CK(g.ray_vec.reserve((size_t)nray * npa * nv));
         CK(g.residual.reserve((size_t)nray * npa));
@@ -282,10 +292,13 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     a.counters = g.queue.p + 1;
     a.dep_bins = binned ? g.dep.p : nullptr;
     a.n_bins = g.dep_bins; a.grid_min = g.dep_min; a.grid_max = g.dep_max;
-    int bps = 0;
-    const char *name = "";
-    CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name));
-    if (bps < 1) bps = 1;
+    int bps = g.cached_bps;
+    const char *name = g.cached_name;
+    if (bps <= 0 || g.cached_ops != ops) {   // occupancy of the selected specialisation: queried once per configuration
+        CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name));
+        if (bps < 1) bps = 1;
+        g.cached_bps = bps; g.cached_name = name; g.cached_ops = ops;
+    }
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;
     int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
     if (host) {   // streaming copy-out: per-lane staging rows, finished rays go straight to the caller's arrays
@@ -295,10 +308,44 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
         a.host_npoints_alloc = host->npa;
         a.host_ray0 = first;
     }
-    CK(cudaMemsetAsync(g.queue.p, 0, sizeof(unsigned long long), g.stream));
-    CK(ops->trace(g.sel, a, grid, g.stream, nullptr, nullptr));
+    // Time slicing (see TraceArgs): rays are suspended after `slice` steps and the survivors are re-launched packed
+    // into full warps, until they fit one per lane.  RAYS_B200_SLICE=0 disables it, =n forces n steps.
+    const long long lanes = (long long)g.num_sms * bps * kTraceBlock;
+    int slice = 0;
+    if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
+    if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) slice = atoi(env); }
+    if (slice > 0) {
+        CK(g.cont_state.reserve((size_t)count * kContStride));
+        CK(g.cont_list[0].reserve((size_t)count)); CK(g.cont_list[1].reserve((size_t)count));
+    }
+    long long n_this = count;
+    for (int phase = 0;; ++phase) {
+        a.nray = n_this;
+        a.slice_steps = (slice > 0 && n_this > lanes) ? slice : 0;      // survivors that fit one per lane run to the end
+        a.resume = phase > 0 ? 1 : 0;
+        a.order = phase > 0 ? g.cont_list[(phase - 1) & 1].p : nullptr;
+        a.cont_state = g.cont_state.p;
+        a.cont_list = g.cont_list[phase & 1].p;
+        a.cont_count = g.queue.p + 3;
+        CK(cudaMemsetAsync(g.queue.p, 0, sizeof(unsigned long long), g.stream));
+        CK(cudaMemsetAsync(g.queue.p + 3, 0, sizeof(unsigned long long), g.stream));
+        const int grid_p = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>((n_this + kTraceBlock - 1) / kTraceBlock, 1));
+        CK(cudaEventRecord(g.ev_m0, g.stream));
+        CK(ops->trace(g.sel, a, grid_p, g.stream, nullptr, nullptr));
+        CK(cudaEventRecord(g.ev_m1, g.stream));
+        g.last_launches += 1;
+        g.last_phases = phase + 1;
+        if (a.slice_steps == 0) { g.main_pending = true; g.main_is_resume = phase > 0; break; }
+        unsigned long long n_susp = 0;
+        CK(cudaMemcpyAsync(&n_susp, g.queue.p + 3, sizeof(n_susp), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev_m0, g.ev_m1));
+        (phase > 0 ? g.last_resume_ms : g.last_first_ms) += ms;
+        if (n_susp == 0) break;
+        n_this = (long long)n_susp;
+    }
     g.last_kernel = name; g.last_grid = grid; g.last_bps = bps;
-    g.last_launches += 1;
     return 0;
 }
 
@@ -306,6 +353,11 @@ int fetch_counters() {
     unsigned long long h[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(h, g.queue.p, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
+    if (g.main_pending) {   // duration of the (last) trace kernel itself
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g.ev_m0, g.ev_m1) == cudaSuccess) (g.main_is_resume ? g.last_resume_ms : g.last_first_ms) += ms;
+        g.main_pending = false;
+    }
     g.last_steps = (long long)h[1];
     g.last_rhs = (long long)h[2];
     return 0;
@@ -412,6 +464,8 @@ int rays_b200_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&g.ev0));
     CK(cudaEventCreate(&g.ev1));
+    CK(cudaEventCreate(&g.ev_m0));
+    CK(cudaEventCreate(&g.ev_m1));
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&g.ev_batch[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming));
@@ -428,6 +482,8 @@ int rays_b200_finalize(void) {
                               &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv, &g.dep};
     for (auto *b : bufs) b->release();
     g.npoints.release(); g.stop.release(); g.queue.release();
+    g.cont_state.release(); g.cont_list[0].release(); g.cont_list[1].release();
+    cudaEventDestroy(g.ev_m0); cudaEventDestroy(g.ev_m1);
     if (g.pinned) cudaFreeHost(g.pinned);
     g.pinned = nullptr; g.pinned_bytes = 0;
     cudaEventDestroy(g.ev0); cudaEventDestroy(g.ev1);
@@ -517,6 +573,7 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
     g.sel.damp = c.damping_model != RAYS_DAMP_NONE;
     g.sel.grads = c.integrate_eq_gradients != 0;
+    g.cached_bps = 0; g.cached_ops = nullptr;
     for (int ode = 1; ode <= 2; ++ode) {
         const TuOps *ops = tu_ops(c.equilib_model, ode);
         if (ops) CK(ops->upload(&d, g.stream));
@@ -579,7 +636,7 @@ static int trace_device_impl(int store_trajectories, bool binned) {
     CK(cudaSetDevice(g.device));
     const rays_cfg &c = g.dc.c;
     const int npa = c.nstep_max + 1;
-    if (store_trajectories) {
+    if (store_trajectories && (g.ray_vec.n < (size_t)g.nray * npa * c.nv || g.residual.n < (size_t)g.nray * npa)) {   // buffers must grow
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         const double need = (double)g.nray * npa * (c.nv + 1) * 8.0;
@@ -589,7 +646,7 @@ static int trace_device_impl(int store_trajectories, bool binned) {
     }
     int rc = ensure_results(g.nray, c.nv, npa, store_trajectories != 0);
     if (rc) return rc;
-    g.last_launches = 0;
+    g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
     CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
     if (binned) CK(cudaMemsetAsync(g.dep.p, 0, (size_t)g.dep_bins * sizeof(double), g.stream));
     CK(cudaEventRecord(g.ev0, g.stream));
@@ -633,6 +690,14 @@ int rays_b200_last_trace_info(int64_t *rhs_evals, char *kernel_name, int name_le
     if (kernel_name && name_len > 0) { std::strncpy(kernel_name, g.last_kernel, (size_t)name_len - 1); kernel_name[name_len - 1] = 0; }
     if (grid) *grid = g.last_grid;
     if (blocks_per_sm) *blocks_per_sm = g.last_bps;
+    return 0;
+}
+
+// kernel time of the last trace: first pass over the fan, resume passes over the suspended rays, launch count
+int rays_b200_last_trace_breakdown(double *first_pass_ms, double *resume_pass_ms, int32_t *n_passes) {
+    if (first_pass_ms) *first_pass_ms = g.last_first_ms;
+    if (resume_pass_ms) *resume_pass_ms = g.last_resume_ms;
+    if (n_passes) *n_passes = g.last_phases;
     return 0;
 }
 
@@ -719,7 +784,7 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
     if (streaming) {
         if ((rc = ensure_results(n, nv, npa, false))) return rc;
         g.have_traj = false;
-        g.last_launches = 0;
+        g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
         CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
         if ((rc = launch_trace(0, n, nullptr, nullptr, false, &hv))) return rc;
         std::vector<int> codes((size_t)n);
@@ -757,7 +822,7 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
         CK(g.residual.reserve((size_t)nbuf * batch * npa));
         g.have_traj = (nbuf == 1);
     }
-    g.last_launches = 0;
+    g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
     CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
     std::vector<int> np((size_t)std::max<long long>(n, 1)), codes((size_t)std::max<long long>(n, 1));
     int ib = 0;
