@@ -210,6 +210,23 @@ __global__ void fan_scatter_kernel(const int *valid, long long n, const int *blo
         for (int k = 0; k < 3; ++k) { rvec0[3 * dst + k] = rv[3 * i + k]; nvec0[3 * dst + k] = nv[3 * i + k]; }
     }
 }
+// The trimmed copy-out moves whole 32-point groups: clear the points between npoints and the next multiple of 32
+// so that the caller's arrays receive zeros there (the reference zero-fills and writes only 1:npoints).
+__global__ void zero_tail_kernel(double *ray_vec, double *residual, const int *npoints, int npa, int nv, long long nray) {
+    const long long iray = blockIdx.x;
+    if (iray >= nray) return;
+    // copy width of this ray's 64-ray group (copy_trajectories): longest ray of the group, rounded up to 32 points
+    __shared__ int gmax;
+    if (threadIdx.x == 0) gmax = 1;
+    __syncthreads();
+    const long long g0 = iray / 64 * 64;
+    if (g0 + threadIdx.x < nray && threadIdx.x < 64) atomicMax(&gmax, npoints[g0 + threadIdx.x]);
+    __syncthreads();
+    const int np = npoints[iray];
+    const int end = min(npa, (gmax + 31) / 32 * 32);
+    if (ray_vec) for (int i = np * nv + threadIdx.x; i < end * nv; i += blockDim.x) ray_vec[(size_t)iray * npa * nv + i] = 0.0;
+    if (residual) for (int i = np + threadIdx.x; i < end; i += blockDim.x) residual[(size_t)iray * npa + i] = 0.0;
+}
 // keep rays with iray % world == rank, order preserved
 __global__ void fan_shard_kernel(long long n_out, int rank, int world, const double *rv, const double *nv, const double *w,
                                  double *rv_o, double *nv_o, double *w_o) {
@@ -719,6 +736,8 @@ int rays_b200_results_download(rays_results *res) {
         if (res->npoints_alloc < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "npoints_alloc < 1");
         for (long long i = 0; i < n; ++i)
             if (np[(size_t)i] > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
+        zero_tail_kernel<<<(unsigned)n, 64, 0, g.stream>>>(res->ray_vec ? g.ray_vec.p : nullptr, res->residual ? g.residual.p : nullptr, g.npoints.p, g.res_npa, nv, n);
+        CK(cudaGetLastError());
         if ((rc = copy_trajectories(res, np, 0, n, g.ray_vec.p, g.residual.p, g.res_npa, nv, g.stream))) return rc;
         CK(cudaStreamSynchronize(g.stream));
     }
@@ -833,6 +852,10 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
         double *tr = want_traj ? g.residual.p + (size_t)b * batch * npa : nullptr;
         if (ib >= nbuf) CK(cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0));   // buffer b free again
         if ((rc = launch_trace(first, count, tv, tr, false))) return rc;
+        if (want_traj) {
+            zero_tail_kernel<<<(unsigned)count, 64, 0, g.stream>>>(res->ray_vec ? tv : nullptr, res->residual ? tr : nullptr, g.npoints.p + first, npa, nv, count);
+            CK(cudaGetLastError());
+        }
         CK(cudaMemcpyAsync(np.data() + first, g.npoints.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaMemcpyAsync(codes.data() + first, g.stop.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaEventRecord(g.ev_batch[b], g.stream));
