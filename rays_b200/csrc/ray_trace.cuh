@@ -590,15 +590,24 @@ constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, 
 // 256-byte coalesced stores, so that the copy is bandwidth- rather than latency-bound (a 13 KB ray takes ~7
 // round trips instead of ~50; the latency-bound version cost the warp about one ray-step per finished ray)
 RD_INLINE void copy_row_to_host(double *__restrict__ dst, const double *__restrict__ src, int n, unsigned lane) {
+    // 16-byte stores on a 16-byte aligned destination (512 contiguous bytes per warp instruction): the head
+    // element goes first when the row starts on an odd 8-byte boundary
+    int head = (reinterpret_cast<uintptr_t>(dst) & 15) ? 1 : 0;
+    if (head > n) head = n;
+    if (head && lane == 0) dst[0] = __ldcg(src);
+    dst += head; src += head; n -= head;
+    const int n2 = n >> 1;     // pairs
+    double2 *__restrict__ d2 = reinterpret_cast<double2 *>(dst);
     int i = (int)lane;
-    for (; i + 32 * 7 < n; i += 32 * 8) {
-        double t[8];
+    for (; i + 32 * 3 < n2; i += 32 * 4) {
+        double2 t[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = __ldcg(src + i + 32 * k);
+        for (int k = 0; k < 4; ++k) { const int j = 2 * (i + 32 * k); t[k] = make_double2(__ldcg(src + j), __ldcg(src + j + 1)); }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dst[i + 32 * k] = t[k];
+        for (int k = 0; k < 4; ++k) d2[i + 32 * k] = t[k];
     }
-    for (; i < n; i += 32) dst[i] = __ldcg(src + i);
+    for (; i < n2; i += 32) d2[i] = make_double2(__ldcg(src + 2 * i), __ldcg(src + 2 * i + 1));
+    if ((n & 1) && lane == 0) dst[n - 1] = __ldcg(src + n - 1);
 }
 
 // suspended-ray record (time slicing): everything a lane needs to carry on with the ray in a later launch
@@ -653,8 +662,11 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
 // warp; the integrator bookkeeping between two evaluations is lane-private.  `work`/`iwork` are automatic in
 // SG_ode and iflag = 1 on every call, so each ds segment restarts the integrator at order 1:
 // the history W lives in per-thread local memory and is re-initialised per segment.
+#ifndef RAYS_SG_MIN_CTAS
+#define RAYS_SG_MIN_CTAS 2
+#endif
 template <class T>
-__global__ void __launch_bounds__(kTraceBlock) trace_sg_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int nv = T::nv();

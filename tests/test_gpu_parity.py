@@ -309,3 +309,24 @@ def test_host_mirror_program_flow(tmp_path):
     assert f.variables["ray_vec"].shape == (11, 501, 12)
     assert np.array_equal(np.array(f.variables["ray_vec"].data), res["ray_vec"])
     f.close()
+
+
+@pytest.mark.parametrize("slice_steps,register", [("5", "1"), ("5", "0"), ("0", "0"), ("40", "1")])
+def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, register, monkeypatch):
+    """The library's execution options change the schedule and the copy-out path, never the results:
+    time slicing (rays suspended after n steps and re-launched packed) x streaming / batched copy-out."""
+    monkeypatch.setenv("RAYS_B200_SLICE", slice_steps)
+    monkeypatch.setenv("RAYS_B200_REGISTER_HOST", register)
+    cfg = init_case("solovev_fan_1M.in", nstep_max=120)
+    r, n, w, _, _ = oracle_fan(cfg, n_r_launch=2, n_theta_launch=3, n_rindex_theta=8, n_rindex_phi=8, dtheta_launch=0.2,
+                               delta_rindex_theta=0.05, delta_rindex_phi=0.04)
+    g, o = _run_both(cfg, r, n, w)
+    st = rb.last_trace_stats()
+    if slice_steps != "0":
+        assert st["n_passes"] >= 2
+    _compare_traces(g, o, cfg, 1e-10, bitwise=True)
+    # and Shampine-Gordon through the same options
+    cfg = init_case("solovev_fan_1M.in", ode_solver_name="SG_ODE", ray_deriv_name="cold", nstep_max=60, rel_err0=1e-6, abs_err0=1e-6,
+                    SG_error_limit=0.1)
+    g, o = _run_both(cfg, r[:96], n[:96], w[:96])
+    _compare_traces(g, o, cfg, 1e-6, bitwise=False)
