@@ -98,6 +98,7 @@ struct ray_results_m {  // RAYS_lib/ray_results_m.f90:44-165
     std::vector<char> ray_stop_flag;
     double total_trace_time = 0;
     int64_t total_ray_steps = 0;
+    bool allocated = false;
 };
 
 struct State {
@@ -619,8 +620,14 @@ static int initialize_ray_init_m(State &S, const NamelistFile &nml, bool do_laun
     return 0;
 }
 
-static void initialize_ray_results_m(State &S) {  // ray_results_m.f90:107-165 (zero-filled)
+// initialize_ray_results_m (ray_results_m.f90:107-165): the dense, zero-filled result arrays.  They are
+// allocated on first use (trace_rays / results / finalize_run) rather than inside initialize(): a host that only
+// wants the on-device deposition profile of a multi-million-ray fan never needs ray_vec(nv, nstep_max+1, nray).
+static void initialize_ray_results_m(State &S) { S.results.allocated = false; }
+static void allocate_ray_results(State &S) {
     ray_results_m &r = S.results;
+    if (r.allocated) return;
+    r.allocated = true;
     const int nv = S.ode.nv;
     const int64_t nray = S.ray_init.nray;
     const int np = S.ode.nstep_max + 1;
@@ -747,6 +754,7 @@ int64_t rays_host_get_fan(const double **rvec0, const double **rindex_vec0, cons
 // views of the module arrays of ray_results_m, in the layout rays_results documents
 int rays_host_results(rays_results *out) {
     if (!g) return RAYS_ERR_NOT_INITIALIZED;
+    allocate_ray_results(*g);
     ray_results_m &r = g->results;
     out->nray = r.number_of_rays; out->nv = r.nv; out->npoints_alloc = r.max_number_of_points;
     out->ray_vec = r.ray_vec.data(); out->residual = r.residual.data(); out->npoints = r.npoints.data();
@@ -780,6 +788,7 @@ int rays_host_trace_rays(void) {
 int rays_host_finalize_run(const char *outdir) {
     if (!g || !g->initialized) { g_err = "finalize_run called before initialize"; return RAYS_ERR_NOT_INITIALIZED; }
     State &S = *g;
+    allocate_ray_results(S);
     ray_results_m &r = S.results;
     if (!r.write_results_netCDF) return 0;
     const int64_t nray = r.number_of_rays;

@@ -330,7 +330,8 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     const long long lanes = (long long)g.num_sms * bps * kTraceBlock;
     int slice = 0;
     if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
-    if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) slice = atoi(env); }
+    bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
+    if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) { slice = atoi(env); forced = true; } }
     if (slice > 0) {
         CK(g.cont_state.reserve((size_t)count * kContStride));
         CK(g.cont_list[0].reserve((size_t)count)); CK(g.cont_list[1].reserve((size_t)count));
@@ -338,7 +339,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     long long n_this = count;
     for (int phase = 0;; ++phase) {
         a.nray = n_this;
-        a.slice_steps = (slice > 0 && n_this > lanes) ? slice : 0;      // survivors that fit one per lane run to the end
+        a.slice_steps = (slice > 0 && (forced || n_this > lanes)) ? slice : 0;      // survivors that fit one per lane run to the end
         a.resume = phase > 0 ? 1 : 0;
         a.order = phase > 0 ? g.cont_list[(phase - 1) & 1].p : nullptr;
         a.cont_state = g.cont_state.p;
