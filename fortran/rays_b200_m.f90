@@ -46,6 +46,7 @@ module rays_b200_m
         real(c_double) :: alphat1(RAYS_NSPECIES), alphat2(RAYS_NSPECIES)
         real(c_double) :: sm_rmaj, sm_kappa, sm_bphi0, sm_iota0, sm_psiB
         real(c_double) :: sm_box_rmin, sm_box_rmax, sm_box_zmin, sm_box_zmax
+        type(rays_spline1d) :: ne_spline, Te_spline, Ti_spline
     end type
     type, bind(C) :: rays_mirror_eq
         integer(c_int32_t) :: density_prof_model, temperature_prof_model(RAYS_NSPECIES), pad_
@@ -125,6 +126,7 @@ contains
             case ('parabolic');  prof_code = 4
             case ('Gaussian');   prof_code = 5
             case ('hyperbolic'); prof_code = 6
+            case ('density_spline_interp', 'temperature_spline_interp'); prof_code = 7
             case default;        prof_code = -1
         end select
     end function prof_code

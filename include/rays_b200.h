@@ -44,7 +44,8 @@ enum rays_wave_mode { RAYS_MODE_PLUS = 1, RAYS_MODE_MINUS = 2, RAYS_MODE_FAST = 
  * multiple_mirror_eq_m.f90:290-368) */
 enum rays_prof_model {
     RAYS_PROF_ZERO = 0, RAYS_PROF_CONSTANT = 1, RAYS_PROF_LINEAR = 2, RAYS_PROF_LINEAR_2 = 3,
-    RAYS_PROF_PARABOLIC = 4, RAYS_PROF_GAUSSIAN = 5, RAYS_PROF_HYPERBOLIC = 6
+    RAYS_PROF_PARABOLIC = 4, RAYS_PROF_GAUSSIAN = 5, RAYS_PROF_HYPERBOLIC = 6,
+    RAYS_PROF_SPLINE = 7              /* 'density_spline_interp' / 'temperature_spline_interp' (axisym_toroid) */
 };
 enum rays_slab_b_model {              /* slab_eq_m.f90:172-215 */
     RAYS_SLAB_B_ZERO = 0, RAYS_SLAB_B_CONSTANT = 1, RAYS_SLAB_B_TOROID = 2,
@@ -143,6 +144,9 @@ typedef struct rays_axisym_eq {       /* axisym_toroid_eq_m.f90:56-94 + solovev_
     /* solovev_magnetics_m module data */
     double sm_rmaj, sm_kappa, sm_bphi0, sm_iota0, sm_psiB;
     double sm_box_rmin, sm_box_rmax, sm_box_zmin, sm_box_zmax;
+    /* density_spline_interp_m.f90:22-27, temperature_spline_interp_m.f90:20-23: profiles on psi_N in [0,1],
+     * normalised to 1 on axis (ne_profile_N, Te_profileN, Ti_profileN); used when the model is RAYS_PROF_SPLINE */
+    rays_spline1d ne_spline, Te_spline, Ti_spline;
 } rays_axisym_eq;
 
 typedef struct rays_mirror_eq {       /* multiple_mirror_eq_m.f90:63-106 + mirror_magnetics_spline_interp_m.f90:32-41 */

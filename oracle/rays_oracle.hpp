@@ -403,6 +403,15 @@ template <class R> inline void axisym_toroid_eq(const rays_cfg &c, const R rvec[
                 for (int i = 0; i < 3; ++i) m.gradns[i][s] = c.n0s[s] * dd_psi * grad_psiN[i];
             }
         } break;
+        case RAYS_PROF_SPLINE: {   // density_spline_interp (L/density_spline_interp_m.f90:107-127)
+            R dens(0.0), dd_psi(0.0);   // (X) dd_psi is undefined in the Fortran for psi > 1 with d_scrape_off = 0
+            if (psiN <= 1.0) cspeval(psiN, p.ne_spline, dens, &dd_psi);
+            if (dens < p.d_scrape_off) { dens = R(p.d_scrape_off); dd_psi = R(0.0); }
+            for (int s = 0; s <= nspec; ++s) {
+                m.ns[s] = c.n0s[s] * dens;
+                for (int i = 0; i < 3; ++i) m.gradns[i][s] = c.n0s[s] * dd_psi * grad_psiN[i];
+            }
+        } break;
     }
     for (int s = 0; s <= nspec; ++s) {
         switch (p.temperature_prof_model[s]) {
@@ -416,6 +425,13 @@ template <class R> inline void axisym_toroid_eq(const rays_cfg &c, const R rvec[
                 parabolic_prof(psiN, R(p.T_scrape_off), R(p.alphat1[s]), R(p.alphat2[s]), t_prof, dt_dpsi);
                 m.ts[s] = c.t0s[s] * t_prof;
                 for (int i = 0; i < 3; ++i) m.gradts[i][s] = c.t0s[s] * dt_dpsi * grad_psiN[i];
+            } break;
+            case RAYS_PROF_SPLINE: {   // temperature_spline_interp (L/temperature_spline_interp_m.f90:82-108): Te for s = 0, Ti else
+                R t(0.0), dt(0.0);
+                if (psiN <= 1.0) cspeval(psiN, s == 0 ? p.Te_spline : p.Ti_spline, t, &dt);
+                if (t < p.T_scrape_off) { t = R(p.T_scrape_off); dt = R(0.0); }
+                m.ts[s] = c.t0s[s] * t;
+                for (int i = 0; i < 3; ++i) m.gradts[i][s] = c.t0s[s] * dt * grad_psiN[i];
             } break;
         }
     }

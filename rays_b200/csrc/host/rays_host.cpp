@@ -115,6 +115,7 @@ struct State {
     // table storage referenced by cfg
     std::vector<double> z_x, z_re, z_im;
     std::vector<double> r_grid, z_grid, Br_fspl, Bz_fspl, Aphi_fspl;
+    std::vector<double> ne_grid, ne_fspl, T_grid, Te_fspl, Ti_fspl;   // density/temperature_spline_interp_m
     std::string workdir;
     std::string namelist_path;
     bool initialized = false;
@@ -132,6 +133,7 @@ static int prof_code(const std::string &s) {
     if (s == "parabolic") return RAYS_PROF_PARABOLIC;
     if (s == "Gaussian") return RAYS_PROF_GAUSSIAN;
     if (s == "hyperbolic") return RAYS_PROF_HYPERBOLIC;
+    if (s == "density_spline_interp" || s == "temperature_spline_interp") return RAYS_PROF_SPLINE;
     return -1;
 }
 static std::string trim(const std::string &s) {
@@ -345,15 +347,56 @@ static int initialize_axisym_toroid_eq_m(State &S, const NamelistFile &nml) {
         p.upper_bound = vert_bound; p.lower_bound = -vert_bound;
     }
     dens = trim(dens);
+    p.ne_spline = rays_spline1d{}; p.Te_spline = rays_spline1d{}; p.Ti_spline = rays_spline1d{};
+    // profile on a uniform psi_N grid, normalised to its first value, not-a-knot cubic spline
+    // (initialize_density_spline_interp, density_spline_interp_m.f90:29-75; cube_spline_1D_init)
+    auto build_profile = [&](int ngrid, const std::vector<double> &in, std::vector<double> &grid, std::vector<double> &fspl,
+                             rays_spline1d &out) -> int {
+        if (ngrid < 4 || ngrid > 200) return fail("spline profile: ngrid must be in 4..200");
+        if (in[0] == 0.0) return fail("spline profile: first value (on axis) is zero");
+        grid.resize((size_t)ngrid);
+        fspl.assign((size_t)4 * ngrid, 0.0);
+        for (int i = 1; i <= ngrid; ++i) {
+            grid[(size_t)i - 1] = 1.0 * (i - 1) / (ngrid - 1);
+            fspl[4 * ((size_t)i - 1)] = in[(size_t)i - 1] / in[0];
+        }
+        int ilinx = 0;
+        if (cspline(grid.data(), ngrid, fspl.data(), &ilinx) || ilinx != 1) return fail("spline profile: cspline failed");
+        out.nx = ngrid; out.pad_ = 0; out.x_grid = grid.data(); out.fspl = fspl.data();
+        return 0;
+    };
     if (dens == "constant") p.density_prof_model = RAYS_PROF_CONSTANT;
     else if (dens == "parabolic") p.density_prof_model = RAYS_PROF_PARABOLIC;
-    else return fail("axisym_toroid_eq: Unknown density_prof_model: " + dens + " (density_spline_interp is a later scope row)");
+    else if (dens == "density_spline_interp") {
+        p.density_prof_model = RAYS_PROF_SPLINE;
+        int ngrid = 0;
+        std::vector<double> ne_in(200, 0.0);
+        NamelistGroup D("density_spline_interp_list");
+        D.add("ngrid", &ngrid); D.add_arr("ne_in", ne_in.data(), 1, 200);
+        if (!D.read(nml, err)) return fail(err);
+        int rc = build_profile(ngrid, ne_in, S.ne_grid, S.ne_fspl, p.ne_spline);
+        if (rc) return rc;
+    } else return fail("axisym_toroid_eq: Unknown density_prof_model: " + dens);
+    int n_T_spline = 0;
     for (int is = 0; is <= S.species.nspec; ++is) {
         std::string t = trim(tprof[is]);
         if (t == "zero") p.temperature_prof_model[is] = RAYS_PROF_ZERO;
         else if (t == "constant") p.temperature_prof_model[is] = RAYS_PROF_CONSTANT;
         else if (t == "parabolic") p.temperature_prof_model[is] = RAYS_PROF_PARABOLIC;
+        else if (t == "temperature_spline_interp") { p.temperature_prof_model[is] = RAYS_PROF_SPLINE; ++n_T_spline; }
         else return fail("axisym_toroid_eq: Unknown temperature_prof_model: " + t);
+    }
+    if (n_T_spline > 0) {   // initialize_temperature_spline_interp (temperature_spline_interp_m.f90:30-78)
+        int ngrid = 0;
+        std::vector<double> Te_in(200, 0.0), Ti_in(200, 0.0);
+        NamelistGroup T("temperature_spline_interp_list");
+        T.add("ngrid", &ngrid); T.add_arr("te_in", Te_in.data(), 1, 200); T.add_arr("ti_in", Ti_in.data(), 1, 200);
+        if (!T.read(nml, err)) return fail(err);
+        std::vector<double> grid2;
+        int rc = build_profile(ngrid, Te_in, S.T_grid, S.Te_fspl, p.Te_spline);
+        if (rc) return rc;
+        if ((rc = build_profile(ngrid, Ti_in, grid2, S.Ti_fspl, p.Ti_spline))) return rc;
+        p.Ti_spline.x_grid = S.T_grid.data();
     }
     return 0;
 }

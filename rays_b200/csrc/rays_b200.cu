@@ -68,6 +68,7 @@ struct Ctx {
     DevCfg dc{};
     KernelSel sel{};
     DevBuf<double> zx, zf, rgrid, zgrid, br, bz, aphi;
+    DevBuf<double> prof_grid[3], prof_fspl[3];   // axisym 1-D profile splines: ne, Te, Ti
     // fan (device)
     long long nray = 0;
     DevBuf<double> rvec0, nvec0, wt;
@@ -140,6 +141,15 @@ int validate_cfg(const rays_cfg &c) {
             return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: spline tables missing");
         if (m.Bz_spline.nx != m.Br_spline.nx || m.Aphi_spline.nx != m.Br_spline.nx || m.Bz_spline.ny != m.Br_spline.ny || m.Aphi_spline.ny != m.Br_spline.ny)
             return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: Br, Bz, Aphi must share one (r,z) grid");
+    }
+    if (c.equilib_model == RAYS_EQ_AXISYM_TOROID) {
+        const rays_axisym_eq &a = c.axisym;
+        auto ok = [](const rays_spline1d &s) { return s.x_grid && s.fspl && s.nx >= 2; };
+        if (a.density_prof_model == RAYS_PROF_SPLINE && !ok(a.ne_spline))
+            return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: density_spline_interp table missing");
+        for (int s = 0; s <= c.nspec; ++s)
+            if (a.temperature_prof_model[s] == RAYS_PROF_SPLINE && !ok(s == 0 ? a.Te_spline : a.Ti_spline))
+                return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: temperature_spline_interp table missing");
     }
     return 0;
 }
@@ -496,7 +506,8 @@ int rays_b200_finalize(void) {
     if (!g.inited) return 0;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
+    DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.prof_grid[0], &g.prof_grid[1], &g.prof_grid[2],
+                              &g.prof_fspl[0], &g.prof_fspl[1], &g.prof_fspl[2], &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
                               &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv, &g.dep};
     for (auto *b : bufs) b->release();
     g.npoints.release(); g.stop.release(); g.queue.release();
@@ -545,6 +556,24 @@ int rays_b200_set_config(const rays_cfg *cfg) {
         rays_spline2d none{};
         c.mirror.Br_spline = none; c.mirror.Bz_spline = none; c.mirror.Aphi_spline = none;
     }
+    {   // axisym_toroid 1-D profile splines (density_spline_interp_m, temperature_spline_interp_m)
+        rays_spline1d *sp[3] = {&c.axisym.ne_spline, &c.axisym.Te_spline, &c.axisym.Ti_spline};
+        const rays_spline1d *src[3] = {&cfg->axisym.ne_spline, &cfg->axisym.Te_spline, &cfg->axisym.Ti_spline};
+        bool used[3] = {false, false, false};
+        if (c.equilib_model == RAYS_EQ_AXISYM_TOROID) {
+            used[0] = c.axisym.density_prof_model == RAYS_PROF_SPLINE;
+            for (int s = 0; s <= c.nspec; ++s)
+                if (c.axisym.temperature_prof_model[s] == RAYS_PROF_SPLINE) used[s == 0 ? 1 : 2] = true;
+        }
+        for (int k = 0; k < 3; ++k) {
+            *sp[k] = rays_spline1d{};
+            if (!used[k]) continue;
+            const size_t nx = (size_t)src[k]->nx;
+            if ((rc = upload_table(g.prof_grid[k], src[k]->x_grid, nx))) return rc;
+            if ((rc = upload_table(g.prof_fspl[k], src[k]->fspl, 4 * nx))) return rc;
+            sp[k]->nx = src[k]->nx; sp[k]->x_grid = g.prof_grid[k].p; sp[k]->fspl = g.prof_fspl[k].p;
+        }
+    }
     // constant products, formed with the same IEEE operations the reference performs per call
     for (int s = 0; s < RAYS_NSPECIES; ++s) { d.qs2[s] = c.qs[s] * c.qs[s]; d.eps0ms[s] = c.eps0 * c.ms[s]; }
     d.omgrf2 = c.omgrf * c.omgrf;
@@ -583,6 +612,7 @@ int rays_b200_set_config(const rays_cfg *cfg) {
         for (int s = 0; s <= c.nspec; ++s) {
             if (c.t0s[s] < 0.0) need = true;                                                    // 'negative_temp' must still fire
             if (c.equilib_model == RAYS_EQ_SOLOVEV && c.solovev.t_prof_model[s] == RAYS_PROF_CONSTANT) need = true;   // (R) resets the density
+            if (c.equilib_model == RAYS_EQ_AXISYM_TOROID && c.axisym.temperature_prof_model[s] == RAYS_PROF_SPLINE) need = true;   // a splined profile may go negative
         }
         d.need_temp = need ? 1 : 0;
     }

@@ -152,11 +152,36 @@ def test_axisym_damping_rk4_and_deposition():
     assert abs(qf - float(np.sum(p_last * o.initial_ray_power))) <= 1e-9 * abs(qo)
 
 
+# ---- tabulated (splined) density / temperature profiles in axisym_toroid ---------------
+@pytest.mark.parametrize("deriv", ["cold", "numerical"])
+def test_axisym_spline_profiles_rk4_bitwise(deriv, tmp_path):
+    # no damping: nothing on the path calls libm, the comparison is bitwise (nv = 12 with the gradient slots)
+    cfg = init_case_text("axisym_spline_profiles.in", [("damping_model='damp_fund_ECH'", "damping_model='no_damp'")], tmp_path,
+                         ray_deriv_name=deriv, nstep_max=300)
+    assert cfg.nv == 12
+    r, n, w, _, _ = oracle_fan(cfg)
+    assert r.shape[0] > 128
+    g, o = _run_both(cfg, r, n, w)
+    _compare_traces(g, o, cfg, 1e-10, bitwise=True)
+
+
+def test_axisym_spline_profiles_damping_and_sg():
+    cfg = init_case("axisym_spline_profiles.in", nstep_max=400)
+    r, n, w, _, _ = oracle_fan(cfg)
+    g, o = _run_both(cfg, r, n, w)
+    _compare_traces(g, o, cfg, 1e-10, bitwise=False)
+    assert np.max(o.end_ray_vec[:, 7]) > 0.5
+    cfg = init_case("axisym_spline_profiles.in", ode_solver_name="SG_ODE", nstep_max=200, rel_err0=1e-7, abs_err0=1e-7)
+    g, o = _run_both(cfg, r[::4], n[::4], w[::4])
+    _compare_traces(g, o, cfg, 1e-7, bitwise=False)
+
+
 # ---- one-point probes -------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case,box", [
     ("slab_ECH_90GHz_case_1.in", ((-0.6, 0.6), (-0.6, 0.6), (-1.1, 1.1))),
     ("solovev_ECH_90GHz_plus_root.in", ((0.5, 1.5), (-0.3, 0.3), (-0.75, 0.75))),
     ("axisym_deposition_fan.in", ((0.5, 1.5), (-0.3, 0.3), (-0.75, 0.75))),
+    ("axisym_spline_profiles.in", ((0.5, 1.5), (-0.3, 0.3), (-0.75, 0.75))),
     ("mpex/rays.in", ((-0.15, 0.15), (-0.15, 0.15), (2.75, 3.65))),
 ])
 def test_probe_equilibrium(case, box):

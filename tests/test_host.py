@@ -33,7 +33,7 @@ def test_constants_carry_single_precision_literals():
 
 def test_namelists_of_all_configs_parse():
     nv = {"slab_ECH_90GHz_case_1.in": 7, "solovev_ECH_90GHz_plus_root.in": 12, "mpex/rays.in": 12, "solovev_fan_1M.in": 7,
-          "axisym_deposition_fan.in": 8}
+          "axisym_deposition_fan.in": 8, "axisym_spline_profiles.in": 13}
     for name, want in nv.items():
         cfg = init_case(name)
         assert cfg.nv == want and cfg.nspec == 1
@@ -146,3 +146,38 @@ def test_mpex_field_file_reader_matches_scipy():
     rg = np.ctypeslib.as_array(cfg.mirror.Br_spline.x_grid, (nx,))
     assert np.allclose(rg, np.array(f.variables["r_grid"].data))
     f.close()
+
+
+def test_spline_profile_namelists_build_normalised_tables():
+    """density_spline_interp_m.f90:93-104 / temperature_spline_interp_m.f90:97-108: uniform psi_N grid on [0,1],
+    values normalised to the first (on-axis) one, not-a-knot cubic spline through them."""
+    import re
+    cfg = init_case("axisym_spline_profiles.in")
+    a = cfg.axisym
+    assert a.density_prof_model == _abi.PROF_SPLINE and list(a.temperature_prof_model)[:2] == [_abi.PROF_SPLINE] * 2
+    txt = open(rb.config_path("axisym_spline_profiles.in")).read()
+    for key, sp in (("ne_in", a.ne_spline), ("Te_in", a.Te_spline), ("Ti_in", a.Ti_spline)):
+        vals = np.array([float(v) for v in re.search(key + r"\s*=\s*([^\n]*)", txt).group(1).split(",")])
+        assert sp.nx == 21 == len(vals)
+        grid = np.ctypeslib.as_array(sp.x_grid, (21,))
+        fs = np.ctypeslib.as_array(sp.fspl, (21, 4))
+        assert np.array_equal(grid, np.array([1.0 * i / 20 for i in range(21)]))
+        assert np.array_equal(fs[:, 0], vals / vals[0]) and fs[0, 0] == 1.0
+        # continuity of the spline and its first two derivatives at the interior knots
+        h = np.diff(grid)
+        end = fs[:-1, 0] + h * (fs[:-1, 1] + h * (fs[:-1, 2] + h * fs[:-1, 3]))
+        assert np.max(np.abs(end - fs[1:, 0])) < 1e-14
+        d1 = fs[:-1, 1] + h * (2 * fs[:-1, 2] + 3 * h * fs[:-1, 3])
+        assert np.max(np.abs(d1[:-1] - fs[1:-1, 1])) < 1e-11
+        # not-a-knot: the third derivative is continuous across the 2nd and the next-to-last knot
+        assert abs(fs[0, 3] - fs[1, 3]) < 1e-9 * max(1.0, abs(fs[0, 3])) and abs(fs[-3, 3] - fs[-2, 3]) < 1e-9 * max(1.0, abs(fs[-3, 3]))
+
+
+def test_spline_profile_errors(tmp_path):
+    L = _abi.load()
+    txt = open(rb.config_path("axisym_spline_profiles.in")).read()
+    for old, new in (("  ngrid = 21\n  ne_in", "  ngrid = 2\n  ne_in"), ("density_prof_model = 'density_spline_interp'", "density_prof_model = 'spline'")):
+        assert old in txt
+        p = tmp_path / "bad.in"
+        p.write_text(txt.replace(old, new))
+        assert L.rays_host_initialize(str(p).encode(), 0) != 0

@@ -158,3 +158,37 @@ def test_flop_count_matches_baseline_md():
     fl, steps, nrhs = orc.count_flops(cfg, r, n, 0, 4)
     assert nrhs >= 4 * steps
     assert 18000 < fl / steps < 24000          # BASELINE.md hand count: ~24.8k +-15% for Solov'ev/deriv_num RK4
+
+
+def test_splined_linear_profile_equals_parabolic(tmp_path):
+    """A not-a-knot spline reproduces a polynomial of degree <= 3, so a tabulated 1 - psi_N density / temperature
+    is the 'parabolic' profile with alpha1 = alpha2 = 1 to rounding: the two axisym_toroid profile paths
+    (density_spline_interp / parabolic_prof) must then trace the same rays."""
+    from _cases import init_case_text
+    psi = np.linspace(0.0, 1.0, 21)
+    lin = ", ".join(f"{v:.17e}" for v in (1.0 - psi))
+    import re
+    import rays_b200 as rb
+    txt = open(rb.config_path("axisym_spline_profiles.in")).read()
+    edits = [(re.search(r"ne_in = [^\n]*", txt).group(0), "ne_in = " + lin), (re.search(r"Te_in = [^\n]*", txt).group(0), "Te_in = " + lin),
+             (re.search(r"Ti_in = [^\n]*", txt).group(0), "Ti_in = " + lin), ("d_scrape_off = 0.001", "d_scrape_off = 0.0"),
+             ("T_scrape_off = 0.002", "T_scrape_off = 0.0")]
+    cfg = init_case_text("axisym_spline_profiles.in", edits, tmp_path, nstep_max=300)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=4, delta_rindex_theta=0.1, n_rindex_phi=4, delta_rindex_phi=0.08)
+    os_, st, _ = orc.trace(cfg, r, n, w)
+    assert st == 0
+    pts = np.stack([np.linspace(0.7, 1.39, 64), np.zeros(64), np.linspace(-0.2, 0.2, 64)], axis=1)
+    es, errs = orc.probe_equilibrium(cfg, pts)
+    edits2 = [("density_prof_model = 'density_spline_interp'", "density_prof_model = 'parabolic'"),
+              ("temperature_prof_model = 2*'temperature_spline_interp'", "temperature_prof_model = 2*'parabolic'"),
+              ("d_scrape_off = 0.001", "d_scrape_off = 0.0"), ("T_scrape_off = 0.002", "T_scrape_off = 0.0")]
+    cfg = init_case_text("axisym_spline_profiles.in", edits2, tmp_path, nstep_max=300)
+    op, st, _ = orc.trace(cfg, r, n, w)
+    ep, errp = orc.probe_equilibrium(cfg, pts)
+    assert np.array_equal(errs, errp) and (errs == 0).sum() > 30
+    ok = errs == 0
+    assert np.allclose(es[ok], ep[ok], rtol=1e-12, atol=1e-12 * np.max(np.abs(ep[ok]), axis=0))
+    assert np.array_equal(os_.npoints, op.npoints) and os_.ray_stop_flag == op.ray_stop_flag
+    fin = np.isfinite(op.end_ray_vec).all(axis=1)
+    assert fin.sum() >= 8
+    assert np.allclose(os_.end_ray_vec[fin], op.end_ray_vec[fin], rtol=1e-8, atol=1e-9)
