@@ -9,9 +9,14 @@
 // Evaluation order, single-precision literals, integer powers by multiplication, complex
 // arithmetic expansion and copysign semantics follow SURVEY.md Appendix A.
 //
-// PARITY STATUS: **parity unpinned** for trajectories (the reference ships no numeric ray
-// outputs and cannot be compiled here: no Fortran compiler, no netCDF).  Pinned sub-pieces: the
-// plasma Z function table M/"Splined Z function results.txt":48-85 (tests/golden/zfun_kat.json).
+// PARITY STATUS: the reference cannot be compiled here (no Fortran compiler, no netCDF) and ships no
+// numeric ray files -- but its example directories ship vector PDFs of the rays the Fortran traced.
+// PINNED on (a) those figures: 23 rays of 5 shipped inputs (slab + Solov'ev, all SG_ODE), 1 798 plotted
+// trajectory points reproduced to the PDFs' resolution of 1e-6 pt (1.3e-9 ... 8.7e-9 m; 3e-14 m in z on
+// the equatorial-plane runs), ray lengths included (tests/golden/ref_plot_vectors.json,
+// tests/test_reference_plots.py); (b) the plasma Z function table M/"Splined Z function results.txt":48-85
+// (tests/golden/zfun_kat.json).  NOT pinned by reference output: RK4_ODE as a stepper, the mirror
+// equilibrium, deriv_num, damping (k and power are pinned only through the positions they drive).
 //
 // Where the Fortran has undefined behaviour the oracle makes a documented deterministic choice
 // (marked "(X)" as in SURVEY.md A.5); the CUDA path makes the same choice.

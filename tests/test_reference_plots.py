@@ -1,0 +1,88 @@
+"""Parity against the REFERENCE'S OWN OUTPUT.  The example directories of the reference ship vector PDFs of the
+rays the Fortran code traced (examples_RAYS/*/ray_plots.*.pdf).  tests/golden/make_ref_plot_vectors.py turned
+their polylines into coordinates (tests/golden/ref_plot_vectors.json): 23 rays of five example inputs, slab and
+Solov'ev, all integrated with SG_ODE, 1 798 plotted trajectory points with a resolution of 1e-6 pt = 1.3e-9 ...
+8.7e-9 m (3e-14 m for z on the x10^-5 axis of the equatorial-plane runs).
+
+Every plotted point must coincide with a saved point of our trajectory of the same ray to that resolution, in
+order, and the plotted ray must end where ours ends.  The oracle is pinned here on CPU; the CUDA path is held to
+the same figures in the gpu-marked test."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import rays_b200 as rb
+import _oracle as orc
+from _cases import init_case, oracle_fan
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "ref_plot_vectors.json")))
+NAMELISTS = sorted({f["namelist"] for f in GOLD["figures"]})
+
+# The reference's run of plus_root ended rays 3 and 5 one saved point earlier than ours: both leave the plasma
+# there and SG is about to declare 'equations stiff' (50 consecutive low-order steps, ode_RAYS.f90:1008-1012) --
+# a counter that rounding-level differences in the step-size history shift by one segment (the figures were made
+# on another compiler/CPU).  All points up to the reference's last one coincide like everywhere else.
+ENDS_EARLY = {("examples/solovev_ECH_90GHz_plus_root.in", 2): 1, ("examples/solovev_ECH_90GHz_plus_root.in", 4): 1}
+TOL_QUANTA = 1.5      # 0.5 from the PDF's rounding per coordinate + the tick-calibration fit
+
+
+def _coord(tr, name):
+    return {"x": tr[:, 0], "y": tr[:, 1], "z": tr[:, 2], "r": np.sqrt(tr[:, 0] ** 2 + tr[:, 1] ** 2)}[name]
+
+
+def _check_against_figures(namelist, res):
+    figs = [f for f in GOLD["figures"] if f["namelist"] == namelist]
+    assert figs
+    n_pts = 0
+    for F in figs:
+        assert len(F["rays"]) == res.nray, "the figure shows every ray of the run"
+        for i, R in enumerate(F["rays"]):
+            tr = res.ray_vec[i, :res.npoints[i]]
+            H, V = _coord(tr, F["h"]), _coord(tr, F["v"])
+            gh, gv = np.array(R["h"]), np.array(R["v"])
+            last = -1
+            for a, b in zip(gh, gv):
+                d = np.maximum(np.abs(H - a) / F["quantum_h"], np.abs(V - b) / F["quantum_v"])
+                k = int(np.argmin(d))
+                assert d[k] <= TOL_QUANTA, (F["pdf"], i, k, float(d[k]))
+                assert k >= last, "plotted points follow the ray"
+                last = k
+            n_pts += len(gh)
+            assert res.npoints[i] - 1 - last == ENDS_EARLY.get((namelist, i), 0), (F["pdf"], i, int(res.npoints[i]), last)
+    return n_pts
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(built):
+    yield
+
+
+@pytest.mark.parametrize("namelist", NAMELISTS)
+def test_oracle_reproduces_the_reference_figures(namelist):
+    cfg = init_case(namelist)
+    assert cfg.ode_solver == 2      # every shipped example figure is a Shampine-Gordon run
+    r, n, w, _, _ = oracle_fan(cfg)
+    o, st, _ = orc.trace(cfg, r, n, w)
+    assert st == 0
+    assert _check_against_figures(namelist, o) >= 80
+
+
+def test_figure_inventory():
+    assert len(GOLD["figures"]) == 8 and sum(len(f["rays"]) for f in GOLD["figures"]) == 41
+    assert sum(len(r["h"]) for f in GOLD["figures"] for r in f["rays"]) == 1798
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("namelist", NAMELISTS)
+def test_cuda_path_reproduces_the_reference_figures(namelist):
+    rb.init(0)
+    cfg = init_case(namelist)
+    r, n, w, _, _ = oracle_fan(cfg)
+    g = rb.trace(cfg, r, n, w)
+    _check_against_figures(namelist, g)
+    # and through the device launcher (ray_init on the GPU) as `program rays` would run the example
+    o, st, _ = orc.trace(cfg, r, n, w)
+    assert np.array_equal(g.npoints, o.npoints) and g.ray_stop_flag == o.ray_stop_flag
