@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--rays", type=int, default=0, help="debug: shrink the fan to about this many candidates")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-rays", type=int, default=12288, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=98304, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--ode", default="", help="measurement aid: override ode_solver_name (RK4_ODE | SG_ODE)")
     ap.add_argument("--deriv", default="", help="measurement aid: override ray_deriv_name (cold | numerical)")
     return ap.parse_args()

@@ -47,6 +47,9 @@ module rays_b200_m
         real(c_double) :: sm_rmaj, sm_kappa, sm_bphi0, sm_iota0, sm_psiB
         real(c_double) :: sm_box_rmin, sm_box_rmax, sm_box_zmin, sm_box_zmax
         type(rays_spline1d) :: ne_spline, Te_spline, Ti_spline
+        type(rays_spline2d) :: Psi_spline
+        type(rays_spline1d) :: T_spline
+        real(c_double) :: eq_psibound
     end type
     type, bind(C) :: rays_mirror_eq
         integer(c_int32_t) :: density_prof_model, temperature_prof_model(RAYS_NSPECIES), pad_

@@ -51,7 +51,7 @@ enum rays_slab_b_model {              /* slab_eq_m.f90:172-215 */
     RAYS_SLAB_B_ZERO = 0, RAYS_SLAB_B_CONSTANT = 1, RAYS_SLAB_B_TOROID = 2,
     RAYS_SLAB_B_LINEAR_SHEAR = 3, RAYS_SLAB_B_LINEAR = 4, RAYS_SLAB_B_LINEAR_2 = 5
 };
-enum rays_axisym_magnetics { RAYS_MAG_SOLOVEV = 1 };  /* axisym_toroid_eq_m.f90:280-291 */
+enum rays_axisym_magnetics { RAYS_MAG_SOLOVEV = 1, RAYS_MAG_EQDSK_SPLINE = 2 };  /* axisym_toroid_eq_m.f90:280-291 */
 
 /* ---- per-ray stop codes <-> the reference's ode_stop_flag strings ------ */
 enum rays_stop_code {
@@ -147,6 +147,12 @@ typedef struct rays_axisym_eq {       /* axisym_toroid_eq_m.f90:56-94 + solovev_
     /* density_spline_interp_m.f90:22-27, temperature_spline_interp_m.f90:20-23: profiles on psi_N in [0,1],
      * normalised to 1 on axis (ne_profile_N, Te_profileN, Ti_profileN); used when the model is RAYS_PROF_SPLINE */
     rays_spline1d ne_spline, Te_spline, Ti_spline;
+    /* eqdsk_magnetics_spline_interp_m.f90:30-55 (magnetics_model = RAYS_MAG_EQDSK_SPLINE): Psi_profile on the g-file's
+     * (R,Z) grid, shifted to 0 on the axis; T_profile = R*Bphi, splined on the R grid as the reference does (:184);
+     * eq_psibound = PSIBOUND - PSIAXIS */
+    rays_spline2d Psi_spline;
+    rays_spline1d T_spline;
+    double eq_psibound;
 } rays_axisym_eq;
 
 typedef struct rays_mirror_eq {       /* multiple_mirror_eq_m.f90:63-106 + mirror_magnetics_spline_interp_m.f90:32-41 */

@@ -127,6 +127,42 @@ inline int bcspeval_fp(R xget, R yget, const rays_spline2d &s, R &f, R &fx, R &f
     return 0;
 }
 
+// bcspevxy + bcspevfn with ict = (1,1,1,1,1,1) (S/bcspeval.f90:128-255, :368-455), as called by eval_2D_fpp
+// (S/quick_cube_splines_m.f90:305-332): f, fx, fy, fxx, fyy, fxy.  (X) on a range error the Fortran prints and
+// uses fval uninitialised; here the outputs are left as the caller set them.
+template <class R>
+inline int bcspeval_fpp(R xget, R yget, const rays_spline2d &s, R &f, R &fx, R &fy, R &fxx, R &fyy, R &fxy) {
+    if (bcspeval_fp(xget, yget, s, f, fx, fy) != 0) return 1;
+    const double *x = s.x_grid, *y = s.y_grid;
+    const int nx = s.nx, ny = s.ny, nxm = nx - 1, nym = ny - 1;
+    R zxget = xget, zyget = yget;   // same zone lookup as bcspeval_fp
+    if (xget < x[0]) zxget = R(x[0]); else if (xget > x[nx - 1]) zxget = R(x[nx - 1]);
+    if (yget < y[0]) zyget = R(y[0]); else if (yget > y[ny - 1]) zyget = R(y[ny - 1]);
+    int ii = 1 + (int)val(R((double)nxm) * (zxget - x[0]) / (x[nx - 1] - x[0]));
+    int i = ii < nxm ? ii : nxm;
+    if (zxget < x[i - 1]) i = i - 1;
+    else if (zxget > x[i]) i = i + 1;
+    int jj = 1 + (int)val(R((double)nym) * (zyget - y[0]) / (y[ny - 1] - y[0]));
+    int j = jj < nym ? jj : nym;
+    if (zyget < y[j - 1]) j = j - 1;
+    else if (zyget > y[j]) j = j + 1;
+    R dx = zxget - x[i - 1];
+    R dy = zyget - y[j - 1];
+    const double *c = s.fspl + (size_t)((j - 1) * nx + (i - 1)) * 16;
+#define F(cx, cy) c[((cy)-1) * 4 + ((cx)-1)]
+    fxx = 2.0 * (F(3, 1) + dy * (F(3, 2) + dy * (F(3, 3) + dy * F(3, 4)))) +
+          6.0 * dx * (F(4, 1) + dy * (F(4, 2) + dy * (F(4, 3) + dy * F(4, 4))));
+    fyy = 2.0 * F(1, 3) + 6.0 * dy * F(1, 4) +
+          dx * (2.0 * F(2, 3) + 6.0 * dy * F(2, 4) +
+                dx * (2.0 * F(3, 3) + 6.0 * dy * F(3, 4) +
+                      dx * (2.0 * F(4, 3) + 6.0 * dy * F(4, 4))));
+    fxy = F(2, 2) + dy * (2.0 * F(2, 3) + dy * 3.0 * F(2, 4)) +
+          2.0 * dx * (F(3, 2) + dy * (2.0 * F(3, 3) + dy * 3.0 * F(3, 4)) +
+                      1.5 * dx * (F(4, 2) + dy * (2.0 * F(4, 3) + dy * 3.0 * F(4, 4))));
+#undef F
+    return 0;
+}
+
 // ============================ profile helpers ================================================
 // parabolic_prof (L/slab_eq_m.f90:354-381, L/axisym_toroid_eq_m.f90:505-521, L/multiple_mirror_eq_m.f90:465-481)
 // (X) fp is left undefined by the Fortran when rho >= 1 and f >= f_min; here it is 0.
@@ -371,6 +407,40 @@ template <class R> inline void solovev_eq(const rays_cfg &c, const R rvec[3], Mo
     if (minval(m.ts, nspec + 1) < 0.0) m.equib_err = RAYS_STOP_NEGATIVE_TEMP;
 }
 
+// eqdsk_magnetics_spline_interp (L/eqdsk_magnetics_spline_interp_m.f90:206-282): psi(R,Z) as a bicubic spline of
+// the g-file's grid (shifted to 0 on axis), R*Bphi as a cubic spline -- on the R grid, as the reference builds it
+// (:184, (R)) -- B = grad(psi) x grad(phi) + RBphi grad(phi)
+template <class R>
+inline void eqdsk_magnetics(const rays_axisym_eq &p, R x, R y, R z, R r, R bvec[3], R g[3][3], R &psi, R gradpsi[3], R &psiN, R gradpsiN[3]) {
+    R PsiR(0.0), PsiZ(0.0), PsiRR(0.0), PsiRZ(0.0), PsiZZ(0.0), RBphi(0.0), RBphiR(0.0);
+    psi = R(0.0);
+    bcspeval_fpp(r, z, p.Psi_spline, psi, PsiR, PsiZ, PsiRR, PsiZZ, PsiRZ);
+    cspeval(r, p.T_spline, RBphi, &RBphiR);
+    R br = PsiZ / r;
+    R bz = -PsiR / r;
+    R bphi = RBphi / r;
+    gradpsi[0] = -x * bz; gradpsi[1] = -y * bz; gradpsi[2] = r * br;
+    psiN = psi / p.eq_psibound;
+    for (int i = 0; i < 3; ++i) gradpsiN[i] = gradpsi[i] / p.eq_psibound;
+    R dbrdr = -br / r + PsiRZ / r;
+    R dbrdz = PsiZZ / r;
+    R dbzdr = -bz / r - PsiRR / r;
+    R dbzdz = -PsiRZ / r;
+    R dbphidr = (RBphiR - bphi) / r;
+    bvec[0] = br * x / r - bphi * y / r;
+    bvec[1] = br * y / r + bphi * x / r;
+    bvec[2] = bz;
+    g[0][0] = (dbrdr * (x * x) + br * (y * y) / r + (-dbphidr + bphi / r) * x * y) / (r * r);
+    g[1][0] = ((dbrdr - br / r) * x * y - dbphidr * (y * y) - bphi * (x * x) / r) / (r * r);
+    g[2][0] = dbrdz * x / r;
+    g[0][1] = ((dbrdr - br / r) * x * y + dbphidr * (x * x) + bphi * (y * y) / r) / (r * r);
+    g[1][1] = (dbrdr * (y * y) + br * (x * x) / r + (dbphidr - bphi / r) * x * y) / (r * r);
+    g[2][1] = dbrdz * y / r;
+    g[0][2] = dbzdr * x / r;
+    g[1][2] = dbzdr * y / r;
+    g[2][2] = dbzdz;
+}
+
 // axisym_toroid_eq + solovev_magnetics (L/axisym_toroid_eq_m.f90:215-362, L/solovev_magnetics_m.f90:124-207)
 template <class R> inline void axisym_toroid_eq(const rays_cfg &c, const R rvec[3], ModelOut<R> &m) {
     const rays_axisym_eq &p = c.axisym;
@@ -383,7 +453,9 @@ template <class R> inline void axisym_toroid_eq(const rays_cfg &c, const R rvec[
     if (z < p.box_zmin - Tiny || z > p.box_zmax + Tiny) m.equib_err = RAYS_STOP_Z_OUT_OF_BOX;
     if (m.equib_err != 0) return;
     R psi, gradpsi[3], psiN, grad_psiN[3];
-    {   // solovev_magnetics
+    if (p.magnetics_model == RAYS_MAG_EQDSK_SPLINE) {
+        eqdsk_magnetics(p, x, y, z, r, m.bvec, m.gradbtensor, psi, gradpsi, psiN, grad_psiN);
+    } else {   // solovev_magnetics
         if (r < p.sm_box_rmin || r > p.sm_box_rmax) m.equib_err = RAYS_STOP_R_OUT_OF_BOUNDS_SOLMAG;
         if (z < p.sm_box_zmin || z > p.sm_box_zmax) m.equib_err = RAYS_STOP_Z_OUT_OF_BOUNDS_SOLMAG;
         if (m.equib_err != 0) {
@@ -447,6 +519,19 @@ template <class R> inline void axisym_toroid_eq(const rays_cfg &c, const R rvec[
 template <class R>
 inline void axisym_toroid_psi(const rays_cfg &c, const R rvec[3], R &psi, R gradpsi[3], R &psiN, R gradpsiN[3]) {
     const rays_axisym_eq &p = c.axisym;
+    if (p.magnetics_model == RAYS_MAG_EQDSK_SPLINE) {   // eqdsk_magnetics_spline_interp_psi (L/eqdsk_magnetics_spline_interp_m.f90:286-318)
+        R x = rvec[0], y = rvec[1], z = rvec[2];
+        R r = Sqrt(x * x + y * y);
+        R PsiR(0.0), PsiZ(0.0);
+        psi = R(0.0);
+        bcspeval_fp(r, z, p.Psi_spline, psi, PsiR, PsiZ);
+        R br = PsiZ / r;
+        R bz = -PsiR / r;
+        gradpsi[0] = -x * bz; gradpsi[1] = -y * bz; gradpsi[2] = r * br;
+        psiN = psi / p.eq_psibound;
+        for (int i = 0; i < 3; ++i) gradpsiN[i] = gradpsi[i] / p.eq_psibound;
+        return;
+    }
     solovev_psi(rvec, p.sm_bphi0, p.sm_iota0, p.sm_rmaj, p.sm_kappa, p.sm_psiB, psi, gradpsi, psiN, gradpsiN);
 }
 

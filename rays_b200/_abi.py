@@ -19,6 +19,7 @@ EQ_OUT = 106
 EQ_SLAB, EQ_SOLOVEV, EQ_AXISYM_TOROID, EQ_MULTIPLE_MIRROR = 1, 2, 3, 4
 ODE_RK4, ODE_SG = 1, 2
 DERIV_COLD, DERIV_NUM = 1, 2
+MAG_SOLOVEV, MAG_EQDSK_SPLINE = 1, 2
 PROF_SPLINE = 7   # enum rays_prof_model: density_spline_interp / temperature_spline_interp
 PARAM_ARCL, PARAM_TIME = 1, 2
 DAMP_NONE, DAMP_FUND_ECH = 0, 1
@@ -57,7 +58,8 @@ class AxisymEq(C.Structure):
                                   "lower_bound", "plasma_psi_limit", "alphan1", "alphan2", "d_scrape_off", "T_scrape_off")] + [
         ("alphat1", D6), ("alphat2", D6)] + [
         (n, C.c_double) for n in ("sm_rmaj", "sm_kappa", "sm_bphi0", "sm_iota0", "sm_psiB", "sm_box_rmin", "sm_box_rmax", "sm_box_zmin", "sm_box_zmax")] + [
-        ("ne_spline", Spline1D), ("Te_spline", Spline1D), ("Ti_spline", Spline1D)]
+        ("ne_spline", Spline1D), ("Te_spline", Spline1D), ("Ti_spline", Spline1D),
+        ("Psi_spline", Spline2D), ("T_spline", Spline1D), ("eq_psibound", C.c_double)]
 
 
 class MirrorEq(C.Structure):

@@ -10,7 +10,9 @@
 // Fatal configuration errors, which `stop 1` in the reference, return a nonzero status and set
 // rays_host_last_error().  Numerical habits that shape results are reproduced: default-kind real
 // literals are single precision widened to double.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <ctime>
@@ -116,6 +118,7 @@ struct State {
     std::vector<double> z_x, z_re, z_im;
     std::vector<double> r_grid, z_grid, Br_fspl, Bz_fspl, Aphi_fspl;
     std::vector<double> ne_grid, ne_fspl, T_grid, Te_fspl, Ti_fspl;   // density/temperature_spline_interp_m
+    std::vector<double> eq_r_grid, eq_z_grid, eq_psi_fspl, eq_T_fspl;   // eqdsk_magnetics_spline_interp_m
     std::string workdir;
     std::string namelist_path;
     bool initialized = false;
@@ -312,6 +315,118 @@ static int initialize_solovev_eq_m(State &S, const NamelistFile &nml) {
     return 0;
 }
 
+static int spline2d_init(const std::vector<double> &rg, const std::vector<double> &zg, const std::vector<double> &f_c_order, std::vector<double> &fspl);
+
+// ReadgFile (eqdsk_utilities_m.f90:52-108): formatted reads '(a48,3i4)', '(5e16.9)', '(2i5)' -- fixed-width fields, a new
+// record per read statement, missing trailing fields read as blanks (= 0)
+struct GFile {
+    int NRBOX = 0, NZBOX = 0, NBOUND = 0, NLIM = 0;
+    double RBOXLEN = 0, ZBOXLEN = 0, R0 = 0, RBOXLFT = 0, ZOFF = 0, RAXIS = 0, ZAXIS = 0, PSIAXIS = 0, PSIBOUND = 0, B0 = 0, CURRENT = 0;
+    std::vector<double> T, P, TTp, Pp, Q, Psi, RBOUND, ZBOUND;
+};
+static int read_gfile(const std::string &path, GFile &g) {
+    FILE *fp = std::fopen(path.c_str(), "r");
+    if (!fp) return fail("ReadgFile: cannot open " + path);
+    std::vector<std::string> lines;
+    {
+        std::string cur;
+        int ch;
+        while ((ch = std::fgetc(fp)) != EOF) {
+            if (ch == '\n') { lines.push_back(cur); cur.clear(); } else if (ch != '\r') cur.push_back((char)ch);
+        }
+        if (!cur.empty()) lines.push_back(cur);
+        std::fclose(fp);
+    }
+    size_t ln = 0;
+    bool bad = false;
+    auto field = [&](const std::string &L, size_t pos, size_t w) { return pos < L.size() ? L.substr(pos, w) : std::string(); };
+    auto to_int = [&](std::string f) { f = trim(f); if (f.empty()) return 0; char *e; long v = std::strtol(f.c_str(), &e, 10); if (*e) bad = true; return (int)v; };
+    auto to_real = [&](std::string f) {
+        f = trim(f);
+        if (f.empty()) return 0.0;
+        for (char &c : f) if (c == 'D' || c == 'd') c = 'E';
+        char *e; double v = std::strtod(f.c_str(), &e); if (*e) bad = true; return v;
+    };
+    auto reals = [&](double *out, size_t n) {   // one read statement: '(5e16.9)' over as many records as the list needs
+        size_t got = 0;
+        while (got < n) {
+            if (ln >= lines.size()) { bad = true; return; }
+            const std::string &L = lines[ln++];
+            for (int k = 0; k < 5 && got < n; ++k) out[got++] = to_real(field(L, 16 * (size_t)k, 16));
+        }
+    };
+    if (lines.empty()) return fail("ReadgFile: empty file " + path);
+    {
+        const std::string &L = lines[ln++];
+        (void)to_int(field(L, 48, 4)); g.NRBOX = to_int(field(L, 52, 4)); g.NZBOX = to_int(field(L, 56, 4));
+    }
+    if (bad || g.NRBOX < 4 || g.NZBOX < 4) return fail("ReadgFile: bad header (NRBOX, NZBOX) in " + path);
+    double h[5];
+    reals(h, 5); g.RBOXLEN = h[0]; g.ZBOXLEN = h[1]; g.R0 = h[2]; g.RBOXLFT = h[3]; g.ZOFF = h[4];
+    reals(h, 5); g.RAXIS = h[0]; g.ZAXIS = h[1]; g.PSIAXIS = h[2]; g.PSIBOUND = h[3]; g.B0 = h[4];
+    reals(h, 5); g.CURRENT = h[0];
+    reals(h, 5);
+    const size_t nr = (size_t)g.NRBOX, nz = (size_t)g.NZBOX;
+    g.T.resize(nr); g.P.resize(nr); g.TTp.resize(nr); g.Pp.resize(nr); g.Q.resize(nr); g.Psi.resize(nr * nz);
+    reals(g.T.data(), nr); reals(g.P.data(), nr); reals(g.TTp.data(), nr); reals(g.Pp.data(), nr);
+    reals(g.Psi.data(), nr * nz);   // ((Psi(i,j), i = 1, NRBOX), j = 1, NZBOX): R fastest
+    reals(g.Q.data(), nr);
+    if (bad || ln >= lines.size()) return fail("ReadgFile: truncated or malformed file " + path);
+    {
+        const std::string &L = lines[ln++];
+        g.NBOUND = to_int(field(L, 0, 5)); g.NLIM = to_int(field(L, 5, 5));
+    }
+    if (bad || g.NBOUND < 1) return fail("ReadgFile: bad NBOUND in " + path);
+    std::vector<double> rz(2 * (size_t)g.NBOUND);
+    reals(rz.data(), rz.size());
+    if (bad) return fail("ReadgFile: truncated boundary in " + path);
+    g.RBOUND.resize((size_t)g.NBOUND); g.ZBOUND.resize((size_t)g.NBOUND);
+    for (int i = 0; i < g.NBOUND; ++i) { g.RBOUND[(size_t)i] = rz[2 * (size_t)i]; g.ZBOUND[(size_t)i] = rz[2 * (size_t)i + 1]; }
+    return 0;   // the limiter contour is not used on the path
+}
+
+// initialize_eqdsk_magnetics_spline_interp (eqdsk_magnetics_spline_interp_m.f90:68-200): geometry from the g-file,
+// psi shifted to zero on axis, Psi_profile (bicubic) and T_profile (R*Bphi; splined on R_grid as the reference does).
+// The q / rho / toroidal-flux profiles built there serve post-processing only and are not on the ray path.
+static int initialize_eqdsk_magnetics(State &S, const NamelistFile &nml) {
+    rays_axisym_eq &p = S.cfg.axisym;
+    std::string file, err;
+    NamelistGroup G("eqdsk_magnetics_spline_interp_list");
+    G.add("eqdsk_file_name", &file);
+    if (!G.read(nml, err)) return fail(err);
+    file = trim(file);
+    if (!file.empty() && file[0] != '/' && !S.workdir.empty()) file = S.workdir + "/" + file;
+    GFile g;
+    int rc = read_gfile(file, g);
+    if (rc) return rc;
+    p.r_axis = g.RAXIS; p.z_axis = g.ZAXIS;
+    p.box_rmin = g.RBOXLFT; p.box_rmax = p.box_rmin + g.RBOXLEN;
+    p.box_zmin = g.ZOFF - g.ZBOXLEN / 2.; p.box_zmax = g.ZOFF + g.ZBOXLEN / 2.;
+    p.inner_bound = *std::min_element(g.RBOUND.begin(), g.RBOUND.end());
+    p.outer_bound = *std::max_element(g.RBOUND.begin(), g.RBOUND.end());
+    p.lower_bound = *std::min_element(g.ZBOUND.begin(), g.ZBOUND.end());
+    p.upper_bound = *std::max_element(g.ZBOUND.begin(), g.ZBOUND.end());
+    const int nr = g.NRBOX, nz = g.NZBOX;
+    S.eq_r_grid.resize((size_t)nr); S.eq_z_grid.resize((size_t)nz);
+    for (int i = 1; i <= nr; ++i) S.eq_r_grid[(size_t)i - 1] = p.box_rmin + (p.box_rmax - p.box_rmin) * (i - 1) / (nr - 1);
+    for (int i = 1; i <= nz; ++i) S.eq_z_grid[(size_t)i - 1] = p.box_zmin + (p.box_zmax - p.box_zmin) * (i - 1) / (nz - 1);
+    for (double &v : g.Psi) v = v - g.PSIAXIS;
+    p.eq_psibound = g.PSIBOUND - g.PSIAXIS;
+    if (p.eq_psibound == 0.0) return fail("eqdsk_magnetics: PSIBOUND equals PSIAXIS");
+    if (spline2d_init(S.eq_r_grid, S.eq_z_grid, g.Psi, S.eq_psi_fspl)) return fail("cube_spline_2D_init: Psi_profile, grid not evenly spaced or error");
+    S.eq_T_fspl.assign((size_t)4 * nr, 0.0);
+    for (int i = 0; i < nr; ++i) S.eq_T_fspl[4 * (size_t)i] = g.T[(size_t)i];
+    int ilinx = 0;
+    if (cspline(S.eq_r_grid.data(), nr, S.eq_T_fspl.data(), &ilinx) || ilinx != 1) return fail("cube_spline_1D_init: T_profile failed");
+    p.Psi_spline.nx = nr; p.Psi_spline.ny = nz; p.Psi_spline.x_grid = S.eq_r_grid.data(); p.Psi_spline.y_grid = S.eq_z_grid.data();
+    p.Psi_spline.fspl = S.eq_psi_fspl.data();
+    p.T_spline.nx = nr; p.T_spline.pad_ = 0; p.T_spline.x_grid = S.eq_r_grid.data(); p.T_spline.fspl = S.eq_T_fspl.data();
+    // solovev_magnetics module data is not used by this model
+    p.sm_rmaj = p.sm_kappa = p.sm_bphi0 = p.sm_iota0 = p.sm_psiB = 0.0;
+    p.sm_box_rmin = p.box_rmin; p.sm_box_rmax = p.box_rmax; p.sm_box_zmin = p.box_zmin; p.sm_box_zmax = p.box_zmax;
+    return 0;
+}
+
 static int initialize_axisym_toroid_eq_m(State &S, const NamelistFile &nml) {
     rays_axisym_eq &p = S.cfg.axisym;
     p.plasma_psi_limit = 1.0;
@@ -327,10 +442,15 @@ static int initialize_axisym_toroid_eq_m(State &S, const NamelistFile &nml) {
     std::string err;
     if (!G.read(nml, err)) return fail(err);
     magnetics = trim(magnetics);
-    if (magnetics != "solovev_magnetics")
-        return fail("initialize_axisym_toroid_eq: unknown magnetics model =" + magnetics + " (eqdsk magnetics are outside the hot-path scope)");
-    p.magnetics_model = RAYS_MAG_SOLOVEV;
-    {   // initialize_solovev_magnetics (solovev_magnetics_m.f90:47-120)
+    p.Psi_spline = rays_spline2d{}; p.T_spline = rays_spline1d{}; p.eq_psibound = 0.0;
+    if (magnetics == "eqdsk_magnetics_spline_interp") {
+        p.magnetics_model = RAYS_MAG_EQDSK_SPLINE;
+        int rc = initialize_eqdsk_magnetics(S, nml);
+        if (rc) return rc;
+    } else if (magnetics != "solovev_magnetics")
+        return fail("initialize_axisym_toroid_eq: unknown magnetics model =" + magnetics + " (eqdsk_magnetics_lin_interp is not provided)");
+    else {   // initialize_solovev_magnetics
+        p.magnetics_model = RAYS_MAG_SOLOVEV;   // (solovev_magnetics_m.f90:47-120)
         double outer_boundary = 0.0;
         NamelistGroup M("solovev_magnetics_list");
         M.add("rmaj", &p.sm_rmaj); M.add("outer_boundary", &outer_boundary); M.add("kappa", &p.sm_kappa);

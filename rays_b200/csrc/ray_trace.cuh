@@ -580,6 +580,7 @@ RD_INLINE void bin_segment(double *bins, int n_bins, double xmin, double xmax, d
 // (deposition_profiles_m.f90:438-499)
 template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
     if (EQ_ == RAYS_EQ_SLAB) return v[0];
+    if (EQ_ == RAYS_EQ_AXISYM_TOROID && g_dc.c.axisym.magnetics_model == RAYS_MAG_EQDSK_SPLINE) return eqdsk_psiN(v[0], v[1], v[2]);
     return solovev_psiN(v[0], v[1], v[2]);
 }
 

@@ -69,6 +69,7 @@ struct Ctx {
     KernelSel sel{};
     DevBuf<double> zx, zf, rgrid, zgrid, br, bz, aphi;
     DevBuf<double> prof_grid[3], prof_fspl[3];   // axisym 1-D profile splines: ne, Te, Ti
+    DevBuf<double> eq_rgrid, eq_zgrid, eq_psi, eq_T;   // eqdsk magnetics: Psi_profile, T_profile
     // fan (device)
     long long nray = 0;
     DevBuf<double> rvec0, nvec0, wt;
@@ -145,6 +146,11 @@ int validate_cfg(const rays_cfg &c) {
     if (c.equilib_model == RAYS_EQ_AXISYM_TOROID) {
         const rays_axisym_eq &a = c.axisym;
         auto ok = [](const rays_spline1d &s) { return s.x_grid && s.fspl && s.nx >= 2; };
+        if (a.magnetics_model != RAYS_MAG_SOLOVEV && a.magnetics_model != RAYS_MAG_EQDSK_SPLINE)
+            return set_err(RAYS_ERR_INVALID_CONFIG, "initialize_axisym_toroid_eq: unknown magnetics model");
+        if (a.magnetics_model == RAYS_MAG_EQDSK_SPLINE &&
+            (!a.Psi_spline.fspl || !a.Psi_spline.x_grid || !a.Psi_spline.y_grid || a.Psi_spline.nx < 2 || a.Psi_spline.ny < 2 || !ok(a.T_spline) || a.eq_psibound == 0.0))
+            return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: eqdsk_magnetics_spline_interp tables missing");
         if (a.density_prof_model == RAYS_PROF_SPLINE && !ok(a.ne_spline))
             return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: density_spline_interp table missing");
         for (int s = 0; s <= c.nspec; ++s)
@@ -507,7 +513,7 @@ int rays_b200_finalize(void) {
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.prof_grid[0], &g.prof_grid[1], &g.prof_grid[2],
-                              &g.prof_fspl[0], &g.prof_fspl[1], &g.prof_fspl[2], &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
+                              &g.prof_fspl[0], &g.prof_fspl[1], &g.prof_fspl[2], &g.eq_rgrid, &g.eq_zgrid, &g.eq_psi, &g.eq_T, &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
                               &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv, &g.dep};
     for (auto *b : bufs) b->release();
     g.npoints.release(); g.stop.release(); g.queue.release();
@@ -574,6 +580,20 @@ int rays_b200_set_config(const rays_cfg *cfg) {
             sp[k]->nx = src[k]->nx; sp[k]->x_grid = g.prof_grid[k].p; sp[k]->fspl = g.prof_fspl[k].p;
         }
     }
+    c.axisym.Psi_spline = rays_spline2d{}; c.axisym.T_spline = rays_spline1d{};
+    if (c.equilib_model == RAYS_EQ_AXISYM_TOROID && c.axisym.magnetics_model == RAYS_MAG_EQDSK_SPLINE) {
+        const rays_axisym_eq &a = cfg->axisym;   // eqdsk_magnetics_spline_interp_m: Psi_profile (bicubic), T_profile (cubic)
+        const size_t nx = (size_t)a.Psi_spline.nx, ny = (size_t)a.Psi_spline.ny, nt = (size_t)a.T_spline.nx;
+        if ((rc = upload_table(g.eq_rgrid, a.Psi_spline.x_grid, nx))) return rc;
+        if ((rc = upload_table(g.eq_zgrid, a.Psi_spline.y_grid, ny))) return rc;
+        if ((rc = upload_table(g.eq_psi, a.Psi_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(g.eq_T, a.T_spline.fspl, 4 * nt))) return rc;
+        c.axisym.Psi_spline.nx = a.Psi_spline.nx; c.axisym.Psi_spline.ny = a.Psi_spline.ny;
+        c.axisym.Psi_spline.x_grid = g.eq_rgrid.p; c.axisym.Psi_spline.y_grid = g.eq_zgrid.p; c.axisym.Psi_spline.fspl = g.eq_psi.p;
+        c.axisym.T_spline.nx = a.T_spline.nx; c.axisym.T_spline.fspl = g.eq_T.p;
+        if (a.T_spline.x_grid == a.Psi_spline.x_grid && nt == nx) c.axisym.T_spline.x_grid = g.eq_rgrid.p;
+        else return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: T_profile must be splined on the g-file's R grid (eqdsk_magnetics_spline_interp_m.f90:184)");
+    }
     // constant products, formed with the same IEEE operations the reference performs per call
     for (int s = 0; s < RAYS_NSPECIES; ++s) { d.qs2[s] = c.qs[s] * c.qs[s]; d.eps0ms[s] = c.eps0 * c.ms[s]; }
     d.omgrf2 = c.omgrf * c.omgrf;
@@ -605,6 +625,7 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     for (int s = 0; s < RAYS_NSPECIES; ++s) { d.rc_ms[s] = mk(c.ms[s]); d.rc_eps0ms[s] = mk(d.eps0ms[s]); }
     d.rc_rk = mk(d.sv_rk); d.rc_rk2 = mk(d.sv_rk2); d.rc_rmaj = mk(d.sv_rmaj); d.rc_rmaj2 = mk(d.sv_rmaj2); d.rc_psiB = mk(d.sv_psiB);
     d.rc_Aphi_LUFS = mk(c.mirror.Aphi_LUFS);
+    d.rc_eq_psibound = mk(c.axisym.eq_psibound);
     d.rc_two_delta = mk(d.dn_two_delta); d.rc_omg_p = mk(d.dn_omg_p); d.rc_omg_m = mk(d.dn_omg_m); d.rc_omg_p2 = mk(d.dn_omg_p2);
     d.rc_omg_m2 = mk(d.dn_omg_m2); d.rc_k0_p = mk(d.dn_k0_p); d.rc_k0_m = mk(d.dn_k0_m); d.rc_omg_delta = mk(d.dn_omg_delta);
     {   // are the temperatures read by anything on this run's path?
