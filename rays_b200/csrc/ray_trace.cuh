@@ -214,7 +214,7 @@ __device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.
 // RHS of all its lanes at ONE place per loop iteration, whatever phase of the integrator each lane is in
 // (the straight transcription called eqn_ray from three divergent sites and ran at 1 % of the FP64 peak).
 // The arithmetic of every piece is the reference's, statement by statement.
-enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_CHECK, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3 };
+enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_CHECK, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3, SG_RETRY };
 
 // step, first block (:840-852): tests for too small a step / tolerance; returns true on crash
 template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps) {
@@ -508,6 +508,7 @@ struct TraceArgs {
     // launches the kernel again over that list (resume = 1), where the survivors are packed into full warps.
     int slice_steps;
     int resume;
+    int sg_align;                   // SG kernel: 1 = lanes advance in alternating predictor / corrector slots (see trace_sg_kernel)
     double *cont_state;             // [nray][kContStride]
     int *cont_list;
     unsigned long long *cont_count;
@@ -701,6 +702,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
     int slice_n = 0;     // steps this ray has taken in this launch
     bool have_f1 = false;     // W.yp holds the derivative at v evaluated together with check_save
     int f1_code = 0;
+    bool slot_b = false;      // warp-uniform: type of the current slot (see the alignment note in the loop)
 
     for (;;) {
         // ---- refill from the work queue (one atomic per warp)
@@ -747,13 +749,26 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
         }
         bool stop = false, did_not_start = false;
 
-        // Lanes run free: each is in its own integrator phase (measured lane utilisation 34 %).  Re-synchronising the
-        // warp at segment boundaries was tried and is 2x slower: segments differ too much in internal step count.
+        // Slot alignment.  Left alone, every lane is in its own integrator phase and the bookkeeping blocks below run
+        // one after the other with a quarter of the lanes each (ncu: 65 % of all warp instructions at 6-9 active
+        // lanes).  An internal step is predictor work -> derivative at p -> corrector work -> derivative at yy, so the
+        // warp alternates two slot types: in an A slot only lanes whose next block is predictor-side work take part
+        // (segment start, after_correct, retry after a failed step), in a B slot only lanes due for after_predict.
+        // A lane that is out of phase (after a segment's check_save, after a failure) sits out one slot and is in
+        // step with the others from then on; check_save itself needs no bookkeeping and runs in either slot.
+        // (Re-synchronising at segment boundaries instead was 2x slower: segments differ in internal step count.)
+        bool go = true;
+        if (a.sg_align) {
+            const bool b_type = st == SG_AFTER_R2;
+            go = st == SG_CHECK || (st != SG_IDLE && (slot_b ? b_type : !b_type));
+            if (__ballot_sync(0xffffffffu, go) == 0u) { slot_b = !slot_b; continue; }
+            slot_b = !slot_b;
+        }
         // ---- lane-private integrator bookkeeping up to the next derivative evaluation
         int req = 0;               // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
                                    // 4: check_save of the new point v + the start derivative of the next segment there
         bool need_predict = false, de_top = false, crashed = false;
-        if (!stop) {
+        if (go) {
             if (st == SG_CHECK) req = 4;
             else if (st == SG_DE_BEGIN || st == SG_AFTER_CHECK) {   // ode/de entry with iflag = 1 (ode_RAYS.f90:425-505)
                 t = s;
@@ -783,8 +798,10 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
             } else if (st == SG_AFTER_R2) {
                 const int r = sg_after_predict<NV>(nv, W, eps);
                 if (r == 0) req = 3;
-                else if (r == 1) need_predict = true;
+                else if (r == 1) { if (a.sg_align) st = SG_RETRY; else need_predict = true; }   // failed: predict again with the reduced step
                 else crashed = true;
+            } else if (st == SG_RETRY) {
+                need_predict = true;
             } else if (st == SG_AFTER_R3) {
                 sg_after_correct<NV>(nv, W, eps);
                 nostep = nostep + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)

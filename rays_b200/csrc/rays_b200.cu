@@ -348,6 +348,8 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
     bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
     if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) { slice = atoi(env); forced = true; } }
+    a.sg_align = 1;        // measurement aid: RAYS_B200_SG_ALIGN=0 lets the SG lanes run free (results are identical)
+    if (const char *env = getenv("RAYS_B200_SG_ALIGN")) { if (env[0]) a.sg_align = atoi(env) != 0; }
     if (slice > 0) {
         CK(g.cont_state.reserve((size_t)count * kContStride));
         CK(g.cont_list[0].reserve((size_t)count)); CK(g.cont_list[1].reserve((size_t)count));
