@@ -347,6 +347,9 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     int slice = 0;
     if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
     bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
+    // An SG ray-step is ~25 right-hand sides and the lanes of a warp drift apart in integrator phase: short slices on
+    // every pass keep the warps packed (1M-ray Solov'ev fan, tol 1e-6: 250 -> 64 steps: 5.15e7 -> 5.65e7 ray-steps/s)
+    if (c.ode_solver == RAYS_ODE_SG && count >= 2 * lanes) { slice = 64; forced = true; }
     if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) { slice = atoi(env); forced = true; } }
     a.sg_align = 1;        // measurement aid: RAYS_B200_SG_ALIGN=0 lets the SG lanes run free (results are identical)
     if (const char *env = getenv("RAYS_B200_SG_ALIGN")) { if (env[0]) a.sg_align = atoi(env) != 0; }
