@@ -306,6 +306,25 @@ int rays_b200_deposition(rays_deposition *dep, double *d_profile_out);
 /* Same, fused into the trace: bins while tracing, no trajectory storage needed. */
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories);
 
+/* ======================= mirror coil fields (row f4) ====================================== */
+/* One coil of the mirror coil set: coil_type + /coil_data_list/ + /current_data_list/
+ * (mirror_magnetics_lib/mirror_magnetics_m.f90:62-75, 101-115).  The conductors are modelled as
+ * n_r_layers x n_z_slices circular filaments (positions: :222-239). */
+typedef struct rays_coil {
+    double inner_radius, outer_radius, z_center, z_width;
+    double I_coil;                    /* current per turn [A] */
+    int64_t n_turns;                  /* integer(KIND=8) in the reference */
+    int32_t n_r_layers, n_z_slices;
+} rays_coil;
+/* calculate_B_on_rz_grid (mirror_magnetics_m.f90:324-368): Br, Bz, Aphi of all coils on the uniform grid
+ * r_grid(n_r) x z_grid(n_z), one thread per grid point, coils and filaments summed in the reference's order
+ * (coil_Brz_field_1Amp :246-287, mirror_Brz_field :291-320, Brz_loop_scaled B_loop_m.f90:191-246, complete
+ * elliptic integrals by Carlson's RF/RD complete_elliptic_int_m.f90:38-507).  Outputs are HOST arrays in the
+ * order of the netCDF field file, [n_z][n_r] (= Fortran Br(n_r,n_z)); r_grid/z_grid may be NULL. */
+int rays_b200_mirror_brz_grid(const rays_coil *coils, int32_t n_coils, int32_t n_r, double r_min, double r_max,
+                              int32_t n_z, double z_min, double z_max, double *r_grid, double *z_grid,
+                              double *Br, double *Bz, double *Aphi);
+
 /* ======================= one-point probes for unit parity tests ========================== */
 /* equilibrium(rvec, eq) (equilibrium_m.f90:135-272) at n points.
  * out[n][RAYS_EQ_OUT] = bvec3, gradbtensor9 (Fortran order (i,j)->[i+3j]), ns6, gradns18 ([i+3s]),

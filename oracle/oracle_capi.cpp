@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "rays_oracle.hpp"
+#include "rays_oracle_coils.hpp"
 
 using namespace rays_oracle;
 
@@ -193,6 +194,20 @@ int oracle_deposition(const rays_cfg *cfg, const rays_results *res, rays_deposit
     double q = 0.0;
     for (int b = 0; b < nb; ++b) q += dep->profile[b];
     dep->Q_sum = q;
+    return 0;
+}
+// calculate_B_on_rz_grid (MM/mirror_magnetics_m.f90:324-368) + one loop field for unit checks
+int oracle_mirror_Brz_grid(const rays_coil *coils, int n_coils, int n_r, double r_min, double r_max, int n_z, double z_min, double z_max,
+                           double *r_grid, double *z_grid, double *Br, double *Bz, double *Aphi) {
+    mirror_Brz_grid(coils, n_coils, n_r, r_min, r_max, n_z, z_min, z_max, r_grid, z_grid, Br, Bz, Aphi);
+    return 0;
+}
+int oracle_Brz_loop_scaled(long n, const double *r, const double *z, double *Br, double *Bz, double *Aphi) {
+    for (long i = 0; i < n; ++i) Brz_loop_scaled(r[i], z[i], Br[i], Bz[i], Aphi[i]);
+    return 0;
+}
+int oracle_elliptic(long n, const double *m, double *K, double *E) {
+    for (long i = 0; i < n; ++i) { K[i] = elliptic_Km(m[i]); E[i] = elliptic_Em(m[i]); }
     return 0;
 }
 int oracle_binner(const double *Q, const double *xQ, int nx, double xmin, double xmax, double *binned, int n_bins) {

@@ -301,6 +301,32 @@ def probe_check_save(v: np.ndarray):
     return out, st
 
 
+def make_coils(coils) -> "C.Array":
+    """list of dicts (inner_radius, outer_radius, z_center, z_width, I_coil, n_turns, n_r_layers, n_z_slices) -> rays_coil[]"""
+    from ._abi import Coil
+    arr = (Coil * len(coils))()
+    for c, d in zip(arr, coils):
+        for k, v in d.items():
+            setattr(c, k, v)
+    return arr
+
+
+def mirror_Brz_grid(coils, n_r: int, r_min: float, r_max: float, n_z: int, z_min: float, z_max: float):
+    """calculate_B_on_rz_grid (mirror_magnetics_m.f90:324-368) on the GPU: r_grid, z_grid, Br, Bz, Aphi; fields [n_z][n_r]"""
+    arr = coils if not isinstance(coils, (list, tuple)) else make_coils(coils)
+    rg, zg = np.zeros(n_r), np.zeros(n_z)
+    Br, Bz, Aphi = (np.zeros((n_z, n_r)) for _ in range(3))
+    _ck(_lib().rays_b200_mirror_brz_grid(arr, len(arr), n_r, r_min, r_max, n_z, z_min, z_max, _dp(rg), _dp(zg), _dp(Br), _dp(Bz), _dp(Aphi)))
+    return rg, zg, Br, Bz, Aphi
+
+
+def mirror_magnetics(namelist_path: str, outdir: str = ".") -> str:
+    """program mirror_magnetics (mirror_magnetics_lib/mirror_magnetics.f90): namelists -> Brz_fields.<name>.nc; returns its path"""
+    buf = C.create_string_buffer(512)
+    _ck(_lib().rays_host_mirror_magnetics(str(namelist_path).encode(), str(outdir).encode(), buf, 512), host=True)
+    return buf.value.decode()
+
+
 def fp64_peak() -> tuple[float, float]:
     """(measured DFMA TFLOP/s, max SM clock MHz): the FP64 roofline denominator."""
     t, m = C.c_double(0), C.c_double(0)

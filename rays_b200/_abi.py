@@ -70,6 +70,12 @@ class MirrorEq(C.Structure):
         ("Br_spline", Spline2D), ("Bz_spline", Spline2D), ("Aphi_spline", Spline2D)]
 
 
+class Coil(C.Structure):
+    """rays_coil (include/rays_b200.h): one coil of the mirror coil set"""
+    _fields_ = [(n, C.c_double) for n in ("inner_radius", "outer_radius", "z_center", "z_width", "I_coil")] + [
+        ("n_turns", C.c_int64), ("n_r_layers", C.c_int32), ("n_z_slices", C.c_int32)]
+
+
 class Cfg(C.Structure):
     _fields_ = [
         ("clight", C.c_double), ("eps0", C.c_double),
@@ -135,13 +141,13 @@ ABI_SYMBOLS = [
     "rays_b200_fan_download", "rays_b200_deposition", "rays_b200_trace_device_binned",
     "rays_b200_probe_equilibrium", "rays_b200_probe_rhs", "rays_b200_probe_check_save",
     "rays_b200_fp64_peak", "rays_b200_host_alloc", "rays_b200_host_free", "rays_b200_stream", "rays_b200_version",
-    "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown",
+    "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown", "rays_b200_mirror_brz_grid",
 ]
 HOST_SYMBOLS = [
     "rays_host_initialize", "rays_host_trace_rays", "rays_host_finalize_run", "rays_host_deallocate", "rays_host_last_error",
     "rays_host_cfg", "rays_host_nspec", "rays_host_run_label", "rays_host_ray_init_model", "rays_host_launch_params",
     "rays_host_directions_in", "rays_host_set_ode", "rays_host_set_fan", "rays_host_get_fan", "rays_host_results",
-    "rays_host_zfun", "rays_host_cspline", "rays_host_bcspline",
+    "rays_host_zfun", "rays_host_cspline", "rays_host_bcspline", "rays_host_mirror_magnetics",
 ]
 
 # RAYS_B200_LIB overrides the library path (A/B experiments with alternative builds)
@@ -195,6 +201,9 @@ def load() -> C.CDLL:
         "rays_host_get_fan": (i64, [P(c_double_p), P(c_double_p), P(c_double_p)]),
         "rays_host_results": (i, [P(Results)]),
         "rays_host_zfun": (i, [dbl, dbl, P(dbl), P(dbl)]),
+        "rays_b200_mirror_brz_grid": (i, [P(Coil), C.c_int32, C.c_int32, dbl, dbl, C.c_int32, dbl, dbl, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, c_double_p]),
+        "rays_host_mirror_magnetics": (i, [cp, cp, C.c_char_p, i]),
         "rays_host_cspline": (i, [c_double_p, i, c_double_p]), "rays_host_bcspline": (i, [c_double_p, i, c_double_p, i, c_double_p]),
     }
     for name, (res, args) in protos.items():

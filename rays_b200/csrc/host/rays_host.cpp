@@ -945,6 +945,75 @@ int rays_host_trace_rays(void) {
     return 0;
 }
 
+// program mirror_magnetics (mirror_magnetics_lib/mirror_magnetics.f90:1-137): initialize_mirror_magnetics
+// (mirror_magnetics_m.f90:134-243: /mirror_magnetics_list/ from `namelist_path`, /coil_data_list/ and
+// /current_data_list/ from the files it names), calculate_B_on_rz_grid on the GPU (rays_b200_mirror_brz_grid),
+// write_mirror_fields_Brz_NC (:372-450) -> <outdir>/Brz_fields.<coil_set>_<current_set>_<case>.nc, the file
+// mirror_magnetics_spline_interp reads.  out_path (optional) receives the file name.
+int rays_host_mirror_magnetics(const char *namelist_path, const char *outdir, char *out_path, int out_len) {
+    std::string path = namelist_path ? namelist_path : "mirror_magnetics.nml";
+    size_t slash = path.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? std::string() : path.substr(0, slash);
+    auto resolve = [&](std::string f) { f = trim(f); return (!f.empty() && f[0] != '/' && !dir.empty()) ? dir + "/" + f : f; };
+    NamelistFile nml;
+    if (!nml.load(path)) return fail(nml.error());
+    std::string coil_data_file, current_data_file, case_name, err;
+    int n_r = 0, n_z = 0, n_coils = 0;
+    double r_min = 0.0, r_max = 0.0, z_min = 0.0, z_max = 0.0, r_LUFS = 0.0, z_LUFS = 0.0;
+    NamelistGroup G("mirror_magnetics_list");
+    G.add("case_name", &case_name); G.add("coil_data_file", &coil_data_file); G.add("current_data_file", &current_data_file);
+    G.add("n_coils", &n_coils); G.add("n_r", &n_r); G.add("n_z", &n_z); G.add("r_min", &r_min); G.add("r_max", &r_max);
+    G.add("z_min", &z_min); G.add("z_max", &z_max); G.add("r_lufs", &r_LUFS); G.add("z_lufs", &z_LUFS);
+    if (!G.read(nml, err)) return fail(err);
+    if (n_coils < 1 || n_r < 1 || n_z < 1) return fail("mirror_magnetics_list: n_coils, n_r, n_z must be >= 1");
+    const size_t nc = (size_t)n_coils;
+    std::vector<double> inner_radius(nc, 0.0), outer_radius(nc, 0.0), z_width(nc, 0.0), z_center(nc, 0.0), I_coil(nc, 0.0);
+    std::vector<int> n_turns(nc, 0), n_r_layers(nc, 0), n_z_slices(nc, 0);
+    std::string coil_set_name, current_set_name;
+    NamelistFile cf, uf;
+    if (!cf.load(resolve(coil_data_file))) return fail(cf.error());
+    NamelistGroup Cg("coil_data_list");
+    Cg.add("coil_set_name", &coil_set_name);
+    Cg.add_arr("inner_radius", inner_radius.data(), 1, n_coils); Cg.add_arr("outer_radius", outer_radius.data(), 1, n_coils);
+    Cg.add_arr("z_width", z_width.data(), 1, n_coils); Cg.add_arr("z_center", z_center.data(), 1, n_coils);
+    Cg.add_arr("n_turns", n_turns.data(), 1, n_coils); Cg.add_arr("n_r_layers", n_r_layers.data(), 1, n_coils);
+    Cg.add_arr("n_z_slices", n_z_slices.data(), 1, n_coils);
+    if (!Cg.read(cf, err)) return fail(err);
+    if (!uf.load(resolve(current_data_file))) return fail(uf.error());
+    NamelistGroup Ug("current_data_list");
+    Ug.add("current_set_name", &current_set_name); Ug.add_arr("i_coil", I_coil.data(), 1, n_coils);
+    if (!Ug.read(uf, err)) return fail(err);
+    std::vector<rays_coil> coils(nc);
+    for (size_t i = 0; i < nc; ++i) {
+        rays_coil &c = coils[i];
+        c.inner_radius = inner_radius[i]; c.outer_radius = outer_radius[i]; c.z_center = z_center[i]; c.z_width = z_width[i];
+        c.I_coil = I_coil[i]; c.n_turns = n_turns[i]; c.n_r_layers = n_r_layers[i]; c.n_z_slices = n_z_slices[i];
+    }
+    const size_t n = (size_t)n_r * n_z;
+    std::vector<double> r_grid((size_t)n_r), z_grid((size_t)n_z), Br(n), Bz(n), Aphi(n);
+    int rc = rays_b200_mirror_brz_grid(coils.data(), n_coils, n_r, r_min, r_max, n_z, z_min, z_max, r_grid.data(), z_grid.data(), Br.data(),
+                                       Bz.data(), Aphi.data());
+    if (rc) { g_err = rays_b200_last_error(); return rc; }
+    const std::string base_file_name = trim(coil_set_name) + "_" + trim(current_set_name) + "_" + trim(case_name);
+    const std::string nc_name = "Brz_fields." + base_file_name + ".nc";
+    NcWriter w;
+    int d_r = w.def_dim("n_r", n_r), d_z = w.def_dim("n_z", n_z);
+    int v0 = w.def_var("r_min", NC_DOUBLE, {}), v1 = w.def_var("r_max", NC_DOUBLE, {}), v2 = w.def_var("z_min", NC_DOUBLE, {});
+    int v3 = w.def_var("z_max", NC_DOUBLE, {}), v4 = w.def_var("r_LUFS", NC_DOUBLE, {}), v5 = w.def_var("z_LUFS", NC_DOUBLE, {});
+    int v6 = w.def_var("r_grid", NC_DOUBLE, {d_r}), v7 = w.def_var("z_grid", NC_DOUBLE, {d_z});
+    // Fortran dims [n_r_id, n_z_id] are stored reversed: C order (n_z, n_r)
+    int v8 = w.def_var("Br", NC_DOUBLE, {d_z, d_r}), v9 = w.def_var("Bz", NC_DOUBLE, {d_z, d_r}), v10 = w.def_var("Aphi", NC_DOUBLE, {d_z, d_r});
+    w.put_att_text("NC_file_name", nc_name);
+    w.put_double(v0, &r_min, 1); w.put_double(v1, &r_max, 1); w.put_double(v2, &z_min, 1); w.put_double(v3, &z_max, 1);
+    w.put_double(v4, &r_LUFS, 1); w.put_double(v5, &z_LUFS, 1);
+    w.put_double(v6, r_grid.data(), r_grid.size()); w.put_double(v7, z_grid.data(), z_grid.size());
+    w.put_double(v8, Br.data(), n); w.put_double(v9, Bz.data(), n); w.put_double(v10, Aphi.data(), n);
+    const std::string full = (outdir && outdir[0] ? std::string(outdir) + "/" : std::string()) + nc_name;
+    if (!w.close(full, err)) { g_err = err; return RAYS_ERR_IO; }
+    if (out_path && out_len > 0) { std::strncpy(out_path, full.c_str(), (size_t)out_len - 1); out_path[out_len - 1] = 0; }
+    return 0;
+}
+
 // finalize_run (RAYS_lib/finalize_run.f90:1-51) -> write_results_NC (ray_results_m.f90:171-249):
 // writes <outdir>/run_results.<run_label>.nc in netCDF classic format with the reference's
 // dimensions, variable names and types so post_process_RAYS / graphics_RAYS read it unchanged.

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "trace_tu.cuh"
+#include "coil_field.cuh"
 
 namespace rays_dev {
 #define RAYS_TU_DECL(eq, ode) extern const TuOps rays_tu_ops_##eq##_##ode;
@@ -1109,6 +1110,47 @@ int rays_b200_probe_rhs(int64_t n, const double *v, double *dvds, int32_t *stop)
 int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_t *stop) {
     if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
     return run_probe(2, n, v, (size_t)g.dc.c.nv, resid, 1, stop);
+}
+
+// ======================= mirror coil fields (row f4) ===========================================================
+int rays_b200_mirror_brz_grid(const rays_coil *coils, int32_t n_coils, int32_t n_r, double r_min, double r_max, int32_t n_z, double z_min,
+                              double z_max, double *r_grid, double *z_grid, double *Br, double *Bz, double *Aphi) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!coils || n_coils < 1 || n_r < 1 || n_z < 1 || !Br || !Bz || !Aphi) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_mirror_brz_grid: bad arguments");
+    for (int i = 0; i < n_coils; ++i)
+        if (coils[i].n_r_layers < 1 || coils[i].n_z_slices < 1 || !(coils[i].inner_radius > 0.0) || !(coils[i].outer_radius >= coils[i].inner_radius))
+            return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_mirror_brz_grid: coil needs n_r_layers, n_z_slices >= 1 and 0 < inner_radius <= outer_radius");
+    CK(cudaSetDevice(g.device));
+    // grids exactly as calculate_B_on_rz_grid forms them (mirror_magnetics_m.f90:340-356)
+    std::vector<double> rg((size_t)n_r), zg((size_t)n_z);
+    if (n_r == 1) rg[0] = r_min; else for (int i = 1; i <= n_r; ++i) rg[(size_t)i - 1] = r_min + (r_max - r_min) * (i - 1) / (n_r - 1);
+    if (n_z == 1) zg[0] = z_min; else for (int j = 1; j <= n_z; ++j) zg[(size_t)j - 1] = z_min + (z_max - z_min) * (j - 1) / (n_z - 1);
+    BLoopConst K;   // B_loop_m.f90:28-33: pi is a default-real literal widened to double
+    K.pi = (double)3.1415926535897932385f;
+    K.mu0 = K.pi * (double)4.e-7f;
+    K.c0 = K.mu0 / (2.0 * K.pi);
+    const size_t n = (size_t)n_r * n_z;
+    DevBuf<double> d_r, d_z, d_out;
+    rays_coil *d_coils = nullptr;
+    CK(d_r.reserve((size_t)n_r)); CK(d_z.reserve((size_t)n_z)); CK(d_out.reserve(3 * n));
+    CK(cudaMalloc(&d_coils, sizeof(rays_coil) * (size_t)n_coils));
+    cudaError_t e = cudaMemcpyAsync(d_coils, coils, sizeof(rays_coil) * (size_t)n_coils, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r.p, rg.data(), sizeof(double) * (size_t)n_r, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_z.p, zg.data(), sizeof(double) * (size_t)n_z, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) {
+        mirror_Brz_grid_kernel<<<(unsigned)((n + 63) / 64), 64, 0, g.stream>>>(d_coils, n_coils, K, n_r, n_z, d_r.p, d_z.p, d_out.p, d_out.p + n, d_out.p + 2 * n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Br, d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Bz, d_out.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Aphi, d_out.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(d_coils);
+    d_r.release(); d_z.release(); d_out.release();
+    CK(e);
+    if (r_grid) std::copy(rg.begin(), rg.end(), r_grid);
+    if (z_grid) std::copy(zg.begin(), zg.end(), z_grid);
+    return 0;
 }
 
 // ======================= measurement helpers =================================================================

@@ -139,6 +139,36 @@ def deposition(cfg, res: ResultArrays, n_bins, grid_min, grid_max):
     return prof, float(d.Q_sum)
 
 
+def mirror_Brz_grid(coils, n_r, r_min, r_max, n_z, z_min, z_max):
+    import rays_b200 as rb
+    L = load()
+    arr = coils if not isinstance(coils, (list, tuple)) else rb.make_coils(coils)
+    rg, zg = np.zeros(n_r), np.zeros(n_z)
+    Br, Bz, Aphi = (np.zeros((n_z, n_r)) for _ in range(3))
+    L.oracle_mirror_Brz_grid.argtypes = [C.POINTER(_abi.Coil), C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double] + [_abi.c_double_p] * 5
+    L.oracle_mirror_Brz_grid(arr, len(arr), n_r, r_min, r_max, n_z, z_min, z_max, _dp(rg), _dp(zg), _dp(Br), _dp(Bz), _dp(Aphi))
+    return rg, zg, Br, Bz, Aphi
+
+
+def Brz_loop_scaled(r, z):
+    L = load()
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    Br, Bz, A = np.zeros_like(r), np.zeros_like(r), np.zeros_like(r)
+    L.oracle_Brz_loop_scaled.argtypes = [C.c_long] + [_abi.c_double_p] * 5
+    L.oracle_Brz_loop_scaled(len(r), _dp(r), _dp(z), _dp(Br), _dp(Bz), _dp(A))
+    return Br, Bz, A
+
+
+def elliptic(m):
+    L = load()
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    K, E = np.zeros_like(m), np.zeros_like(m)
+    L.oracle_elliptic.argtypes = [C.c_long] + [_abi.c_double_p] * 3
+    L.oracle_elliptic(len(m), _dp(m), _dp(K), _dp(E))
+    return K, E
+
+
 def binner(Q, xQ, xmin, xmax, n_bins):
     L = load()
     Q = np.ascontiguousarray(Q, dtype=np.float64)
