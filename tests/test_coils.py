@@ -103,8 +103,8 @@ def test_gpu_grid_equals_oracle():
     # a window inside the small-r series (r < 1e-3 loop radii): real powers -> rounding-level agreement
     g = rb.mirror_Brz_grid(COILS, 17, 0.0, 2.0e-4, 33, 2.8, 3.6)
     o = orc.mirror_Brz_grid(COILS, 17, 0.0, 2.0e-4, 33, 2.8, 3.6)
-    for a, b in zip(g[2:], o[2:]):
-        assert np.allclose(a, b, rtol=1e-13, atol=0)
+    for a, b in zip(g[2:], o[2:]):   # B_r is a sum of 54 filament terms of both signs: tolerance against the field scale
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-13 * np.abs(b).max())
     # ragged shapes and a single-filament coil
     one = [dict(inner_radius=0.5, outer_radius=0.5, z_center=0.0, z_width=0.0, I_coil=1.0, n_turns=1, n_r_layers=1, n_z_slices=1)]
     g = rb.mirror_Brz_grid(one, 7, 0.0, 1.5, 1, 0.3, 0.3)
