@@ -264,10 +264,23 @@ def main():
     except Exception:
         pass
     avg_kernel_s = kernel_ms * 1e-3 / max(trace_launches, 1)
+    # DRAM bytes of the trace kernel from the committed `ncu --set full` capture of this very workload
+    # (profiles/r1_trace_rk4_1M_ncu_full_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of the first pass, which
+    # takes 79 % of the fan's kernel time); null for the measurement-aid workloads that have no capture
+    ncu_traffic = None
+    if not (args.rays or args.ode or args.deriv):
+        try:
+            txt = open(os.path.join(ROOT, "profiles", "r1_trace_rk4_1M_ncu_full_summary.txt")).read()
+            import re
+            rd = float(re.search(r"dram__bytes_read.sum \[Gbyte\] = ([0-9.]+)", txt).group(1))
+            wr = float(re.search(r"dram__bytes_write.sum \[Gbyte\] = ([0-9.]+)", txt).group(1))
+            ncu_traffic = (rd + wr) * 1e9
+        except Exception:
+            ncu_traffic = None
     achieved_tf = flops_per_step * (steps_total / max(trace_launches, 1)) / avg_kernel_s / 1e12
     wb_bytes = (nv + 1) * 8.0 * (steps_total / max(trace_launches, 1))
     roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                "traffic": None, "peak_source": "DFMA microbenchmark on this GPU in this run (rays_b200_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
+                "traffic": ncu_traffic, "peak_source": "DFMA microbenchmark on this GPU in this run (rays_b200_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
                 "flops_per_ray_step": flops_per_step, "kernel": kinfo["kernel"], "grid": kinfo["grid"], "ctas_per_sm": kinfo["blocks_per_sm"],
                 "hbm_writeback_gbs": wb_bytes / avg_kernel_s / 1e9, "avg_kernel_ms": avg_kernel_s * 1e3,
                 "resume_pass_ms": pilot_ms / max(trace_launches, 1), "launches_per_fan": kinfo["n_passes"],

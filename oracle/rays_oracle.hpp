@@ -15,8 +15,9 @@
 // trajectory points reproduced to the PDFs' resolution of 1e-6 pt (1.3e-9 ... 8.7e-9 m; 3e-14 m in z on
 // the equatorial-plane runs), ray lengths included (tests/golden/ref_plot_vectors.json,
 // tests/test_reference_plots.py); (b) the plasma Z function table M/"Splined Z function results.txt":48-85
-// (tests/golden/zfun_kat.json).  NOT pinned by reference output: RK4_ODE as a stepper, the mirror
-// equilibrium, deriv_num, damping (k and power are pinned only through the positions they drive).
+// (tests/golden/zfun_kat.json); (c) coarsely, RK4_ODE + the mirror equilibrium on the MPEX example's raster figure
+// (11 rays, 0.87 mm pixels: tests/golden/ref_raster_vectors.json).  NOT pinned by reference output: deriv_num,
+// damping (k and power are pinned only through the positions they drive), the axisym/eqdsk equilibria.
 //
 // Where the Fortran has undefined behaviour the oracle makes a documented deterministic choice
 // (marked "(X)" as in SURVEY.md A.5); the CUDA path makes the same choice.

@@ -1,0 +1,58 @@
+"""Golden vectors for the RK4 + mirror-equilibrium path from the reference's own output: the MPEX example directory
+ships a raster plot (matplotlib PNG, z-y plane) of the 11 rays the Fortran code traced with RK4_ODE through the
+spline-interpolated mirror field.  Resolution 0.87 mm per pixel on ~0.2 m long rays -- coarse next to the vector
+PDFs of the slab/Solov'ev examples (make_ref_plot_vectors.py), but it is the reference's result for this path.
+
+Extracts the ray-coloured pixels (saturated colours that are not the plot's pure blue / green / red guide lines)
+inside the window the rays occupy, in data coordinates; the axes frame (1-px spines) carries the axis limits
+z in [2.8, 3.6], y in [-0.2, 0.2] (set_XY_lim).  Also copies the example's input next to our configs.
+
+    python tests/golden/make_ref_raster_vectors.py   ->  tests/golden/ref_raster_vectors.json
+"""
+import json
+import os
+import shutil
+
+import numpy as np
+from PIL import Image
+
+REF = "/root/reference/examples_RAYS/MPEX_examples/MPX_2nd_harm_11_rays_nz_delta_d_0.05_psiP_0.05"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def main():
+    cfgdir = os.path.join(ROOT, "rays_b200", "configs", "mpex_nz")
+    os.makedirs(cfgdir, exist_ok=True)
+    shutil.copyfile(os.path.join(REF, "ray_init_2nd_harm_11_rays_nz.in"), os.path.join(cfgdir, "ray_init_2nd_harm_11_rays_nz.in"))
+    txt = open(os.path.join(REF, "rays.in")).read()   # the field file is the one already under configs/mpex/
+    open(os.path.join(cfgdir, "rays.in"), "w").write(txt.replace("mirror_field_NC_file = 'Brz_fields", "mirror_field_NC_file = '../mpex/Brz_fields"))
+
+    im = np.array(Image.open(os.path.join(REF, "Ray_trajectories.png")).convert("RGB")).astype(int)
+    dark = im.max(2) < 90
+    cols = [i for i, c in enumerate(dark.sum(0)) if c > 0.75 * im.shape[0]]
+    rows = [i for i, c in enumerate(dark.sum(1)) if c > 0.75 * im.shape[1]]
+    left, right, bottom = cols[0], cols[-1], rows[-1]
+    # the top spine coincides with the y = 0.2 grid edge; find it as the first row whose frame columns are both dark
+    top = next(i for i in range(im.shape[0]) if dark[i, left] and dark[i, right])
+    zmin, zmax, ymin, ymax = 2.8, 3.6, -0.2, 0.2
+    px_z, px_y = (zmax - zmin) / (right - left), (ymax - ymin) / (bottom - top)
+    r, g, b = im[:, :, 0], im[:, :, 1], im[:, :, 2]
+    sat = im.max(2) - im.min(2) > 60
+    # guide lines are drawn in pure blue / red / green and anti-aliased against white: (t, t, 255), (255, t, t), (t, g, t)
+    guide = ((b >= 235) & (np.abs(r - g) < 20) & (b > r + 10)) | ((r >= 245) & (np.abs(g - b) < 15)) | ((np.abs(r - b) < 6) & (g > r + 40) & (g < 140 + r // 2))
+    ys, xs = np.nonzero(sat & ~guide)
+    z = zmin + (xs - left) * px_z
+    y = ymax - (ys - top) * px_y
+    win = (z > 3.15) & (z < 3.31) & (y > -0.1165) & (y < -0.02)   # above the green LUFS line the rays end on
+    out = {"_doc": "made by tests/golden/make_ref_raster_vectors.py; ray-coloured pixel centres of the reference's MPEX nz figure, metres",
+           "png": "examples_RAYS/MPEX_examples/MPX_2nd_harm_11_rays_nz_delta_d_0.05_psiP_0.05/Ray_trajectories.png",
+           "namelist": "mpex_nz/rays.in", "h": "z", "v": "y", "pixel_h": px_z, "pixel_v": px_y,
+           "frame_px": [int(left), int(right), int(top), int(bottom)],
+           "pixels_h": [round(float(v), 6) for v in z[win]], "pixels_v": [round(float(v), 6) for v in y[win]]}
+    json.dump(out, open(os.path.join(HERE, "ref_raster_vectors.json"), "w"))
+    print("frame", left, right, top, bottom, "pixel", px_z, px_y, "ray pixels", int(win.sum()))
+
+
+if __name__ == "__main__":
+    main()
