@@ -439,7 +439,7 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
             hnew = h;
             if (p5eps < erk) {
                 const double temp2 = (double)(k + 1);
-                const double r = pow(p5eps / erk, 1.0 / temp2);
+                const double r = pow_ool(p5eps / erk, 1.0 / temp2);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(W.x)), h);
             }
