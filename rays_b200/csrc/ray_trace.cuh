@@ -216,6 +216,12 @@ __device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.
 // The arithmetic of every piece is the reference's, statement by statement.
 enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_CHECK, SG_AFTER_R1, SG_AFTER_R2, SG_AFTER_R3, SG_RETRY };
 
+// IEEE quotient / square root through the branch-free exact helpers of ray_physics.cuh (9 and 10 instructions inline
+// instead of ~20 / ~25 with a slow-path call each; the SG kernel is instruction-cache bound).  A zero divisor can only be
+// an error weight wt = releps*|y| + abseps with abs_err0 = 0 and y = 0: x/(+0) = x*inf, as IEEE has it.
+RD_INLINE double sg_quot(double x, const Rcp &c) { return c.d == 0.0 ? x * __longlong_as_double(0x7ff0000000000000LL) : qdiv(x, c); }
+RD_INLINE double sg_sqrt(double x) { return x == __longlong_as_double(0x7ff0000000000000LL) ? x : sqrt_rn(x); }   // sqrt_rn is for finite radicands
+RD_INLINE double sg_div(double x, double d) { return sg_quot(x, rcp_of(d)); }
 // step, first block (:840-852): tests for too small a step / tolerance; returns true on crash
 template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps) {
     const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
@@ -223,8 +229,8 @@ template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps)
     const double p5eps = 0.5 * eps;
     double sum = 0.0;
     #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) { const double q = W.yy[l] / W.wt[l]; sum = sum + q * q; }
-    W.round = twou * sqrt(sum);
+    for (int l = 0; l < neqn; ++l) { const double q = sg_div(W.yy[l], W.wt[l]); sum = sum + q * q; }
+    W.round = twou * sg_sqrt(sum);
     if (p5eps < W.round) { eps = 2.0 * W.round * (1.0 + fouru); return true; }
     W.g[1] = 1.0; W.g[2] = 0.5; W.sig[1] = 1.0;
     W.ifail = 0;
@@ -238,11 +244,11 @@ template <int NV> RD_INLINE void sg_after_start(int neqn, SGWork<NV> &W, double 
     #pragma unroll 1
     for (int l = 0; l < neqn; ++l) {
         W.phi[1][l] = W.yp[l]; W.phi[2][l] = 0.0;
-        const double q = W.yp[l] / W.wt[l]; tot = tot + q * q;
+        const double q = sg_div(W.yp[l], W.wt[l]); tot = tot + q * q;
     }
-    const double total = sqrt(tot);
+    const double total = sg_sqrt(tot);
     double absh = fabs(W.h);
-    if (eps < 16.0 * total * W.h * W.h) absh = 0.25 * sqrt(eps / total);
+    if (eps < 16.0 * total * W.h * W.h) absh = 0.25 * sg_sqrt(sg_div(eps, total));
     W.h = copysign(fmax(absh, fouru * fabs(W.x)), W.h);
     W.hold = 0.0;
     W.k = 1; W.kold = 0;
@@ -266,25 +272,25 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
     const int nsp1 = ns + 1;
     if (ns <= k) {
         beta[ns] = 1.0;
-        alpha[ns] = 1.0 / (double)ns;
+        alpha[ns] = sg_div(1.0, (double)ns);
         double temp1 = h * (double)ns;
         sig[nsp1] = 1.0;
         #pragma unroll 1
         for (int i = nsp1; i <= k; ++i) {
             const double temp2 = psi[i - 1];
             psi[i - 1] = temp1;
-            beta[i] = beta[i - 1] * psi[i - 1] / temp2;
+            beta[i] = sg_div(beta[i - 1] * psi[i - 1], temp2);
             temp1 = temp2 + h;
-            alpha[i] = h / temp1;
+            alpha[i] = sg_div(h, temp1);
             sig[i + 1] = (double)i * alpha[i] * sig[i];
         }
         psi[k] = temp1;
         if (ns <= 1) {
             #pragma unroll 1
-            for (int iq = 1; iq <= k; ++iq) { v[iq] = 1.0 / (double)(iq * (iq + 1)); w[iq] = v[iq]; }
+            for (int iq = 1; iq <= k; ++iq) { v[iq] = sg_div(1.0, (double)(iq * (iq + 1))); w[iq] = v[iq]; }
         } else {
             if (kold < k) {
-                v[k] = 1.0 / (double)(k * kp1);
+                v[k] = sg_div(1.0, (double)(k * kp1));
                 #pragma unroll 1
                 for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
             }
@@ -342,15 +348,17 @@ template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double
     double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
     #pragma unroll 1
     for (int l = 0; l < neqn; ++l) {
-        if (0 < km2) { const double q = (phi[km1][l] + yp[l] - phi[1][l]) / wt[l]; erkm2 = erkm2 + q * q; }
-        if (0 <= km2) { const double q = (phi[k][l] + yp[l] - phi[1][l]) / wt[l]; erkm1 = erkm1 + q * q; }
-        const double q = (yp[l] - phi[1][l]) / wt[l];
+        const Rcp wl = rcp_of(wt[l]);   // up to three quotients by the same weight
+        if (0 < km2) { const double q = sg_quot(phi[km1][l] + yp[l] - phi[1][l], wl); erkm2 = erkm2 + q * q; }
+        if (0 <= km2) { const double q = sg_quot(phi[k][l] + yp[l] - phi[1][l], wl); erkm1 = erkm1 + q * q; }
+        const double q = sg_quot(yp[l] - phi[1][l], wl);
         erk = erk + q * q;
     }
-    if (0 < km2) erkm2 = absh * sig[km1] * kSGgstr[km2] * sqrt(erkm2);
-    if (0 <= km2) erkm1 = absh * sig[k] * kSGgstr[km1] * sqrt(erkm1);
-    const double err = absh * sqrt(erk) * (g[k] - g[kp1]);
-    erk = absh * sqrt(erk) * sig[kp1] * kSGgstr[k];
+    if (0 < km2) erkm2 = absh * sig[km1] * kSGgstr[km2] * sg_sqrt(erkm2);
+    if (0 <= km2) erkm1 = absh * sig[k] * kSGgstr[km1] * sg_sqrt(erkm1);
+    const double rt_erk = sg_sqrt(erk);
+    const double err = absh * rt_erk * (g[k] - g[kp1]);
+    erk = absh * rt_erk * sig[kp1] * kSGgstr[k];
     int knew = k;
     if (0 < km2) {
         if (fmax(erkm1, erkm2) <= erk) knew = km1;
@@ -379,14 +387,16 @@ template <int NV> RD_INLINE int sg_after_predict(int neqn, SGWork<NV> &W, double
     W.phase1 = false;
     W.x = W.xold;
     #pragma unroll 1
-    for (int i = 1; i <= k; ++i)
+    for (int i = 1; i <= k; ++i) {
+        const Rcp bi = rcp_of(W.beta[i]);
         #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) phi[i][l] = (phi[i][l] - phi[i + 1][l]) / W.beta[i];
+        for (int l = 0; l < neqn; ++l) phi[i][l] = sg_quot(phi[i][l] - phi[i + 1][l], bi);
+    }
     #pragma unroll 1
     for (int i = 2; i <= k; ++i) W.psi[i - 1] = W.psi[i] - W.h;
     W.ifail = W.ifail + 1;
     double temp2 = 0.5;
-    if (3 < W.ifail) { if (p5eps < 0.25 * erk) temp2 = sqrt(p5eps / erk); }
+    if (3 < W.ifail) { if (p5eps < 0.25 * erk) temp2 = sg_sqrt(sg_div(p5eps, erk)); }
     if (3 <= W.ifail) knew = 1;
     W.h = temp2 * W.h;
     W.k = knew;
@@ -423,8 +433,8 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
         k = km1; erk = erkm1;
     } else if (kp1 <= ns) {
         #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) { const double q = phi[kp2][l] / wt[l]; erkp1 = erkp1 + q * q; }
-        erkp1 = absh * kSGgstr[kp1] * sqrt(erkp1);
+        for (int l = 0; l < neqn; ++l) { const double q = sg_div(phi[kp2][l], wt[l]); erkp1 = erkp1 + q * q; }
+        erkp1 = absh * kSGgstr[kp1] * sg_sqrt(erkp1);
         if (k == 1) {
             if (erkp1 < 0.5 * erk) { k = kp1; erk = erkp1; }
         } else if (erkm1 <= fmin(erk, erkp1)) {
@@ -439,7 +449,7 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
             hnew = h;
             if (p5eps < erk) {
                 const double temp2 = (double)(k + 1);
-                const double r = pow_ool(p5eps / erk, 1.0 / temp2);
+                const double r = pow_ool(sg_div(p5eps, erk), sg_div(1.0, temp2));
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(W.x)), h);
             }
@@ -455,14 +465,15 @@ template <int NV> RD_INLINE void sg_intrp(int neqn, const SGWork<NV> &W, double 
     const double hi = xout - W.x;
     const int ki = W.kold + 1;
     #pragma unroll 1
-    for (int i = 1; i <= ki; ++i) w[i] = 1.0 / (double)i;
+    for (int i = 1; i <= ki; ++i) w[i] = sg_div(1.0, (double)i);
     g[1] = 1.0; rho[1] = 1.0;
     double term = 0.0;
     #pragma unroll 1
     for (int j = 2; j <= ki; ++j) {
         const double psijm1 = W.psi[j - 1];
-        const double gamma = (hi + term) / psijm1;
-        const double eta = hi / psijm1;
+        const Rcp pj = rcp_of(psijm1);
+        const double gamma = sg_quot(hi + term, pj);
+        const double eta = sg_quot(hi, pj);
         #pragma unroll 1
         for (int i = 1; i <= ki + 1 - j; ++i) w[i] = gamma * w[i] - eta * w[i + 1];
         g[j] = w[1];
