@@ -208,6 +208,11 @@ __device__ const double kSGgstr[14] = {  // ode_RAYS.f90:776-779 (single-precisi
     0.0, (double)0.50e+00f, (double)0.0833e+00f, (double)0.0417e+00f, (double)0.0264e+00f, (double)0.0188e+00f,
     (double)0.0143e+00f, (double)0.0114e+00f, (double)0.00936e+00f, (double)0.00789e+00f, (double)0.00679e+00f,
     (double)0.00592e+00f, (double)0.00524e+00f, (double)0.00468e+00f};
+// 1/i and 1/(i(i+1)) as the compiler's IEEE division forms them: the same bits as the run-time 1.0/real(i)
+__device__ const double kSGinv[15] = {0.0, 1.0 / 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0, 1.0 / 6.0, 1.0 / 7.0, 1.0 / 8.0, 1.0 / 9.0, 1.0 / 10.0,
+                                      1.0 / 11.0, 1.0 / 12.0, 1.0 / 13.0, 1.0 / 14.0};
+__device__ const double kSGinvTri[14] = {0.0, 1.0 / 2.0, 1.0 / 6.0, 1.0 / 12.0, 1.0 / 20.0, 1.0 / 30.0, 1.0 / 42.0, 1.0 / 56.0, 1.0 / 72.0, 1.0 / 90.0,
+                                         1.0 / 110.0, 1.0 / 132.0, 1.0 / 156.0, 1.0 / 182.0};
 __device__ const double kSGtwo[14] = {0.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0, 128.0, 256.0, 512.0, 1024.0, 2048.0, 4096.0, 8192.0};
 
 // step (ode_RAYS.f90:595-1234) is cut at its three right-hand-side evaluations so that a warp evaluates the
@@ -272,7 +277,7 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
     const int nsp1 = ns + 1;
     if (ns <= k) {
         beta[ns] = 1.0;
-        alpha[ns] = sg_div(1.0, (double)ns);
+        alpha[ns] = kSGinv[ns];
         double temp1 = h * (double)ns;
         sig[nsp1] = 1.0;
         #pragma unroll 1
@@ -287,10 +292,10 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
         psi[k] = temp1;
         if (ns <= 1) {
             #pragma unroll 1
-            for (int iq = 1; iq <= k; ++iq) { v[iq] = sg_div(1.0, (double)(iq * (iq + 1))); w[iq] = v[iq]; }
+            for (int iq = 1; iq <= k; ++iq) { v[iq] = kSGinvTri[iq]; w[iq] = v[iq]; }
         } else {
             if (kold < k) {
-                v[k] = sg_div(1.0, (double)(k * kp1));
+                v[k] = kSGinvTri[k];
                 #pragma unroll 1
                 for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; v[i] = v[i] - alpha[j + 1] * v[i + 1]; }
             }
@@ -311,15 +316,18 @@ template <int NV> RD_INLINE void sg_predict(int neqn, SGWork<NV> &W) {
         #pragma unroll 1
         for (int l = 0; l < neqn; ++l) phi[i][l] = beta[i] * phi[i][l];
     #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) { phi[kp2][l] = phi[kp1][l]; phi[kp1][l] = 0.0; W.p[l] = 0.0; }
-    #pragma unroll 1
-    for (int j = 1; j <= k; ++j) {
-        const int i = kp1 - j;
+    for (int l = 0; l < neqn; ++l) {   // component by component (same operation order per component as the reference's
+        phi[kp2][l] = phi[kp1][l];     // i-outer loops): the running sum and phi(l,i+1) stay in registers
+        phi[kp1][l] = 0.0;
+        double pl = 0.0, up = 0.0;
         #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) {
-            W.p[l] = W.p[l] + phi[i][l] * g[i];
-            phi[i][l] = phi[i][l] + phi[i + 1][l];
+        for (int i = k; i >= 1; --i) {
+            const double f = phi[i][l];
+            pl = pl + f * g[i];
+            up = f + up;
+            phi[i][l] = up;
         }
+        W.p[l] = pl;
     }
     if (!W.nornd) {
         #pragma unroll 1
@@ -422,9 +430,11 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
         phi[kp2][l] = phi[kp1][l] - phi[kp2][l];
     }
     #pragma unroll 1
-    for (int i = 1; i <= k; ++i)
+    for (int l = 0; l < neqn; ++l) {
+        const double d = phi[kp1][l];
         #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) phi[i][l] = phi[i][l] + phi[kp1][l];
+        for (int i = 1; i <= k; ++i) phi[i][l] = phi[i][l] + d;
+    }
     double erkp1 = 0.0;
     if (knew == km1 || k == 12) W.phase1 = false;
     if (W.phase1) {
@@ -448,8 +458,7 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
         if (p5eps < erk * kSGtwo[k + 1]) {
             hnew = h;
             if (p5eps < erk) {
-                const double temp2 = (double)(k + 1);
-                const double r = pow_ool(sg_div(p5eps, erk), sg_div(1.0, temp2));
+                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(W.x)), h);
             }
@@ -465,7 +474,7 @@ template <int NV> RD_INLINE void sg_intrp(int neqn, const SGWork<NV> &W, double 
     const double hi = xout - W.x;
     const int ki = W.kold + 1;
     #pragma unroll 1
-    for (int i = 1; i <= ki; ++i) w[i] = sg_div(1.0, (double)i);
+    for (int i = 1; i <= ki; ++i) w[i] = kSGinv[i];
     g[1] = 1.0; rho[1] = 1.0;
     double term = 0.0;
     #pragma unroll 1
