@@ -306,6 +306,22 @@ int rays_b200_deposition(rays_deposition *dep, double *d_profile_out);
 /* Same, fused into the trace: bins while tracing, no trajectory storage needed. */
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories);
 
+/* ======================= O-X mode conversion analysis (row f4) ============================ */
+/* One record per ray: type OX_conv + the per-ray outcome flags of analyze_OX_conv
+ * (post_process_lib/OX_conv_analysis_m.f90:32-47, 91-198). */
+typedef struct rays_ox_conv {
+    double x_max[3], k_max[3];        /* saved point of maximum alpha_e on the ray, k there (find_x_max_ray :202-252)  */
+    double alpha_max;                 /* omega_pe^2/omega^2 at x_max                                                   */
+    double x_cut[3];                  /* point on the O-mode cutoff surface next to x_max (find_x_cutoff_ray :256-311)  */
+    double conv_coeff;                /* O-X conversion coefficient (OX_conv_coeff :315-407); 0 unless `converted`      */
+    double nvecx_c[3], nvecy_c[3], nvecz_c[3];
+    int32_t ray_number, step_number;  /* 1-based, as the reference counts                                             */
+    int32_t found_max, found_cutoff, converted, iteration;
+} rays_ox_conv;
+/* analyze_OX_conv on the trajectories of the last device trace (one thread per ray); out[nray] on the HOST.
+ * The reference's OX_conv_data is the sub-list with converted != 0 (conv_coeff > 1e-4), in ray order. */
+int rays_b200_ox_conv_analysis(rays_ox_conv *out, int64_t *n_converted);
+
 /* ======================= mirror coil fields (row f4) ====================================== */
 /* One coil of the mirror coil set: coil_type + /coil_data_list/ + /current_data_list/
  * (mirror_magnetics_lib/mirror_magnetics_m.f90:62-75, 101-115).  The conductors are modelled as

@@ -9,6 +9,7 @@
 
 #include "rays_oracle.hpp"
 #include "rays_oracle_coils.hpp"
+#include "rays_oracle_ox.hpp"
 
 using namespace rays_oracle;
 
@@ -208,6 +209,14 @@ int oracle_Brz_loop_scaled(long n, const double *r, const double *z, double *Br,
 }
 int oracle_elliptic(long n, const double *m, double *K, double *E) {
     for (long i = 0; i < n; ++i) { K[i] = elliptic_Km(m[i]); E[i] = elliptic_Em(m[i]); }
+    return 0;
+}
+// analyze_OX_conv (P/OX_conv_analysis_m.f90:91-198) on host result arrays
+int oracle_ox_conv(const rays_cfg *cfg, const rays_results *res, rays_ox_conv *out) {
+    const int nv = cfg->nv, npa = res->npoints_alloc;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long iray = 0; iray < res->nray; ++iray)
+        ox_conv_ray(*cfg, res->ray_vec + (size_t)iray * npa * nv, nv, res->npoints[iray], (int)iray + 1, out[iray]);
     return 0;
 }
 int oracle_binner(const double *Q, const double *xQ, int nx, double xmin, double xmax, double *binned, int n_bins) {

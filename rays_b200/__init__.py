@@ -301,6 +301,17 @@ def probe_check_save(v: np.ndarray):
     return out, st
 
 
+def ox_conv_analysis(nray: int):
+    """analyze_OX_conv (OX_conv_analysis_m.f90:91-198) on the trajectories of the last stored device trace:
+    (records[nray] as a numpy structured array, number of converted rays)"""
+    from ._abi import OX_DTYPE
+    out = np.zeros(nray, dtype=np.dtype(OX_DTYPE, align=True))
+    assert out.dtype.itemsize == C.sizeof(_abi.OxConv)
+    n = C.c_int64(0)
+    _ck(_lib().rays_b200_ox_conv_analysis(out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out, int(n.value)
+
+
 def make_coils(coils) -> "C.Array":
     """list of dicts (inner_radius, outer_radius, z_center, z_width, I_coil, n_turns, n_r_layers, n_z_slices) -> rays_coil[]"""
     from ._abi import Coil

@@ -76,6 +76,18 @@ class Coil(C.Structure):
         ("n_turns", C.c_int64), ("n_r_layers", C.c_int32), ("n_z_slices", C.c_int32)]
 
 
+class OxConv(C.Structure):
+    """rays_ox_conv (include/rays_b200.h): per-ray outcome of analyze_OX_conv"""
+    _fields_ = [("x_max", C.c_double * 3), ("k_max", C.c_double * 3), ("alpha_max", C.c_double), ("x_cut", C.c_double * 3), ("conv_coeff", C.c_double),
+                ("nvecx_c", C.c_double * 3), ("nvecy_c", C.c_double * 3), ("nvecz_c", C.c_double * 3)] + [
+        (n, C.c_int32) for n in ("ray_number", "step_number", "found_max", "found_cutoff", "converted", "iteration")]
+
+
+OX_DTYPE = [("x_max", "f8", 3), ("k_max", "f8", 3), ("alpha_max", "f8"), ("x_cut", "f8", 3), ("conv_coeff", "f8"), ("nvecx_c", "f8", 3),
+            ("nvecy_c", "f8", 3), ("nvecz_c", "f8", 3), ("ray_number", "i4"), ("step_number", "i4"), ("found_max", "i4"), ("found_cutoff", "i4"),
+            ("converted", "i4"), ("iteration", "i4")]
+
+
 class Cfg(C.Structure):
     _fields_ = [
         ("clight", C.c_double), ("eps0", C.c_double),
@@ -141,7 +153,7 @@ ABI_SYMBOLS = [
     "rays_b200_fan_download", "rays_b200_deposition", "rays_b200_trace_device_binned",
     "rays_b200_probe_equilibrium", "rays_b200_probe_rhs", "rays_b200_probe_check_save",
     "rays_b200_fp64_peak", "rays_b200_host_alloc", "rays_b200_host_free", "rays_b200_stream", "rays_b200_version",
-    "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown", "rays_b200_mirror_brz_grid",
+    "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown", "rays_b200_mirror_brz_grid", "rays_b200_ox_conv_analysis",
 ]
 HOST_SYMBOLS = [
     "rays_host_initialize", "rays_host_trace_rays", "rays_host_finalize_run", "rays_host_deallocate", "rays_host_last_error",
@@ -204,6 +216,7 @@ def load() -> C.CDLL:
         "rays_b200_mirror_brz_grid": (i, [P(Coil), C.c_int32, C.c_int32, dbl, dbl, C.c_int32, dbl, dbl, c_double_p, c_double_p, c_double_p,
                                        c_double_p, c_double_p]),
         "rays_host_mirror_magnetics": (i, [cp, cp, C.c_char_p, i]),
+        "rays_b200_ox_conv_analysis": (i, [vp, P(i64)]),
         "rays_host_cspline": (i, [c_double_p, i, c_double_p]), "rays_host_bcspline": (i, [c_double_p, i, c_double_p, i, c_double_p]),
     }
     for name, (res, args) in protos.items():

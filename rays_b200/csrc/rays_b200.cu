@@ -269,6 +269,122 @@ template <int EQ_> __global__ void deposition_kernel(long long nray, int nv, int
         xa = xb; Qa = Qb;
     }
 }
+// ---- O-X conversion analysis of stored trajectories (post_process_lib/OX_conv_analysis_m.f90:91-407): one thread per ray
+struct OxEq { double alpha0, gamma0, ns0, gradns0[3], bunit[3]; };
+// equilibrium() as that module uses it: alpha_e, gamma_e, n_e, grad n_e, b.  The Fortran forms the derived quantities whatever
+// equib_err says (equilibrium_m.f90:229-268): a point outside the plasma boundary is evaluated, a point outside the box is not
+template <int EQ_> __device__ __forceinline__ void ox_equilibrium(const double *r, OxEq &q) {
+    Eq<RAYS_NSPECIES> e;
+    equilibrium<EQ_, 0, true>(r[0], r[1], r[2], e);
+    const bool hard = e.err != 0 && e.err != RAYS_STOP_OUT_OF_PLASMA && e.err != RAYS_STOP_NEGATIVE_DENS && e.err != RAYS_STOP_NEGATIVE_TEMP;
+    q.alpha0 = 0.0; q.gamma0 = 0.0; q.ns0 = 0.0;
+    for (int i = 0; i < 3; ++i) { q.gradns0[i] = 0.0; q.bunit[i] = 0.0; }
+    if (hard) return;
+    const DevCfg &d = g_dc;
+    const double bmag = sqrt(e.bvec[0] * e.bvec[0] + e.bvec[1] * e.bvec[1] + e.bvec[2] * e.bvec[2]);
+    for (int i = 0; i < 3; ++i) { q.bunit[i] = e.bvec[i] / bmag; q.gradns0[i] = e.gradns[i][0]; }
+    q.ns0 = e.ns[0];
+    const double omgc = d.c.qs[0] * bmag / d.c.ms[0];
+    const double omgp2 = e.ns[0] * (d.c.qs[0] * d.c.qs[0]) / (d.c.eps0 * d.c.ms[0]);
+    q.alpha0 = omgp2 / (d.c.omgrf * d.c.omgrf);
+    q.gamma0 = omgc / d.c.omgrf;
+}
+__device__ __forceinline__ double ox_norm2(const double a[3]) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+__device__ __forceinline__ double ox_dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+template <int EQ_> __global__ void ox_conv_kernel(long long nray, int nv, int npa, const double *ray_vec, const int *npoints, rays_ox_conv *out) {
+    const long long iray = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (iray >= nray) return;
+    const double one = 1.0, two = 2.0;
+    const double pi = (double)3.1415926535897932385f, conversion_threshold = (double)0.0001f;
+    const double *v = ray_vec + (size_t)iray * npa * nv;
+    const int np = npoints[iray];
+    rays_ox_conv o;
+    memset(&o, 0, sizeof(o));
+    o.ray_number = (int)iray + 1;
+    // find_x_max_ray (:202-252)
+    bool found_max = false;
+    int step_number = 1;
+    double alpha_max = 0.0, x_max[3] = {0, 0, 0}, k_max[3] = {0, 0, 0};
+    OxEq q;
+    ox_equilibrium<EQ_>(v, q);
+    double alpha_low = q.alpha0;
+    for (int i = 2; i <= np; ++i) {
+        ox_equilibrium<EQ_>(v + (size_t)(i - 1) * nv, q);
+        const double alpha_high = q.alpha0;
+        if (alpha_high < alpha_low) {
+            found_max = true;
+            alpha_max = alpha_low;
+            step_number = i - 1;
+            const double *pm = v + (size_t)(i - 2) * nv;
+            for (int k = 0; k < 3; ++k) { x_max[k] = pm[k]; k_max[k] = pm[3 + k]; }
+            break;
+        }
+        alpha_low = alpha_high;
+    }
+    o.found_max = found_max ? 1 : 0;
+    if (found_max) {
+        for (int k = 0; k < 3; ++k) { o.x_max[k] = x_max[k]; o.k_max[k] = k_max[k]; }
+        o.alpha_max = alpha_max;
+        o.step_number = step_number;
+        // find_x_cutoff_ray (:256-311)
+        const double alpha_tolerence = one / (10.0 * 10.0 * 10.0 * 10.0);
+        bool found_cutoff = false;
+        double x_temp[3] = {x_max[0], x_max[1], x_max[2]};
+        ox_equilibrium<EQ_>(x_temp, q);
+        double alpha_temp = q.alpha0;
+        int iteration;
+        for (iteration = 1; iteration <= 10; ++iteration) {
+            if (fabs(alpha_temp - one) <= alpha_tolerence) { found_cutoff = true; break; }
+            ox_equilibrium<EQ_>(x_temp, q);
+            alpha_temp = q.alpha0;
+            const double ng = ox_norm2(q.gradns0);
+            const double mod_grad_alpha = ng * (alpha_temp / q.ns0);
+            const double r = sqrt(x_temp[0] * x_temp[0] + x_temp[1] * x_temp[1]);
+            const double delta = (one - q.alpha0) / mod_grad_alpha;
+            const double step = fmin(delta, 0.25 * r);
+            for (int k = 0; k < 3; ++k) x_temp[k] = x_temp[k] + q.gradns0[k] / ng * step;
+        }
+        o.iteration = iteration;
+        o.found_cutoff = found_cutoff ? 1 : 0;
+        if (found_cutoff) {
+            for (int k = 0; k < 3; ++k) o.x_cut[k] = x_temp[k];
+            // OX_conv_coeff (:315-407)
+            ox_equilibrium<EQ_>(x_temp, q);
+            const double ng = ox_norm2(q.gradns0);
+            double xc[3], yc[3], zc[3], vt[3];
+            for (int k = 0; k < 3; ++k) xc[k] = q.gradns0[k] / ng;
+            vt[0] = q.bunit[1] * xc[2] - q.bunit[2] * xc[1];
+            vt[1] = q.bunit[2] * xc[0] - q.bunit[0] * xc[2];
+            vt[2] = q.bunit[0] * xc[1] - q.bunit[1] * xc[0];
+            const double nvt = ox_norm2(vt);
+            for (int k = 0; k < 3; ++k) yc[k] = vt[k] / nvt;
+            zc[0] = xc[1] * yc[2] - xc[2] * yc[1];
+            zc[1] = xc[2] * yc[0] - xc[0] * yc[2];
+            zc[2] = xc[0] * yc[1] - xc[1] * yc[0];
+            const double theta = acos(ox_dot(xc, q.bunit));
+            const double gamma = fabs(q.gamma0);
+            const double L = q.ns0 / ng;
+            const double k0 = g_dc.c.k0;
+            const double n_vertical = ox_dot(k_max, xc) / k0;
+            const double nz_c = ox_dot(k_max, zc) / k0;
+            const double ny_c = ox_dot(k_max, yc) / k0;
+            const double n_crit = sin(theta) * sqrt(gamma / (one + gamma));
+            const double ct = cos(theta), st = sin(theta);
+            const double F = 0.5 * (one + gamma) * sqrt(gamma) / pow((one + gamma) * (ct * ct) + (st * st) / two, 1.5);
+            const double G = 0.5 * sqrt(gamma) / sqrt((one + gamma) * (ct * ct) + (st * st) / two);
+            const double dz = fabs(nz_c) - n_crit, ay = fabs(ny_c);
+            const double conv_coeff = exp(-pi * k0 * L * (F * (dz * dz) + G * (ay * ay)));
+            if (conv_coeff > conversion_threshold) {
+                o.converted = 1;
+                o.conv_coeff = conv_coeff;
+                for (int k = 0; k < 3; ++k) { o.nvecx_c[k] = n_vertical * xc[k]; o.nvecy_c[k] = ny_c * yc[k]; o.nvecz_c[k] = nz_c * zc[k]; }
+            }
+        }
+    }
+    out[iray] = o;
+}
+
 // DFMA-only microbenchmark (fp64 roofline denominator): 8 independent chains per thread
 __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1110,6 +1226,34 @@ int rays_b200_probe_rhs(int64_t n, const double *v, double *dvds, int32_t *stop)
 int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_t *stop) {
     if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
     return run_probe(2, n, v, (size_t)g.dc.c.nv, resid, 1, stop);
+}
+
+// ======================= O-X conversion analysis (row f4) ======================================================
+int rays_b200_ox_conv_analysis(rays_ox_conv *out, int64_t *n_converted) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (!out) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_ox_conv_analysis: null output");
+    if (!g.have_traj || g.res_nray <= 0) return set_err(RAYS_ERR_INVALID_CONFIG, "analyze_OX_conv needs the trajectories of a stored device trace (trace_device with store)");
+    CK(cudaSetDevice(g.device));
+    const long long n = g.res_nray;
+    rays_ox_conv *d_out = nullptr;
+    CK(cudaMalloc(&d_out, sizeof(rays_ox_conv) * (size_t)n));
+    const unsigned grid = (unsigned)((n + 63) / 64);
+    switch (g.dc.c.equilib_model) {
+        case RAYS_EQ_SLAB: ox_conv_kernel<RAYS_EQ_SLAB><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
+        case RAYS_EQ_SOLOVEV: ox_conv_kernel<RAYS_EQ_SOLOVEV><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
+        case RAYS_EQ_AXISYM_TOROID: ox_conv_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
+        default: ox_conv_kernel<RAYS_EQ_MULTIPLE_MIRROR><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(rays_ox_conv) * (size_t)n, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    cudaFree(d_out);
+    CK(e);
+    int64_t nc = 0;
+    for (long long i = 0; i < n; ++i) nc += out[i].converted ? 1 : 0;
+    if (n_converted) *n_converted = nc;
+    return 0;
 }
 
 // ======================= mirror coil fields (row f4) ===========================================================

@@ -139,6 +139,14 @@ def deposition(cfg, res: ResultArrays, n_bins, grid_min, grid_max):
     return prof, float(d.Q_sum)
 
 
+def ox_conv(cfg, res: ResultArrays):
+    L = load()
+    out = np.zeros(res.nray, dtype=np.dtype(_abi.OX_DTYPE, align=True))
+    L.oracle_ox_conv.argtypes = [C.POINTER(_abi.Cfg), C.POINTER(_abi.Results), C.c_void_p]
+    L.oracle_ox_conv(C.byref(cfg), C.byref(res.c), out.ctypes.data_as(C.c_void_p))
+    return out, int(out["converted"].sum())
+
+
 def mirror_Brz_grid(coils, n_r, r_min, r_max, n_z, z_min, z_max):
     import rays_b200 as rb
     L = load()
