@@ -992,11 +992,18 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
 // Sequence per iteration, in the reference's order (ray_tracing.f90:116-245):
 //   check_save(v) -> [stop: point not saved] -> save point, nstep++ -> s = sout, sout += ds -> s_max / nstep_max
 //   tests -> RK4 stages -> v advanced (or ray stopped by the RHS with v untouched).
-#ifndef RAYS_RK4_MIN_CTAS
-#define RAYS_RK4_MIN_CTAS 4   // measured on the 1M-ray bench fan: 2 -> 284 ms, 3 -> 238, 4 -> 234, 5 -> 246, 6 -> 269
+// Resident CTAs per SM (sets the register budget: 4 -> 128, 3 -> 168 registers per thread), 1M-ray bench fan, deriv_num:
+//   looped determinants:   2 -> 284 ms, 3 -> 238, 4 -> 234, 5 -> 246, 6 -> 269
+//   unrolled determinants (RAYS_DN_UK = 6): 4 -> 154.6 ms, 3 -> 147.3 ms: with more independent FP64 work per warp the
+//   kernel prefers fewer warps that do not spill (stack 232 -> 48 bytes); 2 -> 176.5 ms
+// deriv_cold on the same fan: 4 -> 42.7 ms, 3 -> 39.3, 2 -> 37.7 (3.9e9 ray-steps/s; 352 bytes of spills at 128 registers, none at 255)
+#ifdef RAYS_RK4_MIN_CTAS
+template <class T> struct Rk4Ctas { static constexpr int value = RAYS_RK4_MIN_CTAS; };
+#else
+template <class T> struct Rk4Ctas { static constexpr int value = T::GENERIC ? 3 : (T::DERIV == RAYS_DERIV_NUM ? 3 : 2); };
 #endif
 template <class T>
-__global__ void __launch_bounds__(kTraceBlock, RAYS_RK4_MIN_CTAS) trace_rk4_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int nv = T::nv();
