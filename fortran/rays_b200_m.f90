@@ -88,7 +88,34 @@ module rays_b200_m
         integer(c_int64_t) :: total_ray_steps
     end type
 
+!   coil_type + /coil_data_list/ + /current_data_list/ (mirror_magnetics_lib/mirror_magnetics_m.f90:62-115)
+    type, bind(C) :: rays_coil
+        real(c_double) :: inner_radius, outer_radius, z_center, z_width, I_coil
+        integer(c_int64_t) :: n_turns
+        integer(c_int32_t) :: n_r_layers, n_z_slices
+    end type
+!   type OX_conv + per-ray flags (post_process_lib/OX_conv_analysis_m.f90:32-47)
+    type, bind(C) :: rays_ox_conv
+        real(c_double) :: x_max(3), k_max(3), alpha_max, x_cut(3), conv_coeff, nvecx_c(3), nvecy_c(3), nvecz_c(3)
+        integer(c_int32_t) :: ray_number, step_number, found_max, found_cutoff, converted, iteration
+    end type
+
     interface
+!       calculate_B_on_rz_grid (mirror_magnetics_m.f90:324-368); Br, Bz, Aphi(n_r, n_z) as the module holds them
+        integer(c_int) function rays_b200_mirror_brz_grid(coils, n_coils, n_r, r_min, r_max, n_z, z_min, z_max, &
+                & r_grid, z_grid, Br, Bz, Aphi) bind(C, name='rays_b200_mirror_brz_grid')
+            import :: c_int, c_int32_t, c_double, rays_coil
+            type(rays_coil), intent(in) :: coils(*)
+            integer(c_int32_t), value :: n_coils, n_r, n_z
+            real(c_double), value :: r_min, r_max, z_min, z_max
+            real(c_double), intent(out) :: r_grid(*), z_grid(*), Br(*), Bz(*), Aphi(*)
+        end function
+!       analyze_OX_conv (OX_conv_analysis_m.f90:91-198) on the trajectories the last trace left on the device
+        integer(c_int) function rays_b200_ox_conv_analysis(out, n_converted) bind(C, name='rays_b200_ox_conv_analysis')
+            import :: c_int, c_int64_t, rays_ox_conv
+            type(rays_ox_conv), intent(out) :: out(*)
+            integer(c_int64_t), intent(out) :: n_converted
+        end function
         integer(c_int) function rays_b200_init(device) bind(C, name='rays_b200_init')
             import :: c_int
             integer(c_int), value :: device
