@@ -135,6 +135,8 @@ int validate_cfg(const rays_cfg &c) {
     if (c.integrate_eq_gradients) nv += 5;
     if (c.nv != nv) return set_err(RAYS_ERR_INVALID_CONFIG, "ode_m: nv does not match damping/gradient options (ode_m.f90:160-173)");
     if (c.nstep_max < 0) return set_err(RAYS_ERR_INVALID_CONFIG, "ode_m: nstep_max < 0");
+    if (c.ode_solver == RAYS_ODE_SG && (c.rel_err0 < (double)1.e-10f || c.abs_err0 < (double)1.e-10f))   // SG_ode_m.f90:63-66
+        return set_err(RAYS_ERR_INVALID_CONFIG, "initialize_SG_ode: rel_err0, abs_err0 too small");
     if (c.damping_model == RAYS_DAMP_FUND_ECH && (!c.zfun_re.x_grid || !c.zfun_re.fspl || c.zfun_re.nx < 2))
         return set_err(RAYS_ERR_INVALID_CONFIG, "damping: Z-function spline table missing");
     if (c.equilib_model == RAYS_EQ_MULTIPLE_MIRROR) {
