@@ -12,7 +12,7 @@ namespace rays_dev {
 namespace {
 
 constexpr int kEQ = RAYS_TU_EQ;
-constexpr int kODE = RAYS_TU_ODE;
+[[maybe_unused]] constexpr int kODE = RAYS_TU_ODE;
 
 cudaError_t tu_upload(const DevCfg *dc, cudaStream_t st) {
     return cudaMemcpyToSymbolAsync(g_dc, dc, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, st);
