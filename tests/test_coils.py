@@ -90,6 +90,18 @@ def test_coil_struct_layout():
     assert _abi.C.sizeof(_abi.Coil) == 56 and _abi.Coil.n_turns.offset == 40 and _abi.Coil.n_z_slices.offset == 52
 
 
+def test_generator_refuses_to_run_without_a_gpu(tmp_path):
+    """program mirror_magnetics goes through the CUDA kernel only: no CPU fallback"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb.RaysError):
+        rb.mirror_magnetics(rb.config_path("coils/mirror_magnetics.nml"), str(tmp_path))
+    assert not list(tmp_path.iterdir())
+    with pytest.raises(rb.RaysError):
+        rb.mirror_Brz_grid(COILS, 5, 0.0, 0.2, 5, 2.8, 3.6)
+
+
 # ---- CUDA path ----------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 def test_gpu_grid_equals_oracle():
