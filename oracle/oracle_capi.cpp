@@ -219,6 +219,25 @@ int oracle_ox_conv(const rays_cfg *cfg, const rays_results *res, rays_ox_conv *o
         ox_conv_ray(*cfg, res->ray_vec + (size_t)iray * npa * nv, nv, res->npoints[iray], (int)iray + 1, out[iray]);
     return 0;
 }
+// one row of write_kx_profiles (P/slab_processor_m.f90:783-819): k0*nx of the cold root `mode` (1 plus, 2 minus, 3 fast,
+// 4 slow; k0_sign = +1) at rvec = (x, 0, 0) through solve_nx_vs_ny_nz_by_bz (L/dispersion_solvers_m.f90:116-153), cast to
+// single precision the way the Fortran writes it
+int oracle_kx_profile(const rays_cfg *cfg, long n, const double *x, double ny, double nz, int mode, double *kx_re, double *kx_im) {
+    rays_cfg c = *cfg;
+    c.wave_mode = mode;
+    c.k0_sign = 1;
+    for (long i = 0; i < n; ++i) {
+        const double rvec[3] = {x[i], 0.0, 0.0};
+        EqPoint<double> eq;
+        equilibrium<double>(c, rvec, c.omgrf, eq);
+        const double n2 = ny * eq.bunit[2] - nz * eq.bunit[1];
+        const double n3 = ny * eq.bunit[1] + nz * eq.bunit[2];
+        const Cx<double> nx = solve_n1_vs_n2_n3<double>(c, eq, n2, n3);
+        kx_re[i] = (double)((float)c.k0 * (float)nx.re);
+        kx_im[i] = (double)((float)c.k0 * (float)nx.im);
+    }
+    return 0;
+}
 int oracle_binner(const double *Q, const double *xQ, int nx, double xmin, double xmax, double *binned, int n_bins) {
     return binner_real(Q, xQ, nx, xmin, xmax, binned, n_bins);
 }

@@ -139,6 +139,16 @@ def deposition(cfg, res: ResultArrays, n_bins, grid_min, grid_max):
     return prof, float(d.Q_sum)
 
 
+def kx_profile(cfg, x, ny, nz, mode):
+    """k0*nx of the cold root `mode` (1 plus, 2 minus, 3 fast, 4 slow) at (x, 0, 0), single precision as written"""
+    L = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    re, im = np.zeros_like(x), np.zeros_like(x)
+    L.oracle_kx_profile.argtypes = [C.POINTER(_abi.Cfg), C.c_long, _abi.c_double_p, C.c_double, C.c_double, C.c_int, _abi.c_double_p, _abi.c_double_p]
+    L.oracle_kx_profile(C.byref(cfg), len(x), _dp(x), float(ny), float(nz), int(mode), _dp(re), _dp(im))
+    return re, im
+
+
 def ox_conv(cfg, res: ResultArrays):
     L = load()
     out = np.zeros(res.nray, dtype=np.dtype(_abi.OX_DTYPE, align=True))

@@ -140,3 +140,43 @@ def test_cuda_path_reproduces_the_reference_mpex_raster():
     _check_against_raster(g)
     o, st, _ = orc.trace(cfg, r, n, w)
     assert np.array_equal(g.npoints, o.npoints) and g.ray_stop_flag == o.ray_stop_flag
+
+
+# ---- cold dispersion roots of the launchers: the slab example's kx-profile figures --------------------------
+KX = json.load(open(os.path.join(HERE, "golden", "ref_kx_profiles.json")))
+
+
+@pytest.mark.parametrize("page", range(len(KX["pages"])))
+def test_oracle_reproduces_the_reference_kx_profiles(page):
+    """examples_RAYS/ECH_90GHz_slab/pdf_plots/kx_plots.run_{1,2}.pdf: k0*nx (re, im) of two cold roots at 101 x positions
+    across the slab (write_kx_profiles, slab_processor_m.f90:729-827).  The tick labels are outlined, so the page's y
+    calibration (scale, offset) is fitted: 2 numbers against 404 plotted values, which then agree to the PDF's 1e-4 pt.
+    Where the two roots are a complex pair the fast/slow pages label them the other way round than the current source
+    (an older build drew them): those pages are compared as unordered pairs (re) and by magnitude (im)."""
+    G = KX["pages"][page]
+    cfg = init_case(G["namelist"])
+    r, n, w, _, _ = oracle_fan(cfg)
+    ny, nz = n[G["ray"] - 1, 1], n[G["ray"] - 1, 2]
+    x = np.array([cfg.slab.xmin + i * ((cfg.slab.xmax - cfg.slab.xmin) / 100) for i in range(101)])
+    xp = np.array(G["x_pt"])
+    assert np.max(np.abs(xp - np.linspace(xp[0], xp[-1], 101))) < 2e-4          # the plotted abscissae are that uniform grid
+    modes = (1, 2) if G["roots"] == "plus_minus" else (3, 4)
+    a_re, a_im = orc.kx_profile(cfg, x, ny, nz, modes[0])
+    b_re, b_im = orc.kx_profile(cfg, x, ny, nz, modes[1])
+    Y = [np.array(c) for c in G["curves_pt"]]
+    assert np.ptp(a_re) > 100.0 and max(np.ptp(a_im), np.ptp(b_im)) > 100.0        # propagating and evanescent stretches both present
+    # calibration from the sum of the two real parts (independent of which curve is which root)
+    A = np.stack([a_re + b_re, 2.0 * np.ones(101)], axis=1)
+    scale, off = np.linalg.lstsq(A, Y[0] + Y[2], rcond=None)[0]
+    assert 0.01 < scale < 0.03
+    y = [(c - off) / scale for c in Y]
+    tol = 3e-4 / scale + 2e-7 * np.maximum(np.abs(a_re), np.abs(b_re))             # PDF quantisation + single-precision output
+    tol_i = 3e-4 / scale + 2e-7 * np.abs(a_im)
+    if G["roots"] == "plus_minus":      # strict: red = plus (re, im), blue = minus (re, im), signs included
+        for got, want, t in ((y[0], a_re, tol), (y[1], a_im, tol_i), (y[2], b_re, tol), (y[3], b_im, tol_i)):
+            assert np.all(np.abs(got - want) <= t), float(np.max(np.abs(got - want)))
+    else:
+        same = (np.abs(y[0] - a_re) <= tol) & (np.abs(y[2] - b_re) <= tol)
+        swapped = (np.abs(y[0] - b_re) <= tol) & (np.abs(y[2] - a_re) <= tol)
+        assert np.all(same | swapped)
+        assert np.all(np.abs(np.abs(y[1]) - np.abs(a_im)) <= tol_i) and np.all(np.abs(np.abs(y[3]) - np.abs(b_im)) <= tol_i)
