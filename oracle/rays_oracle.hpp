@@ -11,12 +11,12 @@
 //
 // PARITY STATUS: the reference cannot be compiled here (no Fortran compiler, no netCDF) and ships no
 // numeric ray files -- but its example directories ship vector PDFs of the rays the Fortran traced.
-// PINNED on (a) those figures: 23 rays of 5 shipped inputs (slab + Solov'ev, all SG_ODE), 1 798 plotted
+// PINNED on (a) those figures: 29 rays of 7 inputs (slab + Solov'ev, all SG_ODE; 2 slab inputs reconstructed), 2 164 plotted
 // trajectory points reproduced to the PDFs' resolution of 1e-6 pt (1.3e-9 ... 8.7e-9 m; 3e-14 m in z on
 // the equatorial-plane runs), ray lengths included (tests/golden/ref_plot_vectors.json,
 // tests/test_reference_plots.py); (b) the plasma Z function table M/"Splined Z function results.txt":48-85
 // (tests/golden/zfun_kat.json); (c) the cold dispersion roots of the launchers on the slab example's kx-profile figures
-// (7 pages x 404 values, 1e-4 pt: tests/golden/ref_kx_profiles.json); (d) coarsely, RK4_ODE + the mirror equilibrium on the MPEX example's raster figure
+// (13 pages x 404 values, 1e-4 ... 1e-6 pt: tests/golden/ref_kx_profiles.json); (d) coarsely, RK4_ODE + the mirror equilibrium on the MPEX example's raster figure
 // (11 rays, 0.87 mm pixels: tests/golden/ref_raster_vectors.json).  NOT pinned by reference output: deriv_num,
 // damping (k and power are pinned only through the positions they drive), the axisym/eqdsk equilibria.
 //

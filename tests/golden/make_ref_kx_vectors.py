@@ -22,7 +22,17 @@ PAGES = [("kx_plots.run_1.pdf", 0, "examples/slab_ECH_90GHz_case_1.in", 1, "plus
          ("kx_plots.run_2.pdf", 0, "examples/slab_ECH_90GHz_case_2.in", 1, "plus_minus"),
          ("kx_plots.run_2.pdf", 1, "examples/slab_ECH_90GHz_case_2.in", 1, "fast_slow"),
          ("kx_plots.run_2.pdf", 2, "examples/slab_ECH_90GHz_case_2.in", 2, "plus_minus"),
-         ("kx_plots.run_2.pdf", 3, "examples/slab_ECH_90GHz_case_2.in", 2, "fast_slow")]
+         ("kx_plots.run_2.pdf", 3, "examples/slab_ECH_90GHz_case_2.in", 2, "fast_slow"),
+         # run 3: the input is not shipped; reconstructed from these very pages (make_ref_plot_vectors.py), the ray figure is the independent check
+         ("kx_plots.run_3.pdf", 0, "examples/slab_ECH_90GHz_case_3.in", 1, "plus_minus"),
+         ("kx_plots.run_3.pdf", 1, "examples/slab_ECH_90GHz_case_3.in", 1, "fast_slow"),
+         ("kx_plots.run_3.pdf", 2, "examples/slab_ECH_90GHz_case_3.in", 2, "plus_minus"),
+         ("kx_plots.run_3.pdf", 3, "examples/slab_ECH_90GHz_case_3.in", 2, "fast_slow"),
+         ("kx_plots.run_3.pdf", 4, "examples/slab_ECH_90GHz_case_3.in", 3, "plus_minus"),
+         ("kx_plots.run_3.pdf", 5, "examples/slab_ECH_90GHz_case_3.in", 3, "fast_slow")]
+# pages whose fast/slow curves carry the labels of the current source (ordered comparison with signs); on the two nz = 0.6
+# pages of runs 1 and 2 the complex pair is labelled the other way round (an older build drew them)
+UNORDERED = {("kx_plots.run_1.pdf", 2), ("kx_plots.run_2.pdf", 3)}
 
 
 def page_curves(pdf):
@@ -66,7 +76,7 @@ def main():
             cache[pdf] = page_curves(os.path.join(REF, pdf))
         pg = cache[pdf][ip]
         assert len(pg) == 4 and [c for c, _ in pg] == [(1.0, 0.0, 0.0)] * 2 + [(0.0, 0.0, 1.0)] * 2
-        out["pages"].append({"pdf": "examples_RAYS/ECH_90GHz_slab/pdf_plots/" + pdf, "page": ip, "namelist": nml, "ray": ray, "roots": pair,
+        out["pages"].append({"pdf": "examples_RAYS/ECH_90GHz_slab/pdf_plots/" + pdf, "page": ip, "namelist": nml, "ray": ray, "roots": pair, "ordered": (pdf, ip) not in UNORDERED,
                              "x_pt": [p[0] for p in pg[0][1]], "curves_pt": [[p[1] for p in c] for _, c in pg]})
     json.dump(out, open(os.path.join(HERE, "ref_kx_profiles.json"), "w"))
     print(len(out["pages"]), "pages")

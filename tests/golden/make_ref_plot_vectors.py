@@ -26,6 +26,8 @@ NUM = r"-?\d+(?:\.\d+)?"
 FIGURES = [   # (pdf, example input, what the two plotted coordinates are per page)
     ("ECH_90GHz_slab/pdf_plots/ray_plots.run_1.pdf", "ECH_90GHz_slab/slab_ECH_90GHz_case_1.in", [("z", "x")]),
     ("ECH_90GHz_slab/pdf_plots/ray_plots.run_2.pdf", "ECH_90GHz_slab/slab_ECH_90GHz_case_2.in", [("z", "x")]),
+    # cases 3 and 4 share one figure (rays 1-3: case 3, rays 4-6: case 4); their inputs are not shipped: RECONSTRUCTED below
+    ("ECH_90GHz_slab/pdf_plots/ray_plots.runs_3_and_4.pdf", ("slab_ECH_90GHz_case_3.in", "slab_ECH_90GHz_case_4.in"), [("z", "x")]),
     ("ECH_90GHz_solovev_SG_eq_plane/ray_plots.plus_root.pdf", "ECH_90GHz_solovev_SG_eq_plane/solovev_ECH_90GHz_plus_root.in", [("r", "z"), ("x", "y")]),
     ("ECH_90GHz_solovev_SG_eq_plane/ray_plots.minus_root.pdf", "ECH_90GHz_solovev_SG_eq_plane/solovev_ECH_90GHz_minus_root.in", [("r", "z"), ("x", "y")]),
     ("ECH_90GHz_solovev_SG_eq_plane/ray_plots.minus_root_2.pdf", "ECH_90GHz_solovev_SG_eq_plane/solovev_ECH_90GHz_minus_root_case_2.in", [("r", "z"), ("x", "y")]),
@@ -103,12 +105,39 @@ def translate_namelist(src):
     return t
 
 
+# Cases 3 and 4 of the slab example (README: constant density, linearly increasing Bz with the cyclotron resonance at x = 0,
+# nz = 0.1, 0.4, 0.7; case 3 = X mode launched below the right-hand cutoff, case 4 = X mode launched above the cyclotron
+# resonance) ship figures but no input files.  The inputs were reconstructed from the figures themselves: the kx-profile
+# pages of kx_plots.run_3.pdf fix the equilibrium -- n0 = 4.0e19, bz0 = 3.2151 (the resonant field to five digits) and
+# LBz_scale = 0.53585 are the only values for which all 404 plotted root values of a page, including the 45 185 rad/m spike
+# next to the upper-hybrid resonance, agree to 1e-6 pt (a 1e-5 change of LBz_scale moves that spike by 1 %) -- and the ray
+# figure fixes the launch (x = -0.45 / +0.45, z = -0.6), the root (minus / plus), k0_sign (+1 / -1) and the stepper settings
+# (SG_ODE, ds = 5e-11, nstep_max = 500, tolerances 1e-4 as in case 1: with 1e-8 the rays miss by 10^3 resolutions).
+def reconstructed_case(case1_text, which):
+    t = case1_text
+    edits = [("run_label='run_1'", "run_label='run_%d'" % which), ("n0=1.0e20", "n0=4.0e19"),
+             ("bz_prof_model='constant'", "bz_prof_model='linear'"), ("bz0=1.286", "bz0=3.2151"), ("LBz_scale = 1.125", "LBz_scale = 0.53585"),
+             ("dens_prof_model='linear'", "dens_prof_model='constant'"), ("rindex_z0=0.4", "rindex_z0=0.1"), ("delta_rindex_z0=0.1", "delta_rindex_z0=0.3")]
+    edits += [("x_launch0= -0.08", "x_launch0= -0.45")] if which == 3 else \
+             [("x_launch0= -0.08", "x_launch0= 0.45"), ("wave_mode='minus'", "wave_mode='plus'"), ("k0_sign = 1", "k0_sign = -1")]
+    for old, new in edits:
+        assert old in t, old
+        t = t.replace(old, new)
+    return "! RECONSTRUCTED from the reference's figures (tests/golden/make_ref_plot_vectors.py): the example ships no input for this case\n" + t
+
+
 def main():
     out = {"_doc": "made by tests/golden/make_ref_plot_vectors.py from the reference's example PDFs; coordinates in metres",
            "figures": []}
     for pdf, nml, axes in FIGURES:
-        name = os.path.basename(nml)
-        open(os.path.join(ROOT, "rays_b200", "configs", "examples", name), "w").write(translate_namelist(os.path.join(REF, nml)))
+        if isinstance(nml, tuple):       # the shared figure of the reconstructed cases 3 and 4
+            case1 = translate_namelist(os.path.join(REF, "ECH_90GHz_slab/slab_ECH_90GHz_case_1.in"))
+            for k, nm in enumerate(nml):
+                open(os.path.join(ROOT, "rays_b200", "configs", "examples", nm), "w").write(reconstructed_case(case1, 3 + k))
+            name = None
+        else:
+            name = os.path.basename(nml)
+            open(os.path.join(ROOT, "rays_b200", "configs", "examples", name), "w").write(translate_namelist(os.path.join(REF, nml)))
         pg = pages(os.path.join(REF, pdf))
         assert len(pg) == len(axes), (pdf, len(pg))
         for t, (hname, vname) in zip(pg, axes):
@@ -127,9 +156,11 @@ def main():
                     P = np.array(e[2])
                     rays.append({"h": (ax * P[:, 0] + bx).tolist(), "v": (ay * P[:, 1] + by).tolist()})
             title = [e[1] for e in ev if e[0] == "text" and "geometry" in e[1]]
-            out["figures"].append({"pdf": "examples_RAYS/" + pdf, "namelist": "examples/" + name, "title": title[0] if title else "",
-                                   "h": hname, "v": vname, "v_has_multiplier": bool(offset_text),
-                                   "quantum_h": abs(ax) * 1e-6, "quantum_v": abs(ay) * 1e-6, "rays": rays})
+            groups = [(name, rays)] if name else [(nml[0], rays[:3]), (nml[1], rays[3:])]
+            for nm, rr in groups:
+                out["figures"].append({"pdf": "examples_RAYS/" + pdf, "namelist": "examples/" + nm, "title": title[0] if title else "",
+                                       "h": hname, "v": vname, "v_has_multiplier": bool(offset_text),
+                                       "quantum_h": abs(ax) * 1e-6, "quantum_v": abs(ay) * 1e-6, "rays": rr})
             print(pdf, hname, vname, len(rays), "rays", [len(r["h"]) for r in rays], "multiplier" if offset_text else "")
     json.dump(out, open(os.path.join(HERE, "ref_plot_vectors.json"), "w"))
 

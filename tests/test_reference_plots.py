@@ -1,7 +1,8 @@
 """Parity against the REFERENCE'S OWN OUTPUT.  The example directories of the reference ship vector PDFs of the
 rays the Fortran code traced (examples_RAYS/*/ray_plots.*.pdf).  tests/golden/make_ref_plot_vectors.py turned
-their polylines into coordinates (tests/golden/ref_plot_vectors.json): 23 rays of five example inputs, slab and
-Solov'ev, all integrated with SG_ODE, 1 798 plotted trajectory points with a resolution of 1e-6 pt = 1.3e-9 ...
+their polylines into coordinates (tests/golden/ref_plot_vectors.json): 29 rays of seven example inputs, slab and
+Solov'ev (two of the slab inputs are not shipped and were reconstructed from the figures, see that script), all
+integrated with SG_ODE, 2 164 plotted trajectory points with a resolution of 1e-6 pt = 1.3e-9 ...
 8.7e-9 m (3e-14 m for z on the x10^-5 axis of the equatorial-plane runs).
 
 Every plotted point must coincide with a saved point of our trajectory of the same ray to that resolution, in
@@ -71,8 +72,8 @@ def test_oracle_reproduces_the_reference_figures(namelist):
 
 
 def test_figure_inventory():
-    assert len(GOLD["figures"]) == 8 and sum(len(f["rays"]) for f in GOLD["figures"]) == 41
-    assert sum(len(r["h"]) for f in GOLD["figures"] for r in f["rays"]) == 1798
+    assert len(GOLD["figures"]) == 10 and sum(len(f["rays"]) for f in GOLD["figures"]) == 47
+    assert sum(len(r["h"]) for f in GOLD["figures"] for r in f["rays"]) == 2164
 
 
 @pytest.mark.gpu
@@ -149,7 +150,8 @@ KX = json.load(open(os.path.join(HERE, "golden", "ref_kx_profiles.json")))
 @pytest.mark.parametrize("page", range(len(KX["pages"])))
 def test_oracle_reproduces_the_reference_kx_profiles(page):
     """examples_RAYS/ECH_90GHz_slab/pdf_plots/kx_plots.run_{1,2}.pdf: k0*nx (re, im) of two cold roots at 101 x positions
-    across the slab (write_kx_profiles, slab_processor_m.f90:729-827).  The tick labels are outlined, so the page's y
+    across the slab (write_kx_profiles, slab_processor_m.f90:729-827); run_3's input was reconstructed from its pages, so for
+    those six pages this test is a consistency check of that reconstruction and the ray figure is the independent one.  The tick labels are outlined, so the page's y
     calibration (scale, offset) is fitted: 2 numbers against 404 plotted values, which then agree to the PDF's 1e-4 pt.
     Where the two roots are a complex pair the fast/slow pages label them the other way round than the current source
     (an older build drew them): those pages are compared as unordered pairs (re) and by magnitude (im)."""
@@ -168,11 +170,11 @@ def test_oracle_reproduces_the_reference_kx_profiles(page):
     # calibration from the sum of the two real parts (independent of which curve is which root)
     A = np.stack([a_re + b_re, 2.0 * np.ones(101)], axis=1)
     scale, off = np.linalg.lstsq(A, Y[0] + Y[2], rcond=None)[0]
-    assert 0.01 < scale < 0.03
+    assert 0.001 < scale < 0.1
     y = [(c - off) / scale for c in Y]
     tol = 3e-4 / scale + 2e-7 * np.maximum(np.abs(a_re), np.abs(b_re))             # PDF quantisation + single-precision output
     tol_i = 3e-4 / scale + 2e-7 * np.abs(a_im)
-    if G["roots"] == "plus_minus":      # strict: red = plus (re, im), blue = minus (re, im), signs included
+    if G["ordered"]:      # strict: red = first root (re, im), blue = second root (re, im), signs included
         for got, want, t in ((y[0], a_re, tol), (y[1], a_im, tol_i), (y[2], b_re, tol), (y[3], b_im, tol_i)):
             assert np.all(np.abs(got - want) <= t), float(np.max(np.abs(got - want)))
     else:
