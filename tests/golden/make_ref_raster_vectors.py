@@ -16,15 +16,21 @@ import shutil
 import numpy as np
 from PIL import Image
 
-REF = "/root/reference/examples_RAYS/MPEX_examples/MPX_2nd_harm_11_rays_nz_delta_d_0.05_psiP_0.05"
+REFROOT = "/root/reference/examples_RAYS/MPEX_examples"
+CASES = [   # (example directory, our config directory, ray_init file)
+    ("MPX_2nd_harm_11_rays_nz_delta_d_0.05_psiP_0.05", "mpex_nz", "ray_init_2nd_harm_11_rays_nz.in"),
+    ("MPX_2nd_harm_11_rays_nz_30deg_delta_d_0.05_psiP_0.05", "mpex_nz_30deg", "ray_init_2nd_harm_11_rays_nz_30deg.in"),
+]
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
-def main():
-    cfgdir = os.path.join(ROOT, "rays_b200", "configs", "mpex_nz")
+def one_case(exdir, cfgname, ray_init):
+    REF = os.path.join(REFROOT, exdir)
+    cfgdir = os.path.join(ROOT, "rays_b200", "configs", cfgname)
     os.makedirs(cfgdir, exist_ok=True)
-    shutil.copyfile(os.path.join(REF, "ray_init_2nd_harm_11_rays_nz.in"), os.path.join(cfgdir, "ray_init_2nd_harm_11_rays_nz.in"))
+    shutil.copyfile(os.path.join(REF, ray_init), os.path.join(cfgdir, ray_init))
+    os.chmod(os.path.join(cfgdir, ray_init), 0o644)
     txt = open(os.path.join(REF, "rays.in")).read()   # the field file is the one already under configs/mpex/
     open(os.path.join(cfgdir, "rays.in"), "w").write(txt.replace("mirror_field_NC_file = 'Brz_fields", "mirror_field_NC_file = '../mpex/Brz_fields"))
 
@@ -45,13 +51,18 @@ def main():
     z = zmin + (xs - left) * px_z
     y = ymax - (ys - top) * px_y
     win = (z > 3.15) & (z < 3.31) & (y > -0.1165) & (y < -0.02)   # above the green LUFS line the rays end on
-    out = {"_doc": "made by tests/golden/make_ref_raster_vectors.py; ray-coloured pixel centres of the reference's MPEX nz figure, metres",
-           "png": "examples_RAYS/MPEX_examples/MPX_2nd_harm_11_rays_nz_delta_d_0.05_psiP_0.05/Ray_trajectories.png",
-           "namelist": "mpex_nz/rays.in", "h": "z", "v": "y", "pixel_h": px_z, "pixel_v": px_y,
+    out = {"png": "examples_RAYS/MPEX_examples/" + exdir + "/Ray_trajectories.png",
+           "namelist": cfgname + "/rays.in", "h": "z", "v": "y", "pixel_h": px_z, "pixel_v": px_y,
            "frame_px": [int(left), int(right), int(top), int(bottom)],
            "pixels_h": [round(float(v), 6) for v in z[win]], "pixels_v": [round(float(v), 6) for v in y[win]]}
+    print(exdir, "frame", left, right, top, bottom, "pixel", px_z, px_y, "ray pixels", int(win.sum()))
+    return out
+
+
+def main():
+    out = {"_doc": "made by tests/golden/make_ref_raster_vectors.py; ray-coloured pixel centres of the reference's MPEX figures, metres",
+           "figures": [one_case(*c) for c in CASES]}
     json.dump(out, open(os.path.join(HERE, "ref_raster_vectors.json"), "w"))
-    print("frame", left, right, top, bottom, "pixel", px_z, px_y, "ray pixels", int(win.sum()))
 
 
 if __name__ == "__main__":

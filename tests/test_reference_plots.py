@@ -93,15 +93,14 @@ def test_cuda_path_reproduces_the_reference_figures(namelist):
 RASTER = json.load(open(os.path.join(HERE, "golden", "ref_raster_vectors.json")))
 
 
-def _check_against_raster(res):
-    """The reference's MPEX 'nz' figure (11 rays, RK4_ODE, spline-interpolated mirror field; z-y plane, 0.87 mm per
+def _check_against_raster(res, G):
+    """One of the reference's MPEX figures ('nz' and 'nz_30deg' launch scans: 11 rays, RK4_ODE, spline-interpolated mirror field; z-y plane, 0.87 mm per
     pixel; tests/golden/make_ref_raster_vectors.py).  Rays overdraw each other, so the comparison is between the
     band of ray-coloured pixels and the band of our 11 trajectories, both ways:
       * every trajectory point has a ray-coloured pixel within 2.5 px (1.2 px for the rays whose colour survives the
         anti-aliasing: all but brown and grey), i.e. our rays run where the reference drew rays;
       * 98 % of the ray-coloured pixels lie within 1.5 px of one of our trajectories, i.e. the reference drew no ray
         where we have none -- in particular both edges of the fan and its end on the last flux surface agree."""
-    G = RASTER
     P = np.stack([np.array(G["pixels_h"]) / G["pixel_h"], np.array(G["pixels_v"]) / G["pixel_v"]], axis=1)
     assert res.nray == 11
     bands = []
@@ -123,22 +122,26 @@ def _check_against_raster(res):
     assert abs(min(z_end) - low.min()) < 2.5 * G["pixel_h"] and abs(max(z_end) - low.max()) < 2.5 * G["pixel_h"]
 
 
-def test_oracle_reproduces_the_reference_mpex_raster():
-    cfg = init_case(RASTER["namelist"])
+@pytest.mark.parametrize("fig", range(len(RASTER["figures"])))
+def test_oracle_reproduces_the_reference_mpex_raster(fig):
+    G = RASTER["figures"][fig]
+    cfg = init_case(G["namelist"])
     assert cfg.ode_solver == 1 and cfg.equilib_model == 4      # RK4_ODE, multiple_mirror
     r, n, w, _, _ = oracle_fan(cfg)
     o, st, _ = orc.trace(cfg, r, n, w)
     assert st == 0 and set(s.strip() for s in o.ray_stop_flag) == {"out_of_plasma"}
-    _check_against_raster(o)
+    _check_against_raster(o, G)
 
 
 @pytest.mark.gpu
-def test_cuda_path_reproduces_the_reference_mpex_raster():
+@pytest.mark.parametrize("fig", range(len(RASTER["figures"])))
+def test_cuda_path_reproduces_the_reference_mpex_raster(fig):
     rb.init(0)
-    cfg = init_case(RASTER["namelist"])
+    G = RASTER["figures"][fig]
+    cfg = init_case(G["namelist"])
     r, n, w, _, _ = oracle_fan(cfg)
     g = rb.trace(cfg, r, n, w)
-    _check_against_raster(g)
+    _check_against_raster(g, G)
     o, st, _ = orc.trace(cfg, r, n, w)
     assert np.array_equal(g.npoints, o.npoints) and g.ray_stop_flag == o.ray_stop_flag
 
