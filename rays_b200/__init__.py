@@ -113,6 +113,21 @@ def finalize_run(outdir: str = ".") -> None:
     _ck(_lib().rays_host_finalize_run(str(outdir).encode()), host=True)
 
 
+def write_deposition_profiles(outdir: str, profiles) -> None:
+    """write_deposition_profiles_NC (deposition_profiles_m.f90:336-420): deposition_profiles.<run_label>.nc from a list of
+    dicts with profile_name, grid_name, grid_min, grid_max, profile (n_bins values), Q_sum"""
+    n = len(profiles)
+    nb = len(profiles[0]["profile"])
+    assert all(len(p["profile"]) == nb for p in profiles)
+    names = "".join(p["profile_name"].ljust(20)[:20] for p in profiles).encode()
+    gnames = "".join(p["grid_name"].ljust(20)[:20] for p in profiles).encode()
+    gmin = np.array([p["grid_min"] for p in profiles], dtype=np.float64)
+    gmax = np.array([p["grid_max"] for p in profiles], dtype=np.float64)
+    prof = np.ascontiguousarray(np.stack([np.asarray(p["profile"], dtype=np.float64) for p in profiles]))
+    q = np.array([p["Q_sum"] for p in profiles], dtype=np.float64)
+    _ck(_lib().rays_host_write_deposition_profiles(str(outdir).encode(), n, names, gnames, nb, _dp(gmin), _dp(gmax), _dp(prof), _dp(q)), host=True)
+
+
 def results() -> dict:
     """numpy copies of the ray_results_m arrays after trace_rays()."""
     r = Results()

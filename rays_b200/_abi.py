@@ -159,7 +159,7 @@ HOST_SYMBOLS = [
     "rays_host_initialize", "rays_host_trace_rays", "rays_host_finalize_run", "rays_host_deallocate", "rays_host_last_error",
     "rays_host_cfg", "rays_host_nspec", "rays_host_run_label", "rays_host_ray_init_model", "rays_host_launch_params",
     "rays_host_directions_in", "rays_host_set_ode", "rays_host_set_fan", "rays_host_get_fan", "rays_host_results",
-    "rays_host_zfun", "rays_host_cspline", "rays_host_bcspline", "rays_host_mirror_magnetics",
+    "rays_host_zfun", "rays_host_cspline", "rays_host_bcspline", "rays_host_mirror_magnetics", "rays_host_write_deposition_profiles",
 ]
 
 # RAYS_B200_LIB overrides the library path (A/B experiments with alternative builds)
@@ -216,6 +216,7 @@ def load() -> C.CDLL:
         "rays_b200_mirror_brz_grid": (i, [P(Coil), C.c_int32, C.c_int32, dbl, dbl, C.c_int32, dbl, dbl, c_double_p, c_double_p, c_double_p,
                                        c_double_p, c_double_p]),
         "rays_host_mirror_magnetics": (i, [cp, cp, C.c_char_p, i]),
+        "rays_host_write_deposition_profiles": (i, [cp, i, cp, cp, i, c_double_p, c_double_p, c_double_p, c_double_p]),
         "rays_b200_ox_conv_analysis": (i, [vp, P(i64)]),
         "rays_host_cspline": (i, [c_double_p, i, c_double_p]), "rays_host_bcspline": (i, [c_double_p, i, c_double_p, i, c_double_p]),
     }

@@ -123,10 +123,16 @@ void NcWriter::put_char(int varid, const char *d, size_t n) { Var &v = vars_[var
 
 bool NcWriter::close(const std::string &path, std::string &err) {
     // CDF-2 (64-bit offsets).  Every variable here is < 4 GiB or the file is refused.
+    // Layout (netCDF classic): header, the fixed-size variables in definition order, then numrecs records, each holding
+    // one slab of every record variable in definition order.
     auto put_name = [](std::vector<uint8_t> &o, const std::string &s) { be32(o, (uint32_t)s.size()); o.insert(o.end(), s.begin(), s.end()); while (o.size() % 4) o.push_back(0); };
+    auto is_rec = [&](const Var &v) { return !v.dimids.empty() && dims_[v.dimids[0]].len == 0; };
+    auto slab_count = [&](const Var &v) { uint64_t cnt = 1; for (size_t k = is_rec(v) ? 1 : 0; k < v.dimids.size(); ++k) cnt *= (uint64_t)dims_[v.dimids[k]].len; return cnt; };
+    size_t n_rec_vars = 0;
+    for (auto &v : vars_) n_rec_vars += is_rec(v) ? 1 : 0;
     auto header = [&](const std::vector<uint64_t> &begins, std::vector<uint64_t> &vsizes) {
         std::vector<uint8_t> h = {'C', 'D', 'F', 2};
-        be32(h, 0);  // numrecs
+        be32(h, (uint32_t)numrecs_);
         if (dims_.empty()) { be32(h, 0); be32(h, 0); } else { be32(h, NC_DIMENSION); be32(h, (uint32_t)dims_.size()); for (auto &d : dims_) { put_name(h, d.name); be32(h, (uint32_t)d.len); } }
         if (gatts_.empty()) { be32(h, 0); be32(h, 0); } else {
             be32(h, NC_ATTRIBUTE); be32(h, (uint32_t)gatts_.size());
@@ -140,8 +146,8 @@ bool NcWriter::close(const std::string &path, std::string &err) {
                 for (int d : v.dimids) be32(h, (uint32_t)d);
                 be32(h, 0); be32(h, 0);  // no variable attributes
                 be32(h, (uint32_t)v.type);
-                uint64_t cnt = 1; for (int d : v.dimids) cnt *= (uint64_t)dims_[d].len;
-                uint64_t vs = (cnt * type_size(v.type) + 3) & ~(uint64_t)3;
+                uint64_t vs = slab_count(v) * type_size(v.type);
+                if (!(is_rec(v) && n_rec_vars == 1)) vs = (vs + 3) & ~(uint64_t)3;   // a lone record variable is not padded
                 vsizes[i] = vs;
                 be32(h, vs > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)vs);
                 be64(h, begins.empty() ? 0 : begins[i]);
@@ -153,19 +159,29 @@ bool NcWriter::close(const std::string &path, std::string &err) {
     std::vector<uint8_t> h0 = header(begins, vsizes);
     begins.resize(vars_.size());
     uint64_t off = h0.size();
-    for (size_t i = 0; i < vars_.size(); ++i) { begins[i] = off; off += vsizes[i]; }
+    for (size_t i = 0; i < vars_.size(); ++i) if (!is_rec(vars_[i])) { begins[i] = off; off += vsizes[i]; }
+    for (size_t i = 0; i < vars_.size(); ++i) if (is_rec(vars_[i])) { begins[i] = off; off += vsizes[i]; }
     std::vector<uint8_t> h = header(begins, vsizes);
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) { err = "cannot create '" + path + "'"; return false; }
     std::fwrite(h.data(), 1, h.size(), f);
     for (size_t i = 0; i < vars_.size(); ++i) {
         auto &v = vars_[i];
-        uint64_t cnt = 1; for (int d : v.dimids) cnt *= (uint64_t)dims_[d].len;
-        uint64_t need = cnt * type_size(v.type);
+        if (is_rec(v)) continue;
+        const uint64_t need = slab_count(v) * type_size(v.type);
         if (v.data.size() < need) v.data.resize(need, 0);
         std::fwrite(v.data.data(), 1, need, f);
         for (uint64_t p = need; p < vsizes[i]; ++p) std::fputc(0, f);
     }
+    for (int64_t r = 0; r < numrecs_; ++r)
+        for (size_t i = 0; i < vars_.size(); ++i) {
+            auto &v = vars_[i];
+            if (!is_rec(v)) continue;
+            const uint64_t slab = slab_count(v) * type_size(v.type);
+            if (v.data.size() < slab * (uint64_t)numrecs_) v.data.resize(slab * (uint64_t)numrecs_, 0);
+            std::fwrite(v.data.data() + slab * (uint64_t)r, 1, slab, f);
+            for (uint64_t p = slab; p < vsizes[i]; ++p) std::fputc(0, f);
+        }
     std::fclose(f);
     return true;
 }

@@ -43,10 +43,12 @@ class NcReader {
     int version_ = 1;
 };
 
-// Writer: define dims/vars/atts, then put whole variables (fixed-size only), then close().
+// Writer: define dims/vars/atts, then put whole variables, then close().  A dimension of length 0 is the record
+// (NC_UNLIMITED) dimension; variables whose first dimension it is are record variables, written for set_numrecs(n) records.
 class NcWriter {
   public:
     int def_dim(const std::string &name, int64_t len);
+    void set_numrecs(int64_t n) { numrecs_ = n; }
     int def_var(const std::string &name, int type, const std::vector<int> &dimids);
     void put_att_text(const std::string &name, const std::string &value);
     void put_att_int(const std::string &name, const std::vector<int32_t> &v);
@@ -63,6 +65,7 @@ class NcWriter {
     std::vector<Dim> dims_;
     std::vector<Var> vars_;
     std::vector<Att> gatts_;
+    int64_t numrecs_ = 0;
 };
 
 }  // namespace rays_host

@@ -945,6 +945,52 @@ int rays_host_trace_rays(void) {
     return 0;
 }
 
+// write_deposition_profiles_NC (post_process_lib/deposition_profiles_m.f90:336-420): deposition_profiles.<run_label>.nc with
+// the reference's structure -- record (unlimited) dimension n_profiles, n_bins, n_bins_p1, d20; per-profile Q_sum, n_bins,
+// grid_min, grid_max, profile_name, grid_name, grid (edges: grid_min + delta*(i-1), :151-159), profile; global attributes
+// RAYS_run_label and date_vector.  names: n_profiles x 20 characters, blank padded; profile: [n_profiles][n_bins].
+int rays_host_write_deposition_profiles(const char *outdir, int n_profiles, const char *profile_names, const char *grid_names, int n_bins,
+                                        const double *grid_min, const double *grid_max, const double *profile, const double *Q_sum) {
+    if (!g || !g->initialized) { g_err = "write_deposition_profiles called before initialize"; return RAYS_ERR_NOT_INITIALIZED; }
+    if (n_profiles < 1 || n_bins < 1 || !profile_names || !grid_names || !grid_min || !grid_max || !profile || !Q_sum)
+        return fail("write_deposition_profiles_NC: bad arguments");
+    State &S = *g;
+    NcWriter w;
+    const int d_prof = w.def_dim("n_profiles", 0);          // NF90_UNLIMITED
+    const int d_bins = w.def_dim("n_bins", n_bins);
+    const int d_bp1 = w.def_dim("n_bins_p1", n_bins + 1);
+    const int d20 = w.def_dim("d20", 20);
+    const int v_q = w.def_var("Q_sum", NC_DOUBLE, {d_prof});
+    const int v_nb = w.def_var("n_bins", NC_INT, {d_prof});
+    const int v_gmin = w.def_var("grid_min", NC_DOUBLE, {d_prof});
+    const int v_gmax = w.def_var("grid_max", NC_DOUBLE, {d_prof});
+    const int v_pn = w.def_var("profile_name", NC_CHAR, {d_prof, d20});      // Fortran [d20, n_profiles]
+    const int v_gn = w.def_var("grid_name", NC_CHAR, {d_prof, d20});
+    const int v_grid = w.def_var("grid", NC_DOUBLE, {d_prof, d_bp1});
+    const int v_p = w.def_var("profile", NC_DOUBLE, {d_prof, d_bins});
+    w.put_att_text("RAYS_run_label", S.diagnostics.run_label);
+    w.put_att_int("date_vector", std::vector<int32_t>(S.diagnostics.date_v, S.diagnostics.date_v + 8));
+    w.set_numrecs(n_profiles);
+    std::vector<int32_t> nb((size_t)n_profiles, n_bins);
+    std::vector<double> grid((size_t)n_profiles * (n_bins + 1));
+    for (int p = 0; p < n_profiles; ++p) {
+        const double delta = (grid_max[p] - grid_min[p]) / (double)(float)n_bins;     // real(n_bins): default real
+        for (int i = 1; i <= n_bins + 1; ++i) grid[(size_t)p * (n_bins + 1) + i - 1] = grid_min[p] + delta * (i - 1);
+    }
+    w.put_double(v_q, Q_sum, (size_t)n_profiles);
+    w.put_int(v_nb, nb.data(), nb.size());
+    w.put_double(v_gmin, grid_min, (size_t)n_profiles);
+    w.put_double(v_gmax, grid_max, (size_t)n_profiles);
+    w.put_char(v_pn, profile_names, (size_t)n_profiles * 20);
+    w.put_char(v_gn, grid_names, (size_t)n_profiles * 20);
+    w.put_double(v_grid, grid.data(), grid.size());
+    w.put_double(v_p, profile, (size_t)n_profiles * n_bins);
+    const std::string full = (outdir && outdir[0] ? std::string(outdir) + "/" : std::string()) + "deposition_profiles." + trim(S.diagnostics.run_label) + ".nc";
+    std::string err;
+    if (!w.close(full, err)) { g_err = err; return RAYS_ERR_IO; }
+    return 0;
+}
+
 // program mirror_magnetics (mirror_magnetics_lib/mirror_magnetics.f90:1-137): initialize_mirror_magnetics
 // (mirror_magnetics_m.f90:134-243: /mirror_magnetics_list/ from `namelist_path`, /coil_data_list/ and
 // /current_data_list/ from the files it names), calculate_B_on_rz_grid on the GPU (rays_b200_mirror_brz_grid),

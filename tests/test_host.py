@@ -181,3 +181,34 @@ def test_spline_profile_errors(tmp_path):
         p = tmp_path / "bad.in"
         p.write_text(txt.replace(old, new))
         assert L.rays_host_initialize(str(p).encode(), 0) != 0
+
+
+def test_deposition_profiles_netcdf_contract(tmp_path):
+    """write_deposition_profiles_NC (deposition_profiles_m.f90:336-420): record dimension n_profiles, the per-profile
+    variables and the grid of bin edges; read back with scipy's classic-netCDF reader (stand-in for plot_RAYS_*.py)."""
+    import _oracle as orc
+    from _cases import oracle_fan
+    from scipy.io import netcdf_file
+    cfg = init_case("axisym_deposition_fan.in", nstep_max=300)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=4, delta_rindex_theta=0.1, n_rindex_phi=4, delta_rindex_phi=0.08)
+    o, st, _ = orc.trace(cfg, r, n, w)
+    prof, q = orc.deposition(cfg, o, 101, 0.0, 1.0)
+    assert q > 0
+    # two records exercise the record layout (the reference writes Ptotal_psi and Ptotal_rho for axisym_toroid)
+    rb.write_deposition_profiles(str(tmp_path), [
+        dict(profile_name="Ptotal_psi", grid_name="psi", grid_min=0.0, grid_max=1.0, profile=prof, Q_sum=q),
+        dict(profile_name="Ptotal_rho", grid_name="rho", grid_min=0.0, grid_max=2.0, profile=2.0 * prof, Q_sum=2.0 * q)])
+    f = netcdf_file(str(tmp_path / "deposition_profiles.axisym_deposition_fan.nc"), "r", mmap=False)
+    assert f.dimensions["n_profiles"] is None and f.dimensions["n_bins"] == 101 and f.dimensions["n_bins_p1"] == 102 and f.dimensions["d20"] == 20
+    assert list(f.variables) == ["Q_sum", "n_bins", "grid_min", "grid_max", "profile_name", "grid_name", "grid", "profile"]
+    assert f.variables["profile"].shape == (2, 101) and f.variables["grid"].shape == (2, 102) and f.variables["profile_name"].shape == (2, 20)
+    assert f.variables["profile"].data.dtype == np.dtype(">f8") and f.variables["n_bins"].data.dtype == np.dtype(">i4")
+    assert np.array_equal(np.array(f.variables["profile"].data[0]), prof) and np.array_equal(np.array(f.variables["profile"].data[1]), 2.0 * prof)
+    assert list(f.variables["Q_sum"].data) == [q, 2.0 * q] and list(f.variables["n_bins"].data) == [101, 101]
+    assert list(f.variables["grid_max"].data) == [1.0, 2.0]
+    g1 = np.array(f.variables["grid"].data[1])
+    assert g1[0] == 0.0 and g1[-1] == 2.0 and np.allclose(np.diff(g1), 2.0 / 101, rtol=1e-12)
+    assert b"".join(f.variables["profile_name"].data[1]).decode() == "Ptotal_rho".ljust(20)
+    assert b"".join(f.variables["grid_name"].data[0]).decode() == "psi".ljust(20)
+    assert f.RAYS_run_label.decode().strip() == "axisym_deposition_fan" and len(f.date_vector) == 8
+    f.close()
