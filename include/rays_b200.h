@@ -303,6 +303,16 @@ int rays_b200_fan_download(double *rvec0, double *rindex_vec0, double *ray_pwr_w
  * (host).  If d_profile_out != NULL the per-GPU partial profile (n_bins doubles + Q_sum) is
  * also left at that DEVICE address for an NCCL reduce by the caller. */
 int rays_b200_deposition(rays_deposition *dep, double *d_profile_out);
+/* Reproducible sums (the reference sums bins over rays in ray order, deposition_profiles_m.f90:251).  The
+ * device bins into 64-bit FIXED-POINT accumulators (per-CTA partial profiles in shared memory, added to one global vector
+ * at the end of the trace kernel): integer addition is associative, so the profile is bitwise independent of the order in
+ * which rays, CTAs and GPUs contribute.  One count is *unit = 2^(e-62) with 2^e > sum |ray_pwr_wt| of the fan as it was
+ * uploaded / launched (rays_b200_fan_shard keeps that total, so every shard of one fan uses the same unit).
+ * rays_b200_deposition_fixed returns this GPU's raw bins (acc_out: host, d_acc_out: device, n_bins int64 each, either may
+ * be NULL) for an exact integer reduction across GPUs; profile = sum(acc) * unit.  A host that uploads pre-sharded fans
+ * sets the whole fan's weight with rays_b200_deposition_set_total_weight before tracing. */
+int rays_b200_deposition_fixed(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit);
+int rays_b200_deposition_set_total_weight(double total_weight);
 /* Same, fused into the trace: bins while tracing, no trajectory storage needed. */
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories);
 

@@ -292,6 +292,23 @@ def deposition(n_bins: int, grid_min: float, grid_max: float, d_profile_out: int
     return prof, float(d.Q_sum)
 
 
+def deposition_fixed(n_bins: int, grid_min: float, grid_max: float, d_acc_out: int | None = None):
+    """This GPU's raw fixed-point bins: (acc[n_bins] int64, unit, profile, Q_sum); profile = acc * unit.  Summing `acc` over
+    GPUs in integer arithmetic gives a profile that does not depend on the sharding (rays_b200.h).  d_acc_out: optional
+    DEVICE address of n_bins int64 that receives the same bins (for an NCCL reduce)."""
+    prof = np.zeros(n_bins)
+    acc = np.zeros(n_bins, dtype=np.int64)
+    unit = C.c_double(0)
+    d = Deposition()
+    d.n_bins, d.grid_min, d.grid_max, d.profile = int(n_bins), float(grid_min), float(grid_max), _dp(prof)
+    _ck(_lib().rays_b200_deposition_fixed(C.byref(d), acc.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(d_acc_out) if d_acc_out else None, C.byref(unit)))
+    return acc, unit.value, prof, float(d.Q_sum)
+
+
+def deposition_set_total_weight(total_weight: float) -> None:
+    _ck(_lib().rays_b200_deposition_set_total_weight(float(total_weight)))
+
+
 def probe_equilibrium(rvec: np.ndarray):
     r = np.ascontiguousarray(rvec, dtype=np.float64).reshape(-1, 3)
     out = np.zeros((r.shape[0], _abi.EQ_OUT))

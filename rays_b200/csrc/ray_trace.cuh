@@ -529,16 +529,26 @@ struct TraceArgs {
     int slice_steps;
     int resume;
     int sg_align;                   // SG kernel: 1 = lanes advance in alternating predictor / corrector slots (see trace_sg_kernel)
+    double *sg_state;               // slot-machine SG kernel (ray_trace_sg2.cuh): slot memory, grid * sg_state_bytes_per_cta bytes
     double *cont_state;             // [nray][kContStride]
     int *cont_list;
     unsigned long long *cont_count;
     unsigned long long *queue;      // next ray index to hand out
     unsigned long long *counters;   // [0] ray-steps, [1] RHS evaluations
-    // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_bins == NULL disables it
-    double *dep_bins;               // [n_bins] global accumulator
+    // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_acc == NULL disables it.  Bins are 64-bit FIXED-POINT
+    // accumulators (one unit = 1/dep_scale): integer addition is associative, so the profile does not depend on the order in
+    // which rays, CTAs or GPUs contribute (SURVEY.md 8e "reproducibility": 1/2/4/8-GPU profiles are bitwise identical).  Each
+    // CTA bins into shared memory (dep_smem = n_bins * 8 bytes of dynamic shared memory) and adds its partial profile to
+    // dep_acc once, at the end of the kernel; dep_smem = 0 (more bins than shared memory holds) bins straight into dep_acc.
+    unsigned long long *dep_acc;    // [n_bins] global accumulator
     int n_bins;
-    double grid_min, grid_max;
+    int dep_smem;
+    double grid_min, grid_max, dep_scale;
 };
+struct DepBins { unsigned long long *acc; int n_bins; double xmin, xmax, scale; };
+RD_INLINE void dep_add(const DepBins &b, int i, double x) {
+    atomicAdd(b.acc + i, (unsigned long long)__double2ll_rn(x * b.scale));
+}
 
 RD_INLINE void store_point(double *dst, const double *v, int nv) {
     // dst is 8-byte aligned; pair up into 16-byte stores when the row start allows it
@@ -568,7 +578,9 @@ template <int NV> RD_INLINE void store_point_fixed(double *dst, const double (&v
 
 // binner_real for one segment (bin_to_uniform_grid_m.f90:179-262): spreads delta_Q = Q1 - Q0 uniformly
 // over the bins spanned by [x0, x1]
-RD_INLINE void bin_segment(double *bins, int n_bins, double xmin, double xmax, double xa, double xb, double Qa, double Qb) {
+RD_INLINE void bin_segment(const DepBins &bins, double xa, double xb, double Qa, double Qb) {
+    const int n_bins = bins.n_bins;
+    const double xmin = bins.xmin, xmax = bins.xmax;
     const double x_bin_width = (xmax - xmin) / n_bins;
     const double x_low = fmin(xa, xb), x_high = fmax(xa, xb);
     double ix_low = (x_low - xmin) / x_bin_width, ix_high = (x_high - xmin) / x_bin_width;
@@ -590,12 +602,30 @@ RD_INLINE void bin_segment(double *bins, int n_bins, double xmin, double xmax, d
         ix_high = (double)n_bins; index_high = n_bins;
         delta_i = index_high - index_low;
     }
-    if (delta_i == 0) atomicAdd(bins + index_low - 1, delta_Q);
+    if (index_low < 1 || index_high > n_bins) return;   // NaN abscissa (a point outside the equilibrium's domain): nothing to bin
+    if (delta_i == 0) dep_add(bins, index_low - 1, delta_Q);
     else if (delta_i > 0) {
-        atomicAdd(bins + index_low - 1, delta_Q * (((double)index_low - ix_low) / delta_ix));
-        atomicAdd(bins + index_high - 1, delta_Q * ((ix_high - (double)(index_high - 1)) / delta_ix));
-        for (int i = index_low + 1; i <= index_high - 1; ++i) atomicAdd(bins + i - 1, Q_density);
+        dep_add(bins, index_low - 1, delta_Q * (((double)index_low - ix_low) / delta_ix));
+        dep_add(bins, index_high - 1, delta_Q * ((ix_high - (double)(index_high - 1)) / delta_ix));
+        for (int i = index_low + 1; i <= index_high - 1; ++i) dep_add(bins, i - 1, Q_density);
     }
+}
+// per-CTA partial profile in dynamic shared memory: cleared at kernel start, added to the global accumulator at kernel end
+extern __shared__ unsigned long long s_dep_bins[];
+RD_INLINE DepBins dep_begin(const TraceArgs &a, bool binning) {
+    DepBins b{nullptr, a.n_bins, a.grid_min, a.grid_max, a.dep_scale};
+    if (!binning) return b;
+    if (a.dep_smem > 0) {
+        for (int i = threadIdx.x; i < a.n_bins; i += blockDim.x) s_dep_bins[i] = 0ULL;
+        __syncthreads();
+        b.acc = s_dep_bins;
+    } else b.acc = a.dep_acc;
+    return b;
+}
+RD_INLINE void dep_end(const TraceArgs &a, bool binning) {
+    if (!binning || a.dep_smem <= 0) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.n_bins; i += blockDim.x) { const unsigned long long q = s_dep_bins[i]; if (q) atomicAdd(a.dep_acc + i, q); }
 }
 // abscissa of the deposition profile: Ptotal_x (slab) / Ptotal_psi (axisym_toroid)
 // (deposition_profiles_m.f90:438-499)
@@ -712,7 +742,8 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
     bool stiff = false;
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
-    const bool binning = a.dep_bins != nullptr && T::damp();
+    const bool binning = a.dep_acc != nullptr && T::damp();
+    const DepBins dbins = dep_begin(a, binning);
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
     const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t row = 0;
@@ -919,7 +950,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
                         if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
                         if (binning) {
                             const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
-                            bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
+                            bin_segment(dbins, dep_x, xn, dep_Q, Qn);
                             dep_x = xn; dep_Q = Qn;
                         }
                         ++my_steps;
@@ -976,6 +1007,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
         }
         if (streaming) { flush_finished_rays(a, fin, iray, fin_np, p0, row, nv, lane); fin = false; }
     }
+    dep_end(a, binning);
     unsigned long long stt = my_steps, rh = my_rhs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { stt += __shfl_down_sync(0xffffffffu, stt, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
@@ -1018,7 +1050,8 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
     bool active = false, exhausted = false, first = false;
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
-    const bool binning = a.dep_bins != nullptr && T::damp();
+    const bool binning = a.dep_acc != nullptr && T::damp();
+    const DepBins dbins = dep_begin(a, binning);
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
     const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t row = 0;
@@ -1118,7 +1151,7 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
                         if (fabs(resid_prev) > resid_max) resid_max = fabs(resid_prev);
                         if (binning) {
                             const double xn = dep_abscissa<T::EQ>(v), Qn = v[7] * pwr;
-                            bin_segment(a.dep_bins, a.n_bins, a.grid_min, a.grid_max, dep_x, xn, dep_Q, Qn);
+                            bin_segment(dbins, dep_x, xn, dep_Q, Qn);
                             dep_x = xn; dep_Q = Qn;
                         }
                         ++my_steps;
@@ -1185,6 +1218,7 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
         }
         if (streaming) { flush_finished_rays(a, fin, iray, fin_np, p0, row, nv, lane); fin = false; }
     }
+    dep_end(a, binning);
     unsigned long long st = my_steps, rh = my_rhs;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { st += __shfl_down_sync(0xffffffffu, st, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }

@@ -1,0 +1,732 @@
+// ray_trace_sg2.cuh — Shampine-Gordon trace kernel as a per-CTA SLOT MACHINE.
+//
+// SG_ode (SG_ode_m.f90:89-159) -> ode/de (ode_RAYS.f90:1-593) -> step (:595-1234) / intrp (:1235-1362), every decision of
+// the reference replayed with the reference's arithmetic, as in the per-lane state machine of ray_trace.cuh — what changes
+// is WHO executes WHAT.  Measured shape of the work (oracle statistics on the 1M-ray Solov'ev fan, tol 1e-6): a ds segment
+// restarts the integrator at order 1 and takes 18.7 attempted internal steps, 11.6 of which FAIL and 7.1
+// are accepted, at order k <= 3 (k = 4: 0.05 %): 27 right-hand sides per ray-step, and between two of them each ray needs
+// one of four different bookkeeping blocks.  With one ray pinned to one lane the blocks of a warp run one after another with
+// a third of the lanes each (ncu on the round-1 kernel: 13 of 32 lanes active, 129 KB of divergent code thrashing the
+// instruction cache).  Here a CTA owns kSgSlots ray SLOTS whose whole state (ray + integrator history) lives in slot memory
+// (HBM-backed, L1/L2-resident, field-major so that a warp's accesses coalesce), and every iteration
+//   1. the slots are SORTED by what they need next (predictor + f(p) + error test | f(yy) + history update |
+//      segment boundary: interpolate + check_save + start derivative | restart after a tolerance raise),
+//   2. thread t takes the t-th slot of that order and runs ONE macro-step: bookkeeping -> ONE right-hand side -> bookkeeping.
+// Warps are therefore homogeneous (at most one mixed warp per boundary between kinds), the right-hand side runs at one
+// site with every lane busy, and the once-per-segment work (interpolation, check_save, the start block: 1/27 of the
+// macro-steps) is held back until a batch of it has accumulated (kSgBatch) instead of running with one or two lanes.
+// Finished rays are copied out / re-filled from the global work queue by the whole CTA at the top of an iteration.
+#pragma once
+#include "ray_trace.cuh"
+
+namespace rays_dev {
+
+constexpr int kSgSlots = kTraceBlock;     // slots per CTA = threads per CTA
+#ifndef RAYS_SG_BATCH
+#define RAYS_SG_BATCH 24
+#endif
+constexpr int kSgBatch = RAYS_SG_BATCH;   // segment-boundary slots wait until this many are due (or nothing else is)
+
+enum SgKind : int { K_IDLE = 0, K_PRED, K_CORR, K_CHECK, K_START, K_BEGIN, K_FIN };
+enum SgBits : int { B_FIRST = 1, B_HAVE_F1 = 2, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
+
+// field-major slot memory of one CTA: double field f of slot j at D[f * kSgSlots + j]
+template <int NV> struct SgLayout {
+    enum : int {
+        V = 0, YY = V + NV, WT = YY + NV, P = WT + NV, YP = P + NV, PHI = YP + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16
+        ALPHA = PHI + 17 * NV, BETA = ALPHA + 13, SIG = BETA + 13, VV = SIG + 14, WW = VV + 13, G = WW + 14, PSI = G + 14,
+        S_ = PSI + 13, SOUT, REL, ABS, RPREV, RLAST, RMAX, DEPX, DEPQ, PWR, EPS, ABSDEL, TEND, RELEPS, ABSEPS, T0, X, H, HOLD,
+        ROUND, ABSH, XOLD, ERK, ERKM1, IRAY, NDBL
+    };
+    enum : int { NSTEP = 0, FLAG, P0, SLICE, NS, K, KOLD, IFAIL, KNEW, NOSTEP, KLE4, BITS, F1CODE, FINNP, NINT = 16 };
+};
+
+template <int NV> struct SgSlot {
+    using L = SgLayout<NV>;
+    double *d;   // &D[slot]
+    int *n;      // &I[slot]
+    RD_INLINE double &f(int field) const { return d[(size_t)field * kSgSlots]; }
+    RD_INLINE int &i(int field) const { return n[(size_t)field * kSgSlots]; }
+    RD_INLINE double &v(int l) const { return f(L::V + l); }
+    RD_INLINE double &yy(int l) const { return f(L::YY + l); }
+    RD_INLINE double &wt(int l) const { return f(L::WT + l); }
+    RD_INLINE double &p(int l) const { return f(L::P + l); }
+    RD_INLINE double &yp(int l) const { return f(L::YP + l); }
+    RD_INLINE double &phi(int i_, int l) const { return f(L::PHI + i_ * NV + l); }
+    RD_INLINE double &alpha(int i_) const { return f(L::ALPHA + i_); }
+    RD_INLINE double &beta(int i_) const { return f(L::BETA + i_); }
+    RD_INLINE double &sig(int i_) const { return f(L::SIG + i_); }
+    RD_INLINE double &vv(int i_) const { return f(L::VV + i_); }
+    RD_INLINE double &ww(int i_) const { return f(L::WW + i_); }
+    RD_INLINE double &g(int i_) const { return f(L::G + i_); }
+    RD_INLINE double &psi(int i_) const { return f(L::PSI + i_); }
+};
+
+// ---- the pieces of `step` on slot memory: statement for statement the functions of ray_trace.cuh ---------------------------
+// step, first block (ode_RAYS.f90:840-852); returns true on crash
+template <int NV> RD_INLINE bool sg2_block0(int neqn, const SgSlot<NV> &W, double &eps) {
+    using L = SgLayout<NV>;
+    const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
+    const double h = W.f(L::H), x = W.f(L::X);
+    if (fabs(h) < fouru * fabs(x)) { W.f(L::H) = copysign(fouru * fabs(x), h); return true; }
+    const double p5eps = 0.5 * eps;
+    double sum = 0.0;
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) { const double q = sg_div(W.yy(l), W.wt(l)); sum = sum + q * q; }
+    const double round = twou * sg_sqrt(sum);
+    W.f(L::ROUND) = round;
+    if (p5eps < round) { eps = 2.0 * round * (1.0 + fouru); return true; }
+    W.g(1) = 1.0; W.g(2) = 0.5; W.sig(1) = 1.0;
+    W.i(L::IFAIL) = 0;
+    return false;
+}
+// step, start block after the first derivative evaluation (:858-885)
+template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, double eps, int &bits) {
+    using L = SgLayout<NV>;
+    const double fouru = 4.0 * DBL_EPSILON;
+    const double p5eps = 0.5 * eps;
+    double tot = 0.0;
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) {
+        const double ypl = W.yp(l);
+        W.phi(1, l) = ypl; W.phi(2, l) = 0.0;
+        const double q = sg_div(ypl, W.wt(l)); tot = tot + q * q;
+    }
+    const double total = sg_sqrt(tot);
+    const double h = W.f(L::H);
+    double absh = fabs(h);
+    if (eps < 16.0 * total * h * h) absh = 0.25 * sg_sqrt(sg_div(eps, total));
+    W.f(L::H) = copysign(fmax(absh, fouru * fabs(W.f(L::X))), h);
+    W.f(L::HOLD) = 0.0;
+    W.i(L::K) = 1; W.i(L::KOLD) = 0;
+    bits = (bits & ~B_START) | B_PHASE1 | B_NORND;
+    if (p5eps <= 100.0 * W.f(L::ROUND)) {
+        bits &= ~B_NORND;
+        #pragma unroll 1
+        for (int l = 0; l < neqn; ++l) W.phi(15, l) = 0.0;
+    }
+}
+// step, blocks 1 and 2 (:896-1015): coefficients for this step size/order, then the predicted solution p at x + h
+template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int bits) {
+    using L = SgLayout<NV>;
+    const int k = W.i(L::K), kold = W.i(L::KOLD);
+    int ns = W.i(L::NS);
+    const double h = W.f(L::H);
+    const int kp1 = k + 1, kp2 = k + 2;
+    if (h != W.f(L::HOLD)) ns = 0;
+    if (ns <= kold) ns = ns + 1;
+    const int nsp1 = ns + 1;
+    if (ns <= k) {
+        W.beta(ns) = 1.0;
+        W.alpha(ns) = kSGinv[ns];
+        double temp1 = h * (double)ns;
+        W.sig(nsp1) = 1.0;
+        double beta_prev = 1.0, sig_prev = 1.0;
+        #pragma unroll 1
+        for (int i = nsp1; i <= k; ++i) {
+            const double temp2 = W.psi(i - 1);
+            W.psi(i - 1) = temp1;
+            beta_prev = sg_div(beta_prev * temp1, temp2);
+            W.beta(i) = beta_prev;
+            temp1 = temp2 + h;
+            const double al = sg_div(h, temp1);
+            W.alpha(i) = al;
+            sig_prev = (double)i * al * sig_prev;
+            W.sig(i + 1) = sig_prev;
+        }
+        W.psi(k) = temp1;
+        if (ns <= 1) {
+            #pragma unroll 1
+            for (int iq = 1; iq <= k; ++iq) { W.vv(iq) = kSGinvTri[iq]; W.ww(iq) = kSGinvTri[iq]; }
+        } else {
+            if (kold < k) {
+                W.vv(k) = kSGinvTri[k];
+                #pragma unroll 1
+                for (int j = 1; j <= ns - 2; ++j) { const int i = k - j; W.vv(i) = W.vv(i) - W.alpha(j + 1) * W.vv(i + 1); }
+            }
+            const double al = W.alpha(ns);
+            #pragma unroll 1
+            for (int iq = 1; iq <= kp1 - ns; ++iq) { const double t = W.vv(iq) - al * W.vv(iq + 1); W.vv(iq) = t; W.ww(iq) = t; }
+            W.g(nsp1) = W.ww(1);
+        }
+        #pragma unroll 1
+        for (int i = ns + 2; i <= kp1; ++i) {
+            const double al = W.alpha(i - 1);
+            #pragma unroll 1
+            for (int iq = 1; iq <= kp2 - i; ++iq) W.ww(iq) = W.ww(iq) - al * W.ww(iq + 1);
+            W.g(i) = W.ww(1);
+        }
+    }
+    W.i(L::NS) = ns;
+    #pragma unroll 1
+    for (int i = nsp1; i <= k; ++i) {
+        const double b = W.beta(i);
+        #pragma unroll 1
+        for (int l = 0; l < neqn; ++l) W.phi(i, l) = b * W.phi(i, l);
+    }
+    const bool nornd = (bits & B_NORND) != 0;
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) {   // component by component: same operation order per component as the reference's i-outer loops
+        W.phi(kp2, l) = W.phi(kp1, l);
+        W.phi(kp1, l) = 0.0;
+        double pl = 0.0, up = 0.0;
+        #pragma unroll 1
+        for (int i = k; i >= 1; --i) {
+            const double f = W.phi(i, l);
+            pl = pl + f * W.g(i);
+            up = f + up;
+            W.phi(i, l) = up;
+        }
+        const double y = W.yy(l);
+        if (!nornd) {
+            const double tau = h * pl - W.phi(15, l);
+            const double pp = y + tau;
+            W.p(l) = pp;
+            W.phi(16, l) = (pp - y) - tau;
+        } else W.p(l) = y + h * pl;
+    }
+    const double x = W.f(L::X);
+    W.f(L::XOLD) = x;
+    W.f(L::X) = x + h;
+    W.f(L::ABSH) = fabs(h);
+}
+// step, after the derivative at the predicted point (:1022-1110): error estimates, accept or fail.
+// returns 0 = accepted (corrected solution formed in yy), 1 = failed: retry with the reduced step, 2 = crash (eps doubled)
+template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W, double &eps, int &bits) {
+    using L = SgLayout<NV>;
+    const double fouru = 4.0 * DBL_EPSILON;
+    const int k = W.i(L::K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
+    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps;
+    double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) {
+        const Rcp wl = rcp_of(W.wt(l));   // up to three quotients by the same weight
+        const double ypl = W.yp(l), ph1 = W.phi(1, l);
+        if (0 < km2) { const double q = sg_quot(W.phi(km1, l) + ypl - ph1, wl); erkm2 = erkm2 + q * q; }
+        if (0 <= km2) { const double q = sg_quot(W.phi(k, l) + ypl - ph1, wl); erkm1 = erkm1 + q * q; }
+        const double q = sg_quot(ypl - ph1, wl);
+        erk = erk + q * q;
+    }
+    if (0 < km2) erkm2 = absh * W.sig(km1) * kSGgstr[km2] * sg_sqrt(erkm2);
+    if (0 <= km2) erkm1 = absh * W.sig(k) * kSGgstr[km1] * sg_sqrt(erkm1);
+    const double rt_erk = sg_sqrt(erk);
+    const double gkp1 = W.g(kp1);
+    const double err = absh * rt_erk * (W.g(k) - gkp1);
+    erk = absh * rt_erk * W.sig(kp1) * kSGgstr[k];
+    int knew = k;
+    if (0 < km2) {
+        if (fmax(erkm1, erkm2) <= erk) knew = km1;
+    } else if (0 == km2) {
+        if (erkm1 <= 0.5 * erk) knew = km1;
+    }
+    W.i(L::KNEW) = knew; W.f(L::ERK) = erk; W.f(L::ERKM1) = erkm1;
+    const double h = W.f(L::H);
+    if (err <= eps) {   // accepted: correct (:1123-1141)
+        W.i(L::KOLD) = k;
+        W.f(L::HOLD) = h;
+        const bool nornd = (bits & B_NORND) != 0;
+        #pragma unroll 1
+        for (int l = 0; l < neqn; ++l) {
+            const double pl = W.p(l), dl = W.yp(l) - W.phi(1, l);
+            if (!nornd) {
+                const double rho = h * gkp1 * dl - W.phi(16, l);
+                const double y = pl + rho;
+                W.yy(l) = y;
+                W.phi(15, l) = (y - pl) - rho;
+            } else W.yy(l) = pl + h * gkp1 * dl;
+        }
+        return 0;
+    }
+    // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
+    bits &= ~B_PHASE1;
+    const double x = W.f(L::XOLD);
+    W.f(L::X) = x;
+    #pragma unroll 1
+    for (int i = 1; i <= k; ++i) {
+        const Rcp bi = rcp_of(W.beta(i));
+        #pragma unroll 1
+        for (int l = 0; l < neqn; ++l) W.phi(i, l) = sg_quot(W.phi(i, l) - W.phi(i + 1, l), bi);
+    }
+    #pragma unroll 1
+    for (int i = 2; i <= k; ++i) W.psi(i - 1) = W.psi(i) - h;
+    const int ifail = W.i(L::IFAIL) + 1;
+    W.i(L::IFAIL) = ifail;
+    double temp2 = 0.5;
+    if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sg_sqrt(sg_div(p5eps, erk)); }
+    if (3 <= ifail) knew = 1;
+    double hn = temp2 * h;
+    W.i(L::K) = knew;
+    if (fabs(hn) < fouru * fabs(x)) {
+        W.f(L::H) = copysign(fouru * fabs(x), hn);
+        eps = eps + eps;
+        return 2;
+    }
+    W.f(L::H) = hn;
+    return 1;
+}
+// step, after the derivative at the corrected point (:1147-1231): update differences, choose order and step
+template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W, double eps, int &bits) {
+    using L = SgLayout<NV>;
+    const double fouru = 4.0 * DBL_EPSILON;
+    int k = W.i(L::K);
+    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.i(L::KNEW), ns = W.i(L::NS);
+    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), erkm1 = W.f(L::ERKM1);
+    double erk = W.f(L::ERK);
+    if (knew == km1 || k == 12) bits &= ~B_PHASE1;
+    const bool phase1 = (bits & B_PHASE1) != 0;
+    const bool want_erkp1 = !phase1 && knew != km1 && kp1 <= ns;
+    double erkp1 = 0.0;
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) {
+        const double d = W.yp(l) - W.phi(1, l);
+        W.phi(kp1, l) = d;
+        const double e2 = d - W.phi(kp2, l);
+        W.phi(kp2, l) = e2;
+        #pragma unroll 1
+        for (int i = 1; i <= k; ++i) W.phi(i, l) = W.phi(i, l) + d;
+        if (want_erkp1) { const double q = sg_div(e2, W.wt(l)); erkp1 = erkp1 + q * q; }
+    }
+    if (phase1) {
+        k = kp1; erk = 0.0;
+    } else if (knew == km1) {
+        k = km1; erk = erkm1;
+    } else if (kp1 <= ns) {
+        erkp1 = absh * kSGgstr[kp1] * sg_sqrt(erkp1);
+        if (k == 1) {
+            if (erkp1 < 0.5 * erk) { k = kp1; erk = erkp1; }
+        } else if (erkm1 <= fmin(erk, erkp1)) {
+            k = km1; erk = erkm1;
+        } else if (erkp1 < erk && k < 12) {
+            k = kp1; erk = erkp1;
+        }
+    }
+    double hnew = h + h;
+    if (!phase1) {
+        if (p5eps < erk * kSGtwo[k + 1]) {
+            hnew = h;
+            if (p5eps < erk) {
+                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
+                hnew = absh * fmax(0.5, fmin((double)0.9f, r));
+                hnew = copysign(fmax(hnew, fouru * fabs(W.f(L::X))), h);
+            }
+        }
+    }
+    W.i(L::K) = k;
+    W.f(L::H) = hnew;
+}
+// intrp (ode_RAYS.f90:1235-1362) into the ray vector v; the segment is over, so g/ww of the slot serve as scratch
+template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double xout) {
+    using L = SgLayout<NV>;
+    const double hi = xout - W.f(L::X);
+    const int ki = W.i(L::KOLD) + 1;
+    #pragma unroll 1
+    for (int i = 1; i <= ki; ++i) W.ww(i) = kSGinv[i];
+    W.g(1) = 1.0;
+    double term = 0.0;
+    #pragma unroll 1
+    for (int j = 2; j <= ki; ++j) {
+        const double psijm1 = W.psi(j - 1);
+        const Rcp pj = rcp_of(psijm1);
+        const double gamma = sg_quot(hi + term, pj);
+        const double eta = sg_quot(hi, pj);
+        #pragma unroll 1
+        for (int i = 1; i <= ki + 1 - j; ++i) W.ww(i) = gamma * W.ww(i) - eta * W.ww(i + 1);
+        W.g(j) = W.ww(1);
+        term = psijm1;
+    }
+    #pragma unroll 1
+    for (int l = 0; l < neqn; ++l) {
+        double yo = 0.0;
+        #pragma unroll 1
+        for (int j = 1; j <= ki; ++j) { const int i = ki + 1 - j; yo = yo + W.g(i) * W.phi(i, l); }
+        W.v(l) = W.yy(l) + hi * yo;
+    }
+}
+
+template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
+
+// ---- the kernel -------------------------------------------------------------------------------------------------------------
+#ifndef RAYS_SG2_MIN_CTAS
+#define RAYS_SG2_MIN_CTAS 2
+#endif
+template <class T>
+__global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(const TraceArgs a) {
+    constexpr int NV = T::NV;
+    constexpr int NSM = NSpec<T::NS>::MAX;
+    constexpr int S = kSgSlots;
+    constexpr int NW = kTraceBlock / 32;
+    using L = SgLayout<NV>;
+    const int nv = T::nv();
+    const rays_cfg &c = g_dc.c;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    const int warp = tid >> 5;
+    const int maxnum = 500;
+    const double fouru = 4.0 * DBL_EPSILON;
+    __shared__ int s_kind[S];
+    __shared__ int s_list[S];
+    __shared__ int s_wcnt[NW][4];
+    __shared__ unsigned long long s_base;
+    __shared__ int s_exhausted;
+    double *const D = a.sg_state + (size_t)blockIdx.x * L::NDBL * S;
+    int *const I = reinterpret_cast<int *>(a.sg_state + (size_t)gridDim.x * L::NDBL * S) + (size_t)blockIdx.x * L::NINT * S;
+    const bool binning = a.dep_acc != nullptr && T::damp();
+    const DepBins dbins = dep_begin(a, binning);
+    const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
+    unsigned long long my_steps = 0;
+    unsigned my_rhs = 0;
+    s_kind[tid] = K_IDLE;
+    if (tid == 0) s_exhausted = 0;
+    __syncthreads();
+
+    for (;;) {
+        // ---- 1. rays that ended in the last iteration: streaming copy-out by the warp that holds the slot, slot becomes idle
+        if (__syncthreads_or(s_kind[tid] == K_FIN)) {
+            if (streaming) {
+                unsigned m = __ballot_sync(0xffffffffu, s_kind[tid] == K_FIN);
+                while (m) {
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int sl = warp * 32 + l;
+                    const SgSlot<NV> F{D + sl, I + sl};
+                    const long long ir = (long long)F.f(L::IRAY);
+                    const int np = F.i(L::FINNP), pf = F.i(L::P0);
+                    const size_t rw = (size_t)blockIdx.x * S + sl;
+                    if (a.host_ray_vec)
+                        copy_row_to_host(a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv,
+                                         a.ray_vec + rw * a.npoints_alloc * nv, np * nv, lane);
+                    if (a.host_residual)
+                        copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
+                }
+            }
+            if (s_kind[tid] == K_FIN) s_kind[tid] = K_IDLE;
+        }
+        // ---- 2. refill idle slots from the work queue: one atomic per CTA
+        {
+            const bool want = s_kind[tid] == K_IDLE && !s_exhausted;
+            const unsigned wb = __ballot_sync(0xffffffffu, want);
+            if (lane == 0) s_wcnt[warp][0] = __popc(wb);
+            __syncthreads();
+            int total = 0, before = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const int cw = s_wcnt[w][0]; if (w < warp) before += cw; total += cw; }
+            if (total > 0) {
+                if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
+                __syncthreads();
+                if (want) {
+                    const long long idx = (long long)(s_base + (unsigned long long)(before + __popc(wb & ((1u << lane) - 1u))));
+                    if (idx >= a.nray) s_exhausted = 1;
+                    else {
+                        const SgSlot<NV> W{D + tid, I + tid};
+                        const long long iray = a.order ? (long long)a.order[idx] : idx;
+                        const size_t row = streaming ? (size_t)blockIdx.x * S + tid : (size_t)iray;
+                        W.f(L::IRAY) = (double)iray;
+                        W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
+                        W.i(L::SLICE) = 0;
+                        double v[NV];
+                        if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
+                            RayCarry k;
+                            resume_ray(a, iray, v, nv, k);
+                            W.f(L::S_) = k.s; W.f(L::SOUT) = k.sout; W.i(L::NSTEP) = k.nstep; W.i(L::FLAG) = k.flag;
+                            W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
+                            W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
+                            W.i(L::P0) = streaming ? k.nstep + 1 : 0;
+                            W.i(L::BITS) = 0;
+                        } else {
+                            W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
+                            W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
+                            W.f(L::RPREV) = 0.0; W.f(L::RLAST) = 0.0; W.f(L::RMAX) = 0.0; W.f(L::DEPX) = 0.0; W.f(L::DEPQ) = 0.0;
+                            initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                            if (a.ray_vec) {
+                                double *dst = a.ray_vec + row * a.npoints_alloc * nv;
+                                if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                            }
+                            if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
+                            if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                            W.i(L::BITS) = B_FIRST;
+                        }
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
+                        s_kind[tid] = K_CHECK;
+                    }
+                }
+            }
+        }
+        // ---- 3. sort the slots by what they need next; segment-boundary slots wait for a batch
+        int slot = -1;
+        {
+            const int kd = s_kind[tid];
+            const int key = kd == K_PRED ? 0 : (kd == K_CORR ? 1 : (kd == K_CHECK ? 2 : ((kd == K_START || kd == K_BEGIN) ? 3 : -1)));
+            unsigned bal[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) bal[q] = __ballot_sync(0xffffffffu, key == q);
+            __syncthreads();   // everybody has read s_wcnt / s_base of step 2
+            if (lane < 4) s_wcnt[warp][lane] = __popc(bal[lane]);
+            __syncthreads();
+            int tot[4], bef[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                tot[q] = 0; bef[q] = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { const int cw = s_wcnt[w][q]; if (w < warp) bef[q] += cw; tot[q] += cw; }
+            }
+            const int n_other = tot[0] + tot[1] + tot[3];
+            const bool take_check = tot[2] >= kSgBatch || n_other < S / 4;
+            const int n_check = take_check ? tot[2] : 0;
+            const int n_all = n_other + n_check;
+            if (n_all == 0) {
+                if (tot[2] == 0 && s_exhausted) break;    // every slot idle, queue empty
+                __syncthreads();
+                continue;
+            }
+            if (key >= 0 && (key != 2 || take_check)) {
+                int base = 0;
+                if (key >= 1) base += tot[0];
+                if (key >= 2) base += tot[1];
+                if (key >= 3) base += n_check;
+                const unsigned mine = key == 0 ? bal[0] : (key == 1 ? bal[1] : (key == 2 ? bal[2] : bal[3]));
+                const int befk = key == 0 ? bef[0] : (key == 1 ? bef[1] : (key == 2 ? bef[2] : bef[3]));
+                s_list[base + befk + __popc(mine & ((1u << lane) - 1u))] = tid;
+            }
+            __syncthreads();
+            if (tid < n_all) slot = s_list[tid];
+        }
+        // ---- 4. one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
+        if (slot >= 0) {
+            const SgSlot<NV> W{D + slot, I + slot};
+            const int kind = s_kind[slot];
+            int bits = W.i(L::BITS);
+            int next = kind;
+            int req = 0;   // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
+                           // 4: check_save of the new point v + the start derivative of the next segment there
+            bool stop = false, did_not_start = false, crashed = false, enter = false, de_top = false, suspended = false;
+            int flag = W.i(L::FLAG);
+            double eps = W.f(L::EPS);
+            const long long iray = (long long)W.f(L::IRAY);
+            const size_t row = streaming ? (size_t)blockIdx.x * S + slot : (size_t)iray;
+            if (kind == K_PRED) { sg2_predict<NV>(nv, W, bits); req = 2; }
+            else if (kind == K_CORR) req = 3;
+            else if (kind == K_START) req = 1;
+            else if (kind == K_BEGIN) enter = true;
+            else {   // K_CHECK
+                req = 4;
+                if (bits & B_INTRP) {   // past the output point: interpolate, segment done (iflag = 2)
+                    bits &= ~B_INTRP;
+                    const double sout = W.f(L::SOUT);
+                    sg2_intrp<NV>(nv, W, sout);
+                    W.f(L::S_) = sout;
+                    const int sn = W.i(L::SLICE) + 1;
+                    W.i(L::SLICE) = sn;
+                    if (a.slice_steps > 0 && sn >= a.slice_steps) {   // suspend: packed into full CTAs by the next launch
+                        double v[NV];
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) v[i] = i < nv ? W.v(i) : 0.0;
+                        const int nstep = W.i(L::NSTEP);
+                        RayCarry k{sout, sout, W.f(L::RPREV), W.f(L::RLAST), W.f(L::RMAX), W.f(L::DEPX), W.f(L::DEPQ), W.f(L::REL), W.f(L::ABS), nstep, flag};
+                        suspend_ray(a, iray, v, nv, k);
+                        W.i(L::FINNP) = nstep + 1 - W.i(L::P0);
+                        suspended = true; req = 0; next = K_FIN;
+                    }
+                }
+            }
+            // ---- equilibrium + derivative evaluation: ONE site.  req = 4 also runs check_save on the same equilibrium
+            // (the reference evaluates it twice at this point: check_save.f90:38 and eqn_ray.f90:87 of the next segment's
+            // first derivative), saves the point and runs the loop-top tests of ray_tracing.f90:118-172
+            if (req) {
+                double uu[NV], ff[NV];
+                const int ufield = req == 2 ? L::P : (req == 4 ? L::V : L::YY);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) { uu[i] = i < nv ? W.f(ufield + i) : 0.0; ff[i] = 0.0; }
+                Eq<NSM> e;
+                equilibrium<T::EQ, T::NS, true>(uu[0], uu[1], uu[2], e);
+                double dddx[3], dddk[3], dddw = 0.0;
+                bool have_derivs = false;
+                if (req == 4) {
+                    const bool first = (bits & B_FIRST) != 0;
+                    double resid = 0.0;
+                    if (e.err) {
+                        flag = e.err;
+                        if (T::damp() && uu[7 < NV ? 7 : 0] > c.total_damping_limit) { stop = true; flag = RAYS_STOP_TOTAL_ABSORPTION; }
+                    } else {
+                        check_save_resid<T>(e, uu, resid, stop, flag);
+                        double dddw_cold;
+                        if (T::DERIV == RAYS_DERIV_COLD) {
+                            ray_derivs<T>(e, uu, dddx, dddk, dddw);
+                            have_derivs = true;
+                            dddw_cold = dddw;
+                        } else {
+                            const Rcp K0 = g_dc.rc_k0;
+                            const double nvec[3] = {qdiv(uu[3], K0), qdiv(uu[4], K0), qdiv(uu[5], K0)};
+                            double tx[3], tk[3];
+                            deriv_cold<T::NS>(e, nvec, tx, tk, dddw_cold);
+                        }
+                        check_save_tail<T>(uu, dddw_cold, stop, flag);
+                    }
+                    if (stop) did_not_start = first;
+                    else {
+                        const double pwr = W.f(L::PWR);
+                        if (!first) {   // the point passed check_save: save it (ray_tracing.f90:237-243)
+                            const int nstep = W.i(L::NSTEP) + 1;
+                            W.i(L::NSTEP) = nstep;
+                            const int pp = nstep - W.i(L::P0);
+                            if (a.ray_vec) {
+                                double *dst = a.ray_vec + (row * a.npoints_alloc + pp) * nv;
+                                if (T::GENERIC) store_point(dst, uu, nv); else store_point_fixed<NV>(dst, uu);
+                            }
+                            if (a.residual) a.residual[row * a.npoints_alloc + pp] = resid;
+                            const double rp = W.f(L::RLAST);
+                            W.f(L::RPREV) = rp;
+                            W.f(L::RLAST) = resid;
+                            if (fabs(rp) > W.f(L::RMAX)) W.f(L::RMAX) = fabs(rp);
+                            if (binning) {
+                                const double xn = dep_abscissa<T::EQ>(uu), Qn = uu[7 < NV ? 7 : 0] * pwr;
+                                bin_segment(dbins, W.f(L::DEPX), xn, W.f(L::DEPQ), Qn);
+                                W.f(L::DEPX) = xn; W.f(L::DEPQ) = Qn;
+                            }
+                            ++my_steps;
+                        } else if (binning) { W.f(L::DEPX) = dep_abscissa<T::EQ>(uu); W.f(L::DEPQ) = uu[7 < NV ? 7 : 0] * pwr; }
+                        bits &= ~B_FIRST;
+                        const double sout0 = W.f(L::SOUT);    // top of the trajectory loop (ray_tracing.f90:118-172)
+                        const double sout1 = sout0 + c.ds;
+                        W.f(L::S_) = sout0;
+                        W.f(L::SOUT) = sout1;
+                        if (sout1 > c.s_max) { stop = true; flag = RAYS_STOP_SOUT_GT_SMAX; }
+                        else if (W.i(L::NSTEP) + 1 > c.nstep_max) { stop = true; flag = RAYS_STOP_NSTEP_MAX; }
+                    }
+                }
+                if (!stop) {
+                    int code = e.err;
+                    if (!code && !have_derivs) code = ray_derivs<T>(e, uu, dddx, dddk, dddw);
+                    if (!code) code = ray_equations<T>(e, uu, dddx, dddk, dddw, ff);
+                    if (!code) {
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
+                    }
+                    if (req == 4) {          // kept for the start of the next segment (consumed after de's entry tests)
+                        bits |= B_HAVE_F1;
+                        W.i(L::F1CODE) = code;
+                        enter = true;
+                    } else {
+                        my_rhs += 1;
+                        if (code) { flag = code; W.f(L::SOUT) = W.f(L::S_); stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
+                        else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits); next = K_PRED; }
+                        else if (req == 2) {
+                            const int r = sg2_after_predict<NV>(nv, W, eps, bits);
+                            if (r == 0) next = K_CORR;
+                            else if (r == 1) next = K_PRED;   // failed: predict again with the reduced step
+                            else crashed = true;
+                        } else {
+                            sg2_after_correct<NV>(nv, W, eps, bits);
+                            const int nostep = W.i(L::NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
+                            W.i(L::NOSTEP) = nostep;
+                            int kle4 = W.i(L::KLE4) + 1;
+                            if (4 < W.i(L::KOLD)) kle4 = 0;
+                            W.i(L::KLE4) = kle4;
+                            if (50 <= kle4) bits |= B_STIFF;
+                            de_top = true;
+                        }
+                    }
+                }
+            }
+            if (enter && !stop) {   // ode/de entry with iflag = 1 (ode_RAYS.f90:425-505)
+                const double s = W.f(L::S_), sout = W.f(L::SOUT), rel_err = W.f(L::REL), abs_err = W.f(L::ABS);
+                if (s == sout) { stop = true; flag = RAYS_STOP_SG_T_EQ_TOUT; }
+                else if (rel_err < 0.0 || abs_err < 0.0) { stop = true; flag = RAYS_STOP_SG_BAD_TOL; }
+                else {
+                    eps = fmax(rel_err, abs_err);
+                    if (eps <= 0.0) { stop = true; flag = RAYS_STOP_SG_EPS_LE_0; }
+                    else {
+                        const double del = sout - s;
+                        W.f(L::T0) = s;
+                        W.f(L::ABSDEL) = fabs(del);
+                        W.f(L::TEND) = s + 10.0 * del;
+                        W.i(L::NOSTEP) = 0; W.i(L::KLE4) = 0;
+                        W.f(L::RELEPS) = rel_err / eps;
+                        W.f(L::ABSEPS) = abs_err / eps;
+                        bits = (bits & (B_HAVE_F1 | B_FIRST)) | B_START | B_NORND;
+                        W.f(L::X) = s;
+#pragma unroll
+                        for (int l = 0; l < NV; ++l) if (l < nv) W.yy(l) = W.v(l);
+                        W.f(L::H) = copysign(fmax(fabs(sout - s), fouru * fabs(s)), sout - s);
+                        W.i(L::NS) = 0; W.i(L::K) = 0; W.i(L::KOLD) = 0; W.f(L::HOLD) = 0.0;
+                        de_top = true;
+                    }
+                }
+            }
+            if (de_top && !stop) {   // top of de's loop (ode_RAYS.f90:509-562)
+                const double x = W.f(L::X);
+                if (W.f(L::ABSDEL) <= fabs(x - W.f(L::T0))) {   // past the output point: the segment ends (interpolation is batched)
+                    bits |= B_INTRP;
+                    next = K_CHECK;
+                } else if (maxnum <= W.i(L::NOSTEP)) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
+                    flag = (bits & B_STIFF) ? RAYS_STOP_SG_STIFF : RAYS_STOP_SG_MAXNUM;
+#pragma unroll
+                    for (int l = 0; l < NV; ++l) if (l < nv) W.v(l) = W.yy(l);
+                    W.f(L::S_) = x;
+                    stop = true;
+                } else {
+                    const double h = W.f(L::H);
+                    W.f(L::H) = copysign(fmin(fabs(h), fabs(W.f(L::TEND) - x)), h);
+                    const double releps = W.f(L::RELEPS), abseps = W.f(L::ABSEPS);
+#pragma unroll 1
+                    for (int l = 0; l < nv; ++l) W.wt(l) = releps * fabs(W.yy(l)) + abseps;
+                    if (sg2_block0<NV>(nv, W, eps)) crashed = true;
+                    else if (bits & B_START) {
+                        if (bits & B_HAVE_F1) {   // the start derivative was evaluated together with check_save at this very point
+                            bits &= ~B_HAVE_F1;
+                            my_rhs += 1;
+                            const int f1 = W.i(L::F1CODE);
+                            if (f1) { flag = f1; W.f(L::SOUT) = W.f(L::S_); stop = true; }
+                            else { sg2_after_start<NV>(nv, W, eps, bits); next = K_PRED; }
+                        } else next = K_START;
+                    } else next = K_PRED;
+                }
+            }
+            if (crashed && !stop) {   // iflag = 3: tolerances raised (ode_RAYS.f90:566-575), then SG_ode's test (SG_ode_m.f90:138-149)
+                const double rel_err = eps * W.f(L::RELEPS), abs_err = eps * W.f(L::ABSEPS);
+                W.f(L::REL) = rel_err; W.f(L::ABS) = abs_err;
+#pragma unroll
+                for (int l = 0; l < NV; ++l) if (l < nv) W.v(l) = W.yy(l);
+                W.f(L::S_) = W.f(L::X);
+                const double total_error = fabs(rel_err) + fabs(abs_err);
+                if (total_error > c.SG_error_limit) { flag = RAYS_STOP_ODE_TOTAL_ERROR; stop = true; }
+                else next = K_BEGIN;           // SG_ode loops: ode again from the current s to sout
+            }
+            W.f(L::EPS) = eps;
+            W.i(L::FLAG) = flag;
+            W.i(L::BITS) = bits;
+            if (stop) {
+                a.stop_code[iray] = flag;
+                const int nstep = W.i(L::NSTEP);
+                if (did_not_start) {   // only npoints, flag and the first point are set (ray_tracing.f90:101-112)
+                    a.npoints[iray] = 1;
+                    if (a.initial_ray_power) a.initial_ray_power[iray] = 0.0;
+                    if (a.end_residuals) a.end_residuals[iray] = 0.0;
+                    if (a.max_residuals) a.max_residuals[iray] = 0.0;
+                    if (a.end_ray_parameter) a.end_ray_parameter[iray] = 0.0;
+                    if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = 0.0;
+                    if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = 0.0;
+                } else {               // summary block (ray_tracing.f90:252-260)
+                    a.npoints[iray] = nstep + 1;
+                    if (a.initial_ray_power) a.initial_ray_power[iray] = W.f(L::PWR);
+                    if (a.end_residuals) a.end_residuals[iray] = nstep >= 1 ? W.f(L::RPREV) : 0.0;
+                    if (a.max_residuals) a.max_residuals[iray] = nstep >= 1 ? W.f(L::RMAX) : -DBL_MAX;
+                    if (a.end_ray_parameter) a.end_ray_parameter[iray] = W.v(6);
+                    if (a.end_ray_vec) for (int i = 0; i < nv; ++i) a.end_ray_vec[(size_t)iray * nv + i] = W.v(i);
+                }
+                W.i(L::FINNP) = did_not_start ? 1 : nstep + 1 - W.i(L::P0);
+                next = K_FIN;
+            }
+            (void)suspended;
+            s_kind[slot] = next;
+        }
+        __syncthreads();
+    }
+    dep_end(a, binning);
+    unsigned long long stt = my_steps, rh = my_rhs;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { stt += __shfl_down_sync(0xffffffffu, stt, o); rh += __shfl_down_sync(0xffffffffu, rh, o); }
+    if (lane == 0) { atomicAdd(a.counters, stt); atomicAdd(a.counters + 1, rh); }
+}
+
+}  // namespace rays_dev

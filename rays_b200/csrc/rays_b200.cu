@@ -84,6 +84,8 @@ struct Ctx {
     // time slicing: suspended-ray records and the two resume lists
     DevBuf<double> cont_state;
     DevBuf<int> cont_list[2];
+    DevBuf<double> sg_state;       // slot memory of the Shampine-Gordon slot-machine kernel
+    size_t cached_sgb = 0;
     double last_first_ms = 0, last_resume_ms = 0;
     int last_phases = 0;
     cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
@@ -92,10 +94,12 @@ struct Ctx {
     const char *cached_name = "";
     const void *cached_ops = nullptr;
     // deposition
-    DevBuf<double> dep;
+    DevBuf<unsigned long long> dep;   // fixed-point bins (see TraceArgs::dep_acc)
     int dep_bins = 0;
     double dep_min = 0, dep_max = 0;
     bool dep_fused = false;
+    double fan_weight = 0.0;          // sum |ray_pwr_wt| over the fan as uploaded / launched (kept by fan_shard): sets the bin unit
+    double dep_scale = 1.0;           // units per watt-fraction: 2^(62 - e), 2^e > fan_weight
     // stats
     double last_ms = 0;
     long long last_steps = 0, last_rhs = 0;
@@ -257,7 +261,7 @@ __global__ void fan_shard_kernel(long long n_out, int rank, int world, const dou
 }
 // calculate_deposition_profiles on stored trajectories (deposition_profiles_m.f90:228-292): one thread per ray
 template <int EQ_> __global__ void deposition_kernel(long long nray, int nv, int npa, const double *ray_vec, const int *npoints,
-                                                      const double *pwr, double *bins, int n_bins, double gmin, double gmax) {
+                                                      const double *pwr, const DepBins bins) {
     const long long iray = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (iray >= nray) return;
     const int np = npoints[iray];
@@ -267,7 +271,7 @@ template <int EQ_> __global__ void deposition_kernel(long long nray, int nv, int
     for (int ip = 1; ip < np; ++ip) {
         const double *vp = v + (size_t)ip * nv;
         const double xb = dep_abscissa<EQ_>(vp), Qb = vp[7] * P;
-        bin_segment(bins, n_bins, gmin, gmax, xa, xb, Qa, Qb);
+        bin_segment(bins, xa, xb, Qa, Qb);
         xa = xb; Qa = Qb;
     }
 }
@@ -442,14 +446,20 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     a.end_ray_vec = g.endv.p + (size_t)first * g.res_nv;
     a.queue = g.queue.p;
     a.counters = g.queue.p + 1;
-    a.dep_bins = binned ? g.dep.p : nullptr;
-    a.n_bins = g.dep_bins; a.grid_min = g.dep_min; a.grid_max = g.dep_max;
+    a.dep_acc = binned ? g.dep.p : nullptr;
+    a.n_bins = g.dep_bins; a.grid_min = g.dep_min; a.grid_max = g.dep_max; a.dep_scale = g.dep_scale;
+    a.dep_smem = (binned && (size_t)g.dep_bins * 8 <= 40 * 1024) ? g.dep_bins * 8 : 0;
     int bps = g.cached_bps;
     const char *name = g.cached_name;
     if (bps <= 0 || g.cached_ops != ops) {   // occupancy of the selected specialisation: queried once per configuration
-        CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name));
+        size_t sgb = 0;
+        CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name, &sgb));
         if (bps < 1) bps = 1;
-        g.cached_bps = bps; g.cached_name = name; g.cached_ops = ops;
+        g.cached_bps = bps; g.cached_name = name; g.cached_ops = ops; g.cached_sgb = sgb;
+    }
+    if (g.cached_sgb) {   // Shampine-Gordon slot machine: slot memory for every CTA of the largest grid
+        CK(g.sg_state.reserve(((size_t)g.num_sms * bps * g.cached_sgb + 7) / 8));
+        a.sg_state = g.sg_state.p;
     }
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;
     int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
@@ -468,7 +478,9 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
     // An SG ray-step is ~25 right-hand sides and the lanes of a warp drift apart in integrator phase: short slices on
     // every pass keep the warps packed (1M-ray Solov'ev fan, tol 1e-6: 250 -> 64 steps: 5.15e7 -> 5.65e7 ray-steps/s)
-    if (c.ode_solver == RAYS_ODE_SG && count >= 2 * lanes) { slice = 64; forced = true; }
+    // (the per-lane SG kernel of round 1 needs short slices on every pass to keep its warps packed; the slot machine regroups
+    // its slots every iteration and slices like RK4)
+    if (c.ode_solver == RAYS_ODE_SG && g.sel.sg_lanes && count >= 2 * lanes) { slice = 64; forced = true; }
     if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) { slice = atoi(env); forced = true; } }
     a.sg_align = 1;        // measurement aid: RAYS_B200_SG_ALIGN=0 lets the SG lanes run free (results are identical)
     if (const char *env = getenv("RAYS_B200_SG_ALIGN")) { if (env[0]) a.sg_align = atoi(env) != 0; }
@@ -489,7 +501,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
         CK(cudaMemsetAsync(g.queue.p + 3, 0, sizeof(unsigned long long), g.stream));
         const int grid_p = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>((n_this + kTraceBlock - 1) / kTraceBlock, 1));
         CK(cudaEventRecord(g.ev_m0, g.stream));
-        CK(ops->trace(g.sel, a, grid_p, g.stream, nullptr, nullptr));
+        CK(ops->trace(g.sel, a, grid_p, g.stream, nullptr, nullptr, nullptr));
         CK(cudaEventRecord(g.ev_m1, g.stream));
         g.last_launches += 1;
         g.last_phases = phase + 1;
@@ -638,10 +650,10 @@ int rays_b200_finalize(void) {
     cudaDeviceSynchronize();
     DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.prof_grid[0], &g.prof_grid[1], &g.prof_grid[2],
                               &g.prof_fspl[0], &g.prof_fspl[1], &g.prof_fspl[2], &g.eq_rgrid, &g.eq_zgrid, &g.eq_psi, &g.eq_T, &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
-                              &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv, &g.dep};
+                              &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv};
     for (auto *b : bufs) b->release();
-    g.npoints.release(); g.stop.release(); g.queue.release();
-    g.cont_state.release(); g.cont_list[0].release(); g.cont_list[1].release();
+    g.npoints.release(); g.stop.release(); g.queue.release(); g.dep.release();
+    g.cont_state.release(); g.cont_list[0].release(); g.cont_list[1].release(); g.sg_state.release();
     cudaEventDestroy(g.ev_m0); cudaEventDestroy(g.ev_m1);
     if (g.pinned) cudaFreeHost(g.pinned);
     g.pinned = nullptr; g.pinned_bytes = 0;
@@ -766,6 +778,8 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
     g.sel.damp = c.damping_model != RAYS_DAMP_NONE;
     g.sel.grads = c.integrate_eq_gradients != 0;
+    g.sel.sg_lanes = false;   // measurement aid: RAYS_B200_SG_LANES=1 runs the per-lane SG state machine (identical results)
+    if (const char *env = getenv("RAYS_B200_SG_LANES")) g.sel.sg_lanes = env[0] && atoi(env) != 0;
     g.cached_bps = 0; g.cached_ops = nullptr;
     for (int ode = 1; ode <= 2; ++ode) {
         const TuOps *ops = tu_ops(c.equilib_model, ode);
@@ -791,6 +805,9 @@ int rays_b200_fan_upload(const rays_fan *fan) {
     }
     CK(cudaStreamSynchronize(g.stream));
     g.nray = fan->nray;
+    double wsum = 0.0;
+    if (fan->ray_pwr_wt) for (size_t i = 0; i < n; ++i) wsum += std::fabs(fan->ray_pwr_wt[i]);
+    g.fan_weight = wsum;
     return 0;
 }
 
@@ -823,6 +840,14 @@ int rays_b200_fan_shard(int rank, int world) {
     return 0;
 }
 
+// unit of the fixed-point deposition bins: the absorbed power of a fan cannot exceed the sum of its ray weights, so with
+// 2^e > sum |ray_pwr_wt| every partial sum stays below 2^62 units of 2^(e-62)
+static void set_dep_scale() {
+    int e = 0;
+    if (g.fan_weight > 0.0 && std::isfinite(g.fan_weight)) e = std::ilogb(g.fan_weight) + 1;
+    g.dep_scale = std::ldexp(1.0, 62 - e);
+}
+
 static int trace_device_impl(int store_trajectories, bool binned) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
@@ -841,7 +866,7 @@ static int trace_device_impl(int store_trajectories, bool binned) {
     if (rc) return rc;
     g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
     CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
-    if (binned) CK(cudaMemsetAsync(g.dep.p, 0, (size_t)g.dep_bins * sizeof(double), g.stream));
+    if (binned) CK(cudaMemsetAsync(g.dep.p, 0, (size_t)g.dep_bins * sizeof(unsigned long long), g.stream));
     CK(cudaEventRecord(g.ev0, g.stream));
     if (g.nray > 0) {
         rc = launch_trace(0, g.nray, store_trajectories ? g.ray_vec.p : nullptr, store_trajectories ? g.residual.p : nullptr, binned);
@@ -868,6 +893,7 @@ int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, 
         return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
     CK(g.dep.reserve((size_t)n_bins));
     g.dep_bins = n_bins; g.dep_min = grid_min; g.dep_max = grid_max;
+    set_dep_scale();
     return trace_device_impl(store_trajectories, true);
 }
 
@@ -1106,6 +1132,7 @@ static int run_launch_fan(int kind, long long npos, const std::vector<double> &p
     CK(cudaStreamSynchronize(g.stream));
     pos.release(); dir.release(); rv.release(); nv.release(); valid.release(); counts.release(); total.release();
     g.nray = nray;
+    g.fan_weight = nray > 0 ? (kind == 1 ? 1.0 / (double)nray : 1.0) : 0.0;
     if (nray_out) *nray_out = nray;
     return 0;
 }
@@ -1160,41 +1187,70 @@ int rays_b200_launch_fan_directions(int64_t n_in, const double *rvec_in, const d
 }
 
 // ======================= deposition ==========================================================================
-int rays_b200_deposition(rays_deposition *dep, double *d_profile_out) {
+// calculate_deposition_profiles (deposition_profiles_m.f90:228-292).  The device bins into 64-bit fixed-point accumulators
+// (TraceArgs::dep_acc); acc_out (host, n_bins int64, optional) and d_acc_out (device, optional) receive the raw bins of THIS
+// GPU for an exact integer reduction across GPUs, *unit the value of one count.
+static int deposition_impl(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!dep || dep->n_bins < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad arguments");
     const rays_cfg &c = g.dc.c;
     const int nb = dep->n_bins;
     if (g.dep_fused) {
-        if (nb != g.dep_bins) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: n_bins differs from the binned trace");
+        if (nb != g.dep_bins || dep->grid_min != g.dep_min || dep->grid_max != g.dep_max)
+            return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: n_bins / grid differ from the binned trace");
     } else {
         if (!g.have_traj) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: no stored trajectories; trace with storage or use rays_b200_trace_device_binned");
         if (c.damping_model == RAYS_DAMP_NONE) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: needs a damping model");
         if (c.equilib_model != RAYS_EQ_SLAB && c.equilib_model != RAYS_EQ_AXISYM_TOROID)
             return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
+        if (!(dep->grid_max > dep->grid_min)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad grid");
         CK(g.dep.reserve((size_t)nb));
         g.dep_bins = nb; g.dep_min = dep->grid_min; g.dep_max = dep->grid_max;
-        CK(cudaMemsetAsync(g.dep.p, 0, (size_t)nb * sizeof(double), g.stream));
+        set_dep_scale();
+        CK(cudaMemsetAsync(g.dep.p, 0, (size_t)nb * sizeof(unsigned long long), g.stream));
         if (g.res_nray > 0) {
             const unsigned grid = (unsigned)((g.res_nray + 127) / 128);
+            const DepBins bins{g.dep.p, nb, dep->grid_min, dep->grid_max, g.dep_scale};
             if (c.equilib_model == RAYS_EQ_SLAB)
-                deposition_kernel<RAYS_EQ_SLAB><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, g.dep.p, nb, dep->grid_min, dep->grid_max);
+                deposition_kernel<RAYS_EQ_SLAB><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, bins);
             else
-                deposition_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, g.dep.p, nb, dep->grid_min, dep->grid_max);
+                deposition_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, bins);
             CK(cudaGetLastError());
         }
     }
-    std::vector<double> h((size_t)nb);
-    CK(cudaMemcpyAsync(h.data(), g.dep.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    if (d_profile_out) CK(cudaMemcpyAsync(d_profile_out, g.dep.p, (size_t)nb * sizeof(double), cudaMemcpyDeviceToDevice, g.stream));
+    std::vector<long long> h((size_t)nb);
+    CK(cudaMemcpyAsync(h.data(), g.dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
+    if (d_acc_out) CK(cudaMemcpyAsync(d_acc_out, g.dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
-    double q = 0.0;
-    for (int b = 0; b < nb; ++b) { if (dep->profile) dep->profile[b] = h[(size_t)b]; q += h[(size_t)b]; }
-    dep->Q_sum = q;
-    if (d_profile_out) {
-        CK(cudaMemcpyAsync(d_profile_out + nb, &q, sizeof(double), cudaMemcpyHostToDevice, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+    const double u = 1.0 / g.dep_scale;   // a power of two: the conversions below are exact scalings
+    long long q = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (dep->profile) dep->profile[b] = (double)h[(size_t)b] * u;
+        if (acc_out) acc_out[b] = (int64_t)h[(size_t)b];
+        q += h[(size_t)b];
     }
+    dep->Q_sum = (double)q * u;
+    if (unit) *unit = u;
+    return 0;
+}
+int rays_b200_deposition(rays_deposition *dep, double *d_profile_out) {
+    int rc = deposition_impl(dep, nullptr, nullptr, nullptr);
+    if (rc || !d_profile_out) return rc;
+    std::vector<double> h((size_t)dep->n_bins + 1);   // this GPU's partial profile + Q_sum as doubles (exact: power-of-two unit)
+    std::vector<long long> raw((size_t)dep->n_bins);
+    CK(cudaMemcpyAsync(raw.data(), g.dep.p, raw.size() * sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    for (int b = 0; b < dep->n_bins; ++b) h[(size_t)b] = (double)raw[(size_t)b] / g.dep_scale;
+    h[(size_t)dep->n_bins] = dep->Q_sum;
+    CK(cudaMemcpyAsync(d_profile_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int rays_b200_deposition_fixed(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit) { return deposition_impl(dep, acc_out, d_acc_out, unit); }
+int rays_b200_deposition_set_total_weight(double total_weight) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (!(total_weight >= 0.0)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: total weight must be >= 0");
+    g.fan_weight = total_weight;
     return 0;
 }
 

@@ -3,6 +3,9 @@
 // contract in ray_physics.cuh).  The RK4 translation units also carry the one-point probes and the
 // launch-fan kernels of their equilibrium.
 #include "trace_tu.cuh"
+#if RAYS_TU_ODE == 2
+#include "ray_trace_sg2.cuh"
+#endif
 
 #ifndef RAYS_TU_EQ
 #error "compile with -DRAYS_TU_EQ=<1..4> -DRAYS_TU_ODE=<1,2>"
@@ -18,32 +21,39 @@ cudaError_t tu_upload(const DevCfg *dc, cudaStream_t st) {
     return cudaMemcpyToSymbolAsync(g_dc, dc, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, st);
 }
 
-template <class T> cudaError_t launch_trace(const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, const char *nm) {
+template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb, const char *nm) {
     if (name) *name = nm;
+    if (sgb) *sgb = 0;
+#if RAYS_TU_ODE == 2
+    if (sgb && !s.sg_lanes) *sgb = sg2_state_bytes_per_cta<T::NV>();
+#endif
     if (bps) {
 #if RAYS_TU_ODE == 1
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
 #else
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0);
+        cudaError_t e = s.sg_lanes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kTraceBlock, 0);
 #endif
         if (e != cudaSuccess) return e;
     }
     if (grid <= 0) return cudaSuccess;
 #if RAYS_TU_ODE == 1
-    trace_rk4_kernel<T><<<grid, kTraceBlock, 0, st>>>(a);
+    (void)s;
+    trace_rk4_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
 #else
-    trace_sg_kernel<T><<<grid, kTraceBlock, 0, st>>>(a);
+    if (s.sg_lanes) trace_sg_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
+    else trace_sg2_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
 #endif
     return cudaGetLastError();
 }
 
 #define RAYS_SEL(DER, DMP, GRD, NM)                                                                            \
     if (s.ray_deriv == DER && !s.generic && s.damp == (DMP == 1) && s.grads == (GRD == 1))                     \
-        return launch_trace<Traits<kEQ, 2, DER, DMP, GRD>>(a, grid, st, bps, name, NM);
+        return launch_trace<Traits<kEQ, 2, DER, DMP, GRD>>(s, a, grid, st, bps, name, sgb, NM);
 #define RAYS_GEN(DER, NM)                                                                                      \
-    if (s.ray_deriv == DER && s.generic) return launch_trace<Traits<kEQ, 0, DER, -1, -1>>(a, grid, st, bps, name, NM);
+    if (s.ray_deriv == DER && s.generic) return launch_trace<Traits<kEQ, 0, DER, -1, -1>>(s, a, grid, st, bps, name, sgb, NM);
 
-cudaError_t tu_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name) {
+cudaError_t tu_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb) {
     RAYS_SEL(RAYS_DERIV_COLD, 0, 0, "trace<ns2,cold,nv7>")
     RAYS_SEL(RAYS_DERIV_COLD, 1, 0, "trace<ns2,cold,damp,nv8>")
     RAYS_SEL(RAYS_DERIV_COLD, 0, 1, "trace<ns2,cold,grads,nv12>")

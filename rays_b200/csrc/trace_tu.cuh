@@ -12,6 +12,7 @@ struct KernelSel {
     int ray_deriv;        // RAYS_DERIV_*
     bool generic;         // run-time species count / nv layout
     bool damp, grads;     // used when !generic
+    bool sg_lanes;        // Shampine-Gordon: the per-lane state machine of round 1 (measurement aid) instead of the slot machine
 };
 
 struct FanLaunchArgs {    // launch-fan kernels (ray_init modules), see trace_tu.cu
@@ -28,7 +29,8 @@ struct FanLaunchArgs {    // launch-fan kernels (ray_init modules), see trace_tu
 struct TuOps {
     cudaError_t (*upload)(const DevCfg *, cudaStream_t);
     // occupancy query + launch of the trace kernel selected by sel; grid < 0 -> only report
-    cudaError_t (*trace)(const KernelSel &, const TraceArgs &, int grid, cudaStream_t, int *blocks_per_sm, const char **name);
+    // sg_state_bytes_per_cta: slot memory the Shampine-Gordon slot-machine kernel needs per CTA (0 for the other kernels)
+    cudaError_t (*trace)(const KernelSel &, const TraceArgs &, int grid, cudaStream_t, int *blocks_per_sm, const char **name, size_t *sg_state_bytes_per_cta);
     cudaError_t (*probe_equilibrium)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
     cudaError_t (*probe_rhs)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
     cudaError_t (*probe_check_save)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
