@@ -313,6 +313,11 @@ int rays_b200_deposition(rays_deposition *dep, double *d_profile_out);
  * sets the whole fan's weight with rays_b200_deposition_set_total_weight before tracing. */
 int rays_b200_deposition_fixed(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit);
 int rays_b200_deposition_set_total_weight(double total_weight);
+/* Per-ray summaries of the last trace packed on the device for the gather across GPUs: d_out (DEVICE,
+ * rows_capacity rows) receives one row of 6 + 2 nv doubles per ray: npoints, stop code, initial_ray_power, end_residuals,
+ * max_residuals, end_ray_parameter, start_ray_vec(nv), end_ray_vec(nv) (ray_tracing.f90:252-260).  d_out == NULL only
+ * reports *rows and *row_doubles. */
+int rays_b200_summaries_pack(void *d_out, int64_t rows_capacity, int64_t *rows, int32_t *row_doubles);
 /* Same, fused into the trace: bins while tracing, no trajectory storage needed. */
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories);
 

@@ -305,6 +305,13 @@ def deposition_fixed(n_bins: int, grid_min: float, grid_max: float, d_acc_out: i
     return acc, unit.value, prof, float(d.Q_sum)
 
 
+def summaries_pack(d_out: int | None = None, rows_capacity: int = 0):
+    """Pack the per-ray summaries of the last trace into DEVICE memory at d_out (rows of 6 + 2 nv doubles); returns (rows, row_doubles)."""
+    rows, rd = C.c_int64(0), C.c_int32(0)
+    _ck(_lib().rays_b200_summaries_pack(C.c_void_p(d_out) if d_out else None, int(rows_capacity), C.byref(rows), C.byref(rd)))
+    return int(rows.value), int(rd.value)
+
+
 def deposition_set_total_weight(total_weight: float) -> None:
     _ck(_lib().rays_b200_deposition_set_total_weight(float(total_weight)))
 

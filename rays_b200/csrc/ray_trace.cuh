@@ -636,6 +636,12 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 }
 
 constexpr int kTraceBlock = 128;
+// Shampine-Gordon slot machine (ray_trace_sg2.cuh): every warp of a CTA owns kSgSlots ray slots
+#ifndef RAYS_SG_SLOTS
+#define RAYS_SG_SLOTS 64
+#endif
+constexpr int kSgSlots = RAYS_SG_SLOTS;
+constexpr int kSgWarps = kTraceBlock / 32;
 constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, resid_prev/last/max, dep_x, dep_Q, rel_err, abs_err
 
 // one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the

@@ -1,4 +1,4 @@
-// ray_trace_sg2.cuh — Shampine-Gordon trace kernel as a per-CTA SLOT MACHINE.
+// ray_trace_sg2.cuh — Shampine-Gordon trace kernel as per-warp SLOT MACHINES.
 //
 // SG_ode (SG_ode_m.f90:89-159) -> ode/de (ode_RAYS.f90:1-593) -> step (:595-1234) / intrp (:1235-1362), every decision of
 // the reference replayed with the reference's arithmetic, as in the per-lane state machine of ray_trace.cuh — what changes
@@ -7,39 +7,43 @@
 // are accepted, at order k <= 3 (k = 4: 0.05 %): 27 right-hand sides per ray-step, and between two of them each ray needs
 // one of four different bookkeeping blocks.  With one ray pinned to one lane the blocks of a warp run one after another with
 // a third of the lanes each (ncu on the round-1 kernel: 13 of 32 lanes active, 129 KB of divergent code thrashing the
-// instruction cache).  Here a CTA owns kSgSlots ray SLOTS whose whole state (ray + integrator history) lives in slot memory
-// (HBM-backed, L1/L2-resident, field-major so that a warp's accesses coalesce), and every iteration
-//   1. the slots are SORTED by what they need next (predictor + f(p) + error test | f(yy) + history update |
-//      segment boundary: interpolate + check_save + start derivative | restart after a tolerance raise),
-//   2. thread t takes the t-th slot of that order and runs ONE macro-step: bookkeeping -> ONE right-hand side -> bookkeeping.
-// Warps are therefore homogeneous (at most one mixed warp per boundary between kinds), the right-hand side runs at one
-// site with every lane busy, and the once-per-segment work (interpolation, check_save, the start block: 1/27 of the
-// macro-steps) is held back until a batch of it has accumulated (kSgBatch) instead of running with one or two lanes.
-// Finished rays are copied out / re-filled from the global work queue by the whole CTA at the top of an iteration.
+// instruction cache).  Here every WARP owns kSgSlots ray SLOTS (twice its lanes) whose whole state (ray + integrator
+// history) lives in slot memory (HBM-backed, L1/L2-resident, field-major so that a warp's accesses coalesce), and every
+// iteration of the warp
+//   1. counts what its slots need next (predictor + f(p) + error test | f(yy) + history update | segment boundary:
+//      interpolate + check_save + start derivative | restart after a tolerance raise) and picks the KIND most slots wait for,
+//   2. lane j takes the j-th slot of that kind and runs ONE macro-step: bookkeeping -> ONE right-hand side -> bookkeeping.
+// All lanes of a warp therefore run the same code on 32 different rays whenever 32 slots of one kind exist (with 64 slots
+// there nearly always are), the once-per-segment work (1/27 of the macro-steps) accumulates until it is the largest group
+// instead of running with one or two lanes, and no warp ever waits for another: there is no CTA-level barrier in the loop
+// (the first, CTA-sorted version of this kernel lost 23 % of its stall samples to __syncthreads).
+// Finished rays are copied out / re-filled from the global work queue by the warp at the top of an iteration.
 #pragma once
 #include "ray_trace.cuh"
 
 namespace rays_dev {
 
-constexpr int kSgSlots = kTraceBlock;     // slots per CTA = threads per CTA
-#ifndef RAYS_SG_BATCH
-#define RAYS_SG_BATCH 24
-#endif
-constexpr int kSgBatch = RAYS_SG_BATCH;   // segment-boundary slots wait until this many are due (or nothing else is)
+// kSgSlots (slots per warp, 32 < kSgSlots <= 64: lane l keeps the books of slots l and l + 32) and kSgWarps: ray_trace.cuh
+static_assert(kSgSlots > 32 && kSgSlots <= 64, "a lane keeps the kinds of two slots");
 
 enum SgKind : int { K_IDLE = 0, K_PRED, K_CORR, K_CHECK, K_START, K_BEGIN, K_FIN };
-enum SgBits : int { B_FIRST = 1, B_HAVE_F1 = 2, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
+enum SgBits : int { B_FIRST = 1, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
 
-// field-major slot memory of one CTA: double field f of slot j at D[f * kSgSlots + j]
+// field-major slot memory of one warp: double field f of slot j at D[f * kSgSlots + j]
 template <int NV> struct SgLayout {
     enum : int {
-        V = 0, YY = V + NV, WT = YY + NV, P = WT + NV, YP = P + NV, PHI = YP + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16
+        V = 0, YY = V + NV, WT = YY + NV, PHI = WT + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16
         ALPHA = PHI + 17 * NV, BETA = ALPHA + 13, SIG = BETA + 13, VV = SIG + 14, WW = VV + 13, G = WW + 14, PSI = G + 14,
         S_ = PSI + 13, SOUT, REL, ABS, RPREV, RLAST, RMAX, DEPX, DEPQ, PWR, EPS, ABSDEL, TEND, RELEPS, ABSEPS, T0, X, H, HOLD,
         ROUND, ABSH, XOLD, ERK, ERKM1, IRAY, NDBL
     };
-    enum : int { NSTEP = 0, FLAG, P0, SLICE, NS, K, KOLD, IFAIL, KNEW, NOSTEP, KLE4, BITS, F1CODE, FINNP, NINT = 16 };
+    enum : int { NSTEP = 0, FLAG, P0, SLICE, NS, K, KOLD, IFAIL, KNEW, NOSTEP, KLE4, BITS, FINNP, NINT = 14 };
 };
+// component loops are unrolled (independent loads in flight) for the specialised kernels, real loops for the generic one
+#ifndef RAYS_SG_UNROLL
+#define RAYS_SG_UNROLL 1
+#endif
+template <int NV> struct SgUnroll { static constexpr int L = (RAYS_SG_UNROLL && NV <= 13) ? NV : 1; };
 
 template <int NV> struct SgSlot {
     using L = SgLayout<NV>;
@@ -50,8 +54,6 @@ template <int NV> struct SgSlot {
     RD_INLINE double &v(int l) const { return f(L::V + l); }
     RD_INLINE double &yy(int l) const { return f(L::YY + l); }
     RD_INLINE double &wt(int l) const { return f(L::WT + l); }
-    RD_INLINE double &p(int l) const { return f(L::P + l); }
-    RD_INLINE double &yp(int l) const { return f(L::YP + l); }
     RD_INLINE double &phi(int i_, int l) const { return f(L::PHI + i_ * NV + l); }
     RD_INLINE double &alpha(int i_) const { return f(L::ALPHA + i_); }
     RD_INLINE double &beta(int i_) const { return f(L::BETA + i_); }
@@ -62,7 +64,10 @@ template <int NV> struct SgSlot {
     RD_INLINE double &psi(int i_) const { return f(L::PSI + i_); }
 };
 
-// ---- the pieces of `step` on slot memory: statement for statement the functions of ray_trace.cuh ---------------------------
+// ---- the pieces of `step` on slot memory: the statements of sg_block0 ... sg_intrp (ray_trace.cuh), with the loops over the
+// history index i outside and the loops over the components inside and unrolled (per component the operation order is the
+// reference's).  The predicted solution p and the derivative yp live in registers: both are produced and consumed within
+// one macro-step.
 // step, first block (ode_RAYS.f90:840-852); returns true on crash
 template <int NV> RD_INLINE bool sg2_block0(int neqn, const SgSlot<NV> &W, double &eps) {
     using L = SgLayout<NV>;
@@ -71,8 +76,8 @@ template <int NV> RD_INLINE bool sg2_block0(int neqn, const SgSlot<NV> &W, doubl
     if (fabs(h) < fouru * fabs(x)) { W.f(L::H) = copysign(fouru * fabs(x), h); return true; }
     const double p5eps = 0.5 * eps;
     double sum = 0.0;
-    #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) { const double q = sg_div(W.yy(l), W.wt(l)); sum = sum + q * q; }
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) { const double q = sg_div(W.yy(l), W.wt(l)); sum = sum + q * q; }
     const double round = twou * sg_sqrt(sum);
     W.f(L::ROUND) = round;
     if (p5eps < round) { eps = 2.0 * round * (1.0 + fouru); return true; }
@@ -81,16 +86,15 @@ template <int NV> RD_INLINE bool sg2_block0(int neqn, const SgSlot<NV> &W, doubl
     return false;
 }
 // step, start block after the first derivative evaluation (:858-885)
-template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, double eps, int &bits) {
+template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
     using L = SgLayout<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
     const double p5eps = 0.5 * eps;
     double tot = 0.0;
-    #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) {
-        const double ypl = W.yp(l);
-        W.phi(1, l) = ypl; W.phi(2, l) = 0.0;
-        const double q = sg_div(ypl, W.wt(l)); tot = tot + q * q;
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) {
+        W.phi(1, l) = yp[l]; W.phi(2, l) = 0.0;
+        const double q = sg_div(yp[l], W.wt(l)); tot = tot + q * q;
     }
     const double total = sg_sqrt(tot);
     const double h = W.f(L::H);
@@ -102,12 +106,12 @@ template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, 
     bits = (bits & ~B_START) | B_PHASE1 | B_NORND;
     if (p5eps <= 100.0 * W.f(L::ROUND)) {
         bits &= ~B_NORND;
-        #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) W.phi(15, l) = 0.0;
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) W.phi(15, l) = 0.0;
     }
 }
 // step, blocks 1 and 2 (:896-1015): coefficients for this step size/order, then the predicted solution p at x + h
-template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int bits) {
+template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int bits, double (&p)[NV]) {
     using L = SgLayout<NV>;
     const int k = W.i(L::K), kold = W.i(L::KOLD);
     int ns = W.i(L::NS);
@@ -161,29 +165,37 @@ template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int 
     #pragma unroll 1
     for (int i = nsp1; i <= k; ++i) {
         const double b = W.beta(i);
-        #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) W.phi(i, l) = b * W.phi(i, l);
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) W.phi(i, l) = b * W.phi(i, l);
     }
-    const bool nornd = (bits & B_NORND) != 0;
-    #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) {   // component by component: same operation order per component as the reference's i-outer loops
+    double up[NV];
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) {
         W.phi(kp2, l) = W.phi(kp1, l);
         W.phi(kp1, l) = 0.0;
-        double pl = 0.0, up = 0.0;
-        #pragma unroll 1
-        for (int i = k; i >= 1; --i) {
+        p[l] = 0.0; up[l] = 0.0;
+    }
+    #pragma unroll 1
+    for (int i = k; i >= 1; --i) {
+        const double gi = W.g(i);
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) {
             const double f = W.phi(i, l);
-            pl = pl + f * W.g(i);
-            up = f + up;
-            W.phi(i, l) = up;
+            p[l] = p[l] + f * gi;
+            up[l] = f + up[l];
+            W.phi(i, l) = up[l];
         }
+    }
+    const bool nornd = (bits & B_NORND) != 0;
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) {
         const double y = W.yy(l);
         if (!nornd) {
-            const double tau = h * pl - W.phi(15, l);
+            const double tau = h * p[l] - W.phi(15, l);
             const double pp = y + tau;
-            W.p(l) = pp;
+            p[l] = pp;
             W.phi(16, l) = (pp - y) - tau;
-        } else W.p(l) = y + h * pl;
+        } else p[l] = y + h * p[l];
     }
     const double x = W.f(L::X);
     W.f(L::XOLD) = x;
@@ -192,19 +204,21 @@ template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int 
 }
 // step, after the derivative at the predicted point (:1022-1110): error estimates, accept or fail.
 // returns 0 = accepted (corrected solution formed in yy), 1 = failed: retry with the reduced step, 2 = crash (eps doubled)
-template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W, double &eps, int &bits) {
+template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W, double &eps, int &bits, const double (&p)[NV], const double (&yp)[NV]) {
     using L = SgLayout<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
     const int k = W.i(L::K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
     const double absh = W.f(L::ABSH), p5eps = 0.5 * eps;
     double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
-    #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) {
+    double dl[NV];   // yp - phi(1)
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) {
         const Rcp wl = rcp_of(W.wt(l));   // up to three quotients by the same weight
-        const double ypl = W.yp(l), ph1 = W.phi(1, l);
-        if (0 < km2) { const double q = sg_quot(W.phi(km1, l) + ypl - ph1, wl); erkm2 = erkm2 + q * q; }
-        if (0 <= km2) { const double q = sg_quot(W.phi(k, l) + ypl - ph1, wl); erkm1 = erkm1 + q * q; }
-        const double q = sg_quot(ypl - ph1, wl);
+        const double ph1 = W.phi(1, l);
+        if (0 < km2) { const double q = sg_quot(W.phi(km1, l) + yp[l] - ph1, wl); erkm2 = erkm2 + q * q; }
+        if (0 <= km2) { const double q = sg_quot(W.phi(k, l) + yp[l] - ph1, wl); erkm1 = erkm1 + q * q; }
+        dl[l] = yp[l] - ph1;
+        const double q = sg_quot(dl[l], wl);
         erk = erk + q * q;
     }
     if (0 < km2) erkm2 = absh * W.sig(km1) * kSGgstr[km2] * sg_sqrt(erkm2);
@@ -225,15 +239,14 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
         W.i(L::KOLD) = k;
         W.f(L::HOLD) = h;
         const bool nornd = (bits & B_NORND) != 0;
-        #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) {
-            const double pl = W.p(l), dl = W.yp(l) - W.phi(1, l);
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) {
             if (!nornd) {
-                const double rho = h * gkp1 * dl - W.phi(16, l);
-                const double y = pl + rho;
+                const double rho = h * gkp1 * dl[l] - W.phi(16, l);
+                const double y = p[l] + rho;
                 W.yy(l) = y;
-                W.phi(15, l) = (y - pl) - rho;
-            } else W.yy(l) = pl + h * gkp1 * dl;
+                W.phi(15, l) = (y - p[l]) - rho;
+            } else W.yy(l) = p[l] + h * gkp1 * dl[l];
         }
         return 0;
     }
@@ -241,11 +254,20 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
     bits &= ~B_PHASE1;
     const double x = W.f(L::XOLD);
     W.f(L::X) = x;
+    double nxt[NV];   // phi(i+1) as it was: row i+1 is restored after row i reads it, so read the rows top-down once
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) nxt[l] = W.phi(kp1, l);
+    // the reference restores i = 1..k in ascending order, each row from the NOT YET restored row above it: identical to
+    // walking down from i = k with the original value of row i + 1 carried along
     #pragma unroll 1
-    for (int i = 1; i <= k; ++i) {
+    for (int i = k; i >= 1; --i) {
         const Rcp bi = rcp_of(W.beta(i));
-        #pragma unroll 1
-        for (int l = 0; l < neqn; ++l) W.phi(i, l) = sg_quot(W.phi(i, l) - W.phi(i + 1, l), bi);
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) {
+            const double cur = W.phi(i, l);
+            W.phi(i, l) = sg_quot(cur - nxt[l], bi);
+            nxt[l] = cur;
+        }
     }
     #pragma unroll 1
     for (int i = 2; i <= k; ++i) W.psi(i - 1) = W.psi(i) - h;
@@ -265,7 +287,7 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
     return 1;
 }
 // step, after the derivative at the corrected point (:1147-1231): update differences, choose order and step
-template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W, double eps, int &bits) {
+template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
     using L = SgLayout<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
     int k = W.i(L::K);
@@ -276,15 +298,19 @@ template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W
     const bool phase1 = (bits & B_PHASE1) != 0;
     const bool want_erkp1 = !phase1 && knew != km1 && kp1 <= ns;
     double erkp1 = 0.0;
-    #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) {
-        const double d = W.yp(l) - W.phi(1, l);
-        W.phi(kp1, l) = d;
-        const double e2 = d - W.phi(kp2, l);
+    double d[NV];
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) {
+        d[l] = yp[l] - W.phi(1, l);
+        W.phi(kp1, l) = d[l];
+        const double e2 = d[l] - W.phi(kp2, l);
         W.phi(kp2, l) = e2;
-        #pragma unroll 1
-        for (int i = 1; i <= k; ++i) W.phi(i, l) = W.phi(i, l) + d;
         if (want_erkp1) { const double q = sg_div(e2, W.wt(l)); erkp1 = erkp1 + q * q; }
+    }
+    #pragma unroll 1
+    for (int i = 1; i <= k; ++i) {
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) W.phi(i, l) = W.phi(i, l) + d[l];
     }
     if (phase1) {
         k = kp1; erk = 0.0;
@@ -334,16 +360,29 @@ template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double
         W.g(j) = W.ww(1);
         term = psijm1;
     }
+    double yo[NV];
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) yo[l] = 0.0;
     #pragma unroll 1
-    for (int l = 0; l < neqn; ++l) {
-        double yo = 0.0;
-        #pragma unroll 1
-        for (int j = 1; j <= ki; ++j) { const int i = ki + 1 - j; yo = yo + W.g(i) * W.phi(i, l); }
-        W.v(l) = W.yy(l) + hi * yo;
+    for (int j = 1; j <= ki; ++j) {
+        const int i = ki + 1 - j;
+        const double gi = W.g(i);
+        #pragma unroll (SgUnroll<NV>::L)
+        for (int l = 0; l < NV; ++l) if (l < neqn) yo[l] = yo[l] + gi * W.phi(i, l);
     }
+    #pragma unroll (SgUnroll<NV>::L)
+    for (int l = 0; l < NV; ++l) if (l < neqn) W.v(l) = W.yy(l) + hi * yo[l];
 }
 
-template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
+// streaming copy-out of one finished ray by the whole warp: out of line, it runs once per ray
+static RD_NOINLINE void sg2_flush_row(const TraceArgs &a, long long ir, int np, int pf, size_t rw, int nv, unsigned lane) {
+    if (a.host_ray_vec)
+        copy_row_to_host(a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv, a.ray_vec + rw * a.npoints_alloc * nv, np * nv, lane);
+    if (a.host_residual)
+        copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
+}
+
+template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgWarps * kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------------
 #ifndef RAYS_SG2_MIN_CTAS
@@ -354,157 +393,149 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     constexpr int S = kSgSlots;
-    constexpr int NW = kTraceBlock / 32;
     using L = SgLayout<NV>;
     const int nv = T::nv();
     const rays_cfg &c = g_dc.c;
-    const int tid = threadIdx.x;
-    const unsigned lane = tid & 31;
-    const int warp = tid >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int maxnum = 500;
     const double fouru = 4.0 * DBL_EPSILON;
-    __shared__ int s_kind[S];
-    __shared__ int s_list[S];
-    __shared__ int s_wcnt[NW][4];
-    __shared__ unsigned long long s_base;
-    __shared__ int s_exhausted;
-    double *const D = a.sg_state + (size_t)blockIdx.x * L::NDBL * S;
-    int *const I = reinterpret_cast<int *>(a.sg_state + (size_t)gridDim.x * L::NDBL * S) + (size_t)blockIdx.x * L::NINT * S;
+    __shared__ int s_kind_all[kSgWarps][S];
+    int *const s_kind = s_kind_all[warp];
+    const size_t gwarp = (size_t)blockIdx.x * kSgWarps + warp;                 // this warp's slot group
+    const size_t nwarps = (size_t)gridDim.x * kSgWarps;
+    double *const D = a.sg_state + gwarp * L::NDBL * S;
+    int *const I = reinterpret_cast<int *>(a.sg_state + nwarps * L::NDBL * S) + gwarp * L::NINT * S;
     const bool binning = a.dep_acc != nullptr && T::damp();
     const DepBins dbins = dep_begin(a, binning);
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
+    const bool own1 = (int)lane + 32 < S;      // this lane also keeps the books of slot lane + 32
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
-    s_kind[tid] = K_IDLE;
-    if (tid == 0) s_exhausted = 0;
-    __syncthreads();
+    unsigned iter = 0;
+    bool exhausted = false;
+    s_kind[lane] = K_IDLE;
+    if (own1) s_kind[lane + 32] = K_IDLE;
+    __syncwarp();
 
-    for (;;) {
-        // ---- 1. rays that ended in the last iteration: streaming copy-out by the warp that holds the slot, slot becomes idle
-        if (__syncthreads_or(s_kind[tid] == K_FIN)) {
-            if (streaming) {
-                unsigned m = __ballot_sync(0xffffffffu, s_kind[tid] == K_FIN);
-                while (m) {
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int sl = warp * 32 + l;
-                    const SgSlot<NV> F{D + sl, I + sl};
-                    const long long ir = (long long)F.f(L::IRAY);
-                    const int np = F.i(L::FINNP), pf = F.i(L::P0);
-                    const size_t rw = (size_t)blockIdx.x * S + sl;
-                    if (a.host_ray_vec)
-                        copy_row_to_host(a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv,
-                                         a.ray_vec + rw * a.npoints_alloc * nv, np * nv, lane);
-                    if (a.host_residual)
-                        copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
-                }
-            }
-            if (s_kind[tid] == K_FIN) s_kind[tid] = K_IDLE;
-        }
-        // ---- 2. refill idle slots from the work queue: one atomic per CTA
+    for (;; ++iter) {
+        int k0 = s_kind[lane], k1 = own1 ? s_kind[lane + 32] : -1;
+        // ---- 1. rays that ended: streaming copy-out by the whole warp, the slot becomes idle
         {
-            const bool want = s_kind[tid] == K_IDLE && !s_exhausted;
-            const unsigned wb = __ballot_sync(0xffffffffu, want);
-            if (lane == 0) s_wcnt[warp][0] = __popc(wb);
-            __syncthreads();
-            int total = 0, before = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { const int cw = s_wcnt[w][0]; if (w < warp) before += cw; total += cw; }
-            if (total > 0) {
-                if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
-                __syncthreads();
-                if (want) {
-                    const long long idx = (long long)(s_base + (unsigned long long)(before + __popc(wb & ((1u << lane) - 1u))));
-                    if (idx >= a.nray) s_exhausted = 1;
-                    else {
-                        const SgSlot<NV> W{D + tid, I + tid};
-                        const long long iray = a.order ? (long long)a.order[idx] : idx;
-                        const size_t row = streaming ? (size_t)blockIdx.x * S + tid : (size_t)iray;
-                        W.f(L::IRAY) = (double)iray;
-                        W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
-                        W.i(L::SLICE) = 0;
-                        double v[NV];
-                        if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
-                            RayCarry k;
-                            resume_ray(a, iray, v, nv, k);
-                            W.f(L::S_) = k.s; W.f(L::SOUT) = k.sout; W.i(L::NSTEP) = k.nstep; W.i(L::FLAG) = k.flag;
-                            W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
-                            W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
-                            W.i(L::P0) = streaming ? k.nstep + 1 : 0;
-                            W.i(L::BITS) = 0;
-                        } else {
-                            W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
-                            W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
-                            W.f(L::RPREV) = 0.0; W.f(L::RLAST) = 0.0; W.f(L::RMAX) = 0.0; W.f(L::DEPX) = 0.0; W.f(L::DEPQ) = 0.0;
-                            initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
-                            if (a.ray_vec) {
-                                double *dst = a.ray_vec + row * a.npoints_alloc * nv;
-                                if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
-                            }
-                            if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
-                            if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                            W.i(L::BITS) = B_FIRST;
+            const unsigned f0 = __ballot_sync(0xffffffffu, k0 == K_FIN), f1 = __ballot_sync(0xffffffffu, k1 == K_FIN);
+            if (f0 | f1) {
+                if (streaming) {
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned m = half ? f1 : f0;
+                        while (m) {
+                            const int sl = __ffs(m) - 1 + 32 * half;
+                            m &= m - 1;
+                            const SgSlot<NV> F{D + sl, I + sl};
+                            const long long ir = (long long)F.f(L::IRAY);
+                            const int np = F.i(L::FINNP), pf = F.i(L::P0);
+                            sg2_flush_row(a, ir, np, pf, gwarp * S + sl, nv, lane);
                         }
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
-                        s_kind[tid] = K_CHECK;
                     }
                 }
+                if (k0 == K_FIN) k0 = K_IDLE;
+                if (k1 == K_FIN) k1 = K_IDLE;
             }
         }
-        // ---- 3. sort the slots by what they need next; segment-boundary slots wait for a batch
+        // ---- 2. refill idle slots from the work queue: one atomic per warp
+        if (!exhausted) {
+            const unsigned w0 = __ballot_sync(0xffffffffu, k0 == K_IDLE), w1 = __ballot_sync(0xffffffffu, k1 == K_IDLE);
+            const int total = __popc(w0) + __popc(w1);
+            if (total > 0) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int half = 0; half < 2; ++half) {
+                    const bool want = half ? (k1 == K_IDLE) : (k0 == K_IDLE);
+                    const unsigned wb = half ? w1 : w0;
+                    if (want) {
+                        const long long idx = (long long)(base + (unsigned long long)((half ? __popc(w0) : 0) + __popc(wb & ((1u << lane) - 1u))));
+                        if (idx < a.nray) {
+                            const int sl = (int)lane + 32 * half;
+                            const SgSlot<NV> W{D + sl, I + sl};
+                            const long long iray = a.order ? (long long)a.order[idx] : idx;
+                            const size_t row = streaming ? gwarp * S + sl : (size_t)iray;
+                            W.f(L::IRAY) = (double)iray;
+                            W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
+                            W.i(L::SLICE) = 0;
+                            double v[NV];
+                            if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
+                                RayCarry k;
+                                resume_ray(a, iray, v, nv, k);
+                                W.f(L::S_) = k.s; W.f(L::SOUT) = k.sout; W.i(L::NSTEP) = k.nstep; W.i(L::FLAG) = k.flag;
+                                W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
+                                W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
+                                W.i(L::P0) = streaming ? k.nstep + 1 : 0;
+                                W.i(L::BITS) = 0;
+                            } else {
+                                W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
+                                W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
+                                W.f(L::RPREV) = 0.0; W.f(L::RLAST) = 0.0; W.f(L::RMAX) = 0.0; W.f(L::DEPX) = 0.0; W.f(L::DEPQ) = 0.0;
+                                initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                                if (a.ray_vec) {
+                                    double *dst = a.ray_vec + row * a.npoints_alloc * nv;
+                                    if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
+                                }
+                                if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
+                                if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                                W.i(L::BITS) = B_FIRST;
+                            }
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
+                            if (half) k1 = K_CHECK; else k0 = K_CHECK;
+                        }
+                    }
+                }
+                if (base + (unsigned long long)total >= (unsigned long long)a.nray) exhausted = true;
+            }
+        }
+        // ---- 3. what do the slots of this warp need next?  Take the kind most of them wait for (restarts after a tolerance
+        // raise are rare and get their turn every 16th iteration), lane j takes the j-th slot of that kind
         int slot = -1;
         {
-            const int kd = s_kind[tid];
-            const int key = kd == K_PRED ? 0 : (kd == K_CORR ? 1 : (kd == K_CHECK ? 2 : ((kd == K_START || kd == K_BEGIN) ? 3 : -1)));
-            unsigned bal[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) bal[q] = __ballot_sync(0xffffffffu, key == q);
-            __syncthreads();   // everybody has read s_wcnt / s_base of step 2
-            if (lane < 4) s_wcnt[warp][lane] = __popc(bal[lane]);
-            __syncthreads();
-            int tot[4], bef[4];
+            unsigned b0[4], b1[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                tot[q] = 0; bef[q] = 0;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) { const int cw = s_wcnt[w][q]; if (w < warp) bef[q] += cw; tot[q] += cw; }
+                const int kq = q == 0 ? K_PRED : (q == 1 ? K_CORR : (q == 2 ? K_CHECK : K_START));
+                b0[q] = __ballot_sync(0xffffffffu, k0 == kq || (q == 3 && k0 == K_BEGIN));
+                b1[q] = __ballot_sync(0xffffffffu, k1 == kq || (q == 3 && k1 == K_BEGIN));
             }
-            const int n_other = tot[0] + tot[1] + tot[3];
-            const bool take_check = tot[2] >= kSgBatch || n_other < S / 4;
-            const int n_check = take_check ? tot[2] : 0;
-            const int n_all = n_other + n_check;
-            if (n_all == 0) {
-                if (tot[2] == 0 && s_exhausted) break;    // every slot idle, queue empty
-                __syncthreads();
-                continue;
-            }
-            if (key >= 0 && (key != 2 || take_check)) {
-                int base = 0;
-                if (key >= 1) base += tot[0];
-                if (key >= 2) base += tot[1];
-                if (key >= 3) base += n_check;
-                const unsigned mine = key == 0 ? bal[0] : (key == 1 ? bal[1] : (key == 2 ? bal[2] : bal[3]));
-                const int befk = key == 0 ? bef[0] : (key == 1 ? bef[1] : (key == 2 ? bef[2] : bef[3]));
-                s_list[base + befk + __popc(mine & ((1u << lane) - 1u))] = tid;
-            }
-            __syncthreads();
-            if (tid < n_all) slot = s_list[tid];
+            const int cP = __popc(b0[0]) + __popc(b1[0]), cC = __popc(b0[1]) + __popc(b1[1]), cK = __popc(b0[2]) + __popc(b1[2]), cR = __popc(b0[3]) + __popc(b1[3]);
+            if (cP + cC + cK + cR == 0 && exhausted) break;     // every slot idle, queue empty
+            int q = 0, best = cP;
+            if (cC > best) { q = 1; best = cC; }
+            if (cK > best) { q = 2; best = cK; }
+            if (cR > 0 && (best == 0 || (iter & 15u) == 0u)) q = 3;
+            const unsigned m0 = q == 0 ? b0[0] : (q == 1 ? b0[1] : (q == 2 ? b0[2] : b0[3]));
+            const unsigned m1 = q == 0 ? b1[0] : (q == 1 ? b1[1] : (q == 2 ? b1[2] : b1[3]));
+            const int n0 = __popc(m0);
+            if ((int)lane < n0) slot = (int)__fns(m0, 0, (int)lane + 1);
+            else if ((int)lane - n0 < __popc(m1)) slot = 32 + (int)__fns(m1, 0, (int)lane - n0 + 1);
         }
         // ---- 4. one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
+        int next = -1;
+        const int ka = __shfl_sync(0xffffffffu, k0, slot & 31), kb = __shfl_sync(0xffffffffu, k1, slot & 31);   // kinds are kept by lane slot % 32
         if (slot >= 0) {
             const SgSlot<NV> W{D + slot, I + slot};
-            const int kind = s_kind[slot];
+            const int kind = slot < 32 ? ka : kb;
             int bits = W.i(L::BITS);
-            int next = kind;
+            next = kind;
             int req = 0;   // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
                            // 4: check_save of the new point v + the start derivative of the next segment there
-            bool stop = false, did_not_start = false, crashed = false, enter = false, de_top = false, suspended = false;
+            bool stop = false, did_not_start = false, crashed = false, enter = false, de_top = false, have_f1 = false;
+            int f1_code = 0;
             int flag = W.i(L::FLAG);
             double eps = W.f(L::EPS);
             const long long iray = (long long)W.f(L::IRAY);
-            const size_t row = streaming ? (size_t)blockIdx.x * S + slot : (size_t)iray;
-            if (kind == K_PRED) { sg2_predict<NV>(nv, W, bits); req = 2; }
+            const size_t row = streaming ? gwarp * S + slot : (size_t)iray;
+            double uu[NV], ff[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { uu[i] = 0.0; ff[i] = 0.0; }
+            if (kind == K_PRED) { sg2_predict<NV>(nv, W, bits, uu); req = 2; }
             else if (kind == K_CORR) req = 3;
             else if (kind == K_START) req = 1;
             else if (kind == K_BEGIN) enter = true;
@@ -517,7 +548,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                     W.f(L::S_) = sout;
                     const int sn = W.i(L::SLICE) + 1;
                     W.i(L::SLICE) = sn;
-                    if (a.slice_steps > 0 && sn >= a.slice_steps) {   // suspend: packed into full CTAs by the next launch
+                    if (a.slice_steps > 0 && sn >= a.slice_steps) {   // suspend: packed into full warps by the next launch
                         double v[NV];
 #pragma unroll
                         for (int i = 0; i < NV; ++i) v[i] = i < nv ? W.v(i) : 0.0;
@@ -525,7 +556,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                         RayCarry k{sout, sout, W.f(L::RPREV), W.f(L::RLAST), W.f(L::RMAX), W.f(L::DEPX), W.f(L::DEPQ), W.f(L::REL), W.f(L::ABS), nstep, flag};
                         suspend_ray(a, iray, v, nv, k);
                         W.i(L::FINNP) = nstep + 1 - W.i(L::P0);
-                        suspended = true; req = 0; next = K_FIN;
+                        req = 0; next = K_FIN;
                     }
                 }
             }
@@ -533,10 +564,11 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
             // (the reference evaluates it twice at this point: check_save.f90:38 and eqn_ray.f90:87 of the next segment's
             // first derivative), saves the point and runs the loop-top tests of ray_tracing.f90:118-172
             if (req) {
-                double uu[NV], ff[NV];
-                const int ufield = req == 2 ? L::P : (req == 4 ? L::V : L::YY);
+                if (req != 2) {
+                    const int ufield = req == 4 ? L::V : L::YY;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) { uu[i] = i < nv ? W.f(ufield + i) : 0.0; ff[i] = 0.0; }
+                    for (int i = 0; i < NV; ++i) if (i < nv) uu[i] = W.f(ufield + i);
+                }
                 Eq<NSM> e;
                 equilibrium<T::EQ, T::NS, true>(uu[0], uu[1], uu[2], e);
                 double dddx[3], dddk[3], dddw = 0.0;
@@ -598,25 +630,20 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                     int code = e.err;
                     if (!code && !have_derivs) code = ray_derivs<T>(e, uu, dddx, dddk, dddw);
                     if (!code) code = ray_equations<T>(e, uu, dddx, dddk, dddw, ff);
-                    if (!code) {
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
-                    }
-                    if (req == 4) {          // kept for the start of the next segment (consumed after de's entry tests)
-                        bits |= B_HAVE_F1;
-                        W.i(L::F1CODE) = code;
+                    if (req == 4) {          // the start derivative of the next segment (consumed after de's entry tests, below)
+                        have_f1 = true; f1_code = code;
                         enter = true;
                     } else {
                         my_rhs += 1;
                         if (code) { flag = code; W.f(L::SOUT) = W.f(L::S_); stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
-                        else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits); next = K_PRED; }
+                        else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits, ff); next = K_PRED; }
                         else if (req == 2) {
-                            const int r = sg2_after_predict<NV>(nv, W, eps, bits);
+                            const int r = sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
                             if (r == 0) next = K_CORR;
                             else if (r == 1) next = K_PRED;   // failed: predict again with the reduced step
                             else crashed = true;
                         } else {
-                            sg2_after_correct<NV>(nv, W, eps, bits);
+                            sg2_after_correct<NV>(nv, W, eps, bits, ff);
                             const int nostep = W.i(L::NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
                             W.i(L::NOSTEP) = nostep;
                             int kle4 = W.i(L::KLE4) + 1;
@@ -643,7 +670,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                         W.i(L::NOSTEP) = 0; W.i(L::KLE4) = 0;
                         W.f(L::RELEPS) = rel_err / eps;
                         W.f(L::ABSEPS) = abs_err / eps;
-                        bits = (bits & (B_HAVE_F1 | B_FIRST)) | B_START | B_NORND;
+                        bits = (bits & B_FIRST) | B_START | B_NORND;
                         W.f(L::X) = s;
 #pragma unroll
                         for (int l = 0; l < NV; ++l) if (l < nv) W.yy(l) = W.v(l);
@@ -655,7 +682,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
             }
             if (de_top && !stop) {   // top of de's loop (ode_RAYS.f90:509-562)
                 const double x = W.f(L::X);
-                if (W.f(L::ABSDEL) <= fabs(x - W.f(L::T0))) {   // past the output point: the segment ends (interpolation is batched)
+                if (W.f(L::ABSDEL) <= fabs(x - W.f(L::T0))) {   // past the output point: the segment ends (the interpolation waits for its batch)
                     bits |= B_INTRP;
                     next = K_CHECK;
                 } else if (maxnum <= W.i(L::NOSTEP)) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
@@ -668,16 +695,14 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                     const double h = W.f(L::H);
                     W.f(L::H) = copysign(fmin(fabs(h), fabs(W.f(L::TEND) - x)), h);
                     const double releps = W.f(L::RELEPS), abseps = W.f(L::ABSEPS);
-#pragma unroll 1
-                    for (int l = 0; l < nv; ++l) W.wt(l) = releps * fabs(W.yy(l)) + abseps;
-                    if (sg2_block0<NV>(nv, W, eps)) crashed = true;
+#pragma unroll (SgUnroll<NV>::L)
+                    for (int l = 0; l < NV; ++l) if (l < nv) W.wt(l) = releps * fabs(W.yy(l)) + abseps;
+                    if (sg2_block0<NV>(nv, W, eps)) crashed = true;   // (a start derivative evaluated above is dropped: the restart evaluates it again)
                     else if (bits & B_START) {
-                        if (bits & B_HAVE_F1) {   // the start derivative was evaluated together with check_save at this very point
-                            bits &= ~B_HAVE_F1;
+                        if (have_f1) {   // the start derivative was evaluated together with check_save at this very point
                             my_rhs += 1;
-                            const int f1 = W.i(L::F1CODE);
-                            if (f1) { flag = f1; W.f(L::SOUT) = W.f(L::S_); stop = true; }
-                            else { sg2_after_start<NV>(nv, W, eps, bits); next = K_PRED; }
+                            if (f1_code) { flag = f1_code; W.f(L::SOUT) = W.f(L::S_); stop = true; }
+                            else { sg2_after_start<NV>(nv, W, eps, bits, ff); next = K_PRED; }
                         } else next = K_START;
                     } else next = K_PRED;
                 }
@@ -717,10 +742,14 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                 W.i(L::FINNP) = did_not_start ? 1 : nstep + 1 - W.i(L::P0);
                 next = K_FIN;
             }
-            (void)suspended;
-            s_kind[slot] = next;
         }
-        __syncthreads();
+        // ---- 5. books: the kinds the macro-steps left behind (and the refills of step 2) go back to the warp's table
+        __syncwarp();
+        s_kind[lane] = k0;
+        if (own1) s_kind[lane + 32] = k1;
+        __syncwarp();
+        if (slot >= 0) s_kind[slot] = next;
+        __syncwarp();
     }
     dep_end(a, binning);
     unsigned long long stt = my_steps, rh = my_rhs;

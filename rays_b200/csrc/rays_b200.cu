@@ -259,6 +259,16 @@ __global__ void fan_shard_kernel(long long n_out, int rank, int world, const dou
     for (int k = 0; k < 3; ++k) { rv_o[3 * j + k] = rv[3 * i + k]; nv_o[3 * j + k] = nv[3 * i + k]; }
     w_o[j] = w[i];
 }
+// per-ray summaries of the last trace as one row of 6 + 2 nv doubles per ray (the fixed-size record SURVEY.md 8e gathers
+// across GPUs): npoints, stop code, initial_ray_power, end_residuals, max_residuals, end_ray_parameter, start_ray_vec, end_ray_vec
+__global__ void pack_summaries_kernel(long long nray, int nv, const int *npoints, const int *stop, const double *pwr, const double *endres,
+                                      const double *maxres, const double *endpar, const double *startv, const double *endv, double *out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nray) return;
+    double *o = out + (size_t)i * (6 + 2 * nv);
+    o[0] = (double)npoints[i]; o[1] = (double)stop[i]; o[2] = pwr[i]; o[3] = endres[i]; o[4] = maxres[i]; o[5] = endpar[i];
+    for (int k = 0; k < nv; ++k) { o[6 + k] = startv[(size_t)i * nv + k]; o[6 + nv + k] = endv[(size_t)i * nv + k]; }
+}
 // calculate_deposition_profiles on stored trajectories (deposition_profiles_m.f90:228-292): one thread per ray
 template <int EQ_> __global__ void deposition_kernel(long long nray, int nv, int npa, const double *ray_vec, const int *npoints,
                                                       const double *pwr, const DepBins bins) {
@@ -461,10 +471,11 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
         CK(g.sg_state.reserve(((size_t)g.num_sms * bps * g.cached_sgb + 7) / 8));
         a.sg_state = g.sg_state.p;
     }
-    long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;
+    long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;   // (an SG CTA holds twice that many rays; a small fan still spreads over the SMs)
     int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
-    if (host) {   // streaming copy-out: per-lane staging rows, finished rays go straight to the caller's arrays
-        const size_t lanes = (size_t)grid * kTraceBlock;
+    const int rays_per_cta = g.cached_sgb ? kSgWarps * kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: 64 slots per warp)
+    if (host) {   // streaming copy-out: per-lane (per-slot) staging rows, finished rays go straight to the caller's arrays
+        const size_t lanes = (size_t)grid * rays_per_cta;
         if (host->ray_vec) { CK(g.ray_vec.reserve(lanes * g.res_npa * g.res_nv)); a.ray_vec = g.ray_vec.p; a.host_ray_vec = host->ray_vec; }
         if (host->residual) { CK(g.residual.reserve(lanes * g.res_npa)); a.residual = g.residual.p; a.host_residual = host->residual; }
         a.host_npoints_alloc = host->npa;
@@ -472,7 +483,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     }
     // Time slicing (see TraceArgs): rays are suspended after `slice` steps and the survivors are re-launched packed
     // into full warps, until they fit one per lane.  RAYS_B200_SLICE=0 disables it, =n forces n steps.
-    const long long lanes = (long long)g.num_sms * bps * kTraceBlock;
+    const long long lanes = (long long)g.num_sms * bps * rays_per_cta;
     int slice = 0;
     if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
     bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
@@ -1251,6 +1262,22 @@ int rays_b200_deposition_set_total_weight(double total_weight) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!(total_weight >= 0.0)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: total weight must be >= 0");
     g.fan_weight = total_weight;
+    return 0;
+}
+
+int rays_b200_summaries_pack(void *d_out, int64_t rows_capacity, int64_t *rows, int32_t *row_doubles) {
+    if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
+    if (rows) *rows = g.res_nray;
+    if (row_doubles) *row_doubles = 6 + 2 * g.res_nv;
+    if (!d_out) return 0;
+    if (rows_capacity < g.res_nray) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_summaries_pack: output smaller than the last trace");
+    CK(cudaSetDevice(g.device));
+    if (g.res_nray > 0) {
+        pack_summaries_kernel<<<(unsigned)((g.res_nray + 255) / 256), 256, 0, g.stream>>>(g.res_nray, g.res_nv, g.npoints.p, g.stop.p, g.pwr.p, g.endres.p, g.maxres.p,
+                                                                                             g.endpar.p, g.startv.p, g.endv.p, (double *)d_out);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(g.stream));
     return 0;
 }
 

@@ -355,3 +355,99 @@ def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, regi
                     SG_error_limit=0.1)
     g, o = _run_both(cfg, r[:96], n[:96], w[:96])
     _compare_traces(g, o, cfg, 1e-6, bitwise=False)
+
+
+# ---- parity at scale (VERDICT r1, next #1b): >= 64k-ray slices of the bench fans ---------------------------------------------
+def test_config4_slice_65k_rays_bitwise():
+    """every 16th ray of the 1 048 576-ray bench fan (RK4, deriv_num, nstep_max = 1000): 65 536 rays, bitwise against the oracle"""
+    cfg = init_case("solovev_fan_1M.in")
+    r, n, w, _, _ = oracle_fan(cfg, cap=1 << 21)
+    assert r.shape[0] == 1048576
+    idx = np.arange(0, r.shape[0], 16)
+    g = rb.trace(cfg, r[idx], n[idx], w[idx])
+    o, st, _ = orc.trace(cfg, r[idx], n[idx], w[idx], nthreads=0)
+    assert st == 0
+    assert np.array_equal(g.npoints, o.npoints) and np.array_equal(g.ray_stop_code, o.ray_stop_code)
+    assert np.array_equal(g.ray_vec, o.ray_vec, equal_nan=True)
+    assert np.array_equal(g.residual, o.residual, equal_nan=True)
+    assert np.array_equal(g.end_ray_vec, o.end_ray_vec, equal_nan=True)
+
+
+def test_sg_slot_machine_equals_the_per_lane_kernel_and_the_oracle(monkeypatch):
+    """16 384 rays of the bench fan with Shampine-Gordon: the slot-machine kernel, the round-1 per-lane kernel and the oracle take the
+    same steps to the same stop reasons; the two device kernels run the same arithmetic and agree bitwise"""
+    cfg = init_case("solovev_fan_1M.in", ode_solver_name="SG_ODE", ray_deriv_name="cold", rel_err0=1e-6, abs_err0=1e-6, SG_error_limit=0.1)
+    r, n, w, _, _ = oracle_fan(cfg, cap=1 << 21)
+    idx = np.arange(0, r.shape[0], 64)
+    g = rb.trace(cfg, r[idx], n[idx], w[idx])
+    assert "trace" in rb.last_trace_stats()["kernel"]
+    monkeypatch.setenv("RAYS_B200_SG_LANES", "1")
+    g1 = rb.trace(cfg, r[idx], n[idx], w[idx])
+    monkeypatch.delenv("RAYS_B200_SG_LANES")
+    rb.set_config(cfg)
+    assert np.array_equal(g.npoints, g1.npoints) and np.array_equal(g.ray_stop_code, g1.ray_stop_code)
+    assert np.array_equal(g.ray_vec, g1.ray_vec, equal_nan=True) and np.array_equal(g.residual, g1.residual, equal_nan=True)
+    o, st, nrhs = orc.trace(cfg, r[idx], n[idx], w[idx], nthreads=0)
+    assert np.array_equal(g.npoints, o.npoints), np.nonzero(g.npoints != o.npoints)[0][:10]
+    assert np.array_equal(g.ray_stop_code, o.ray_stop_code)
+    g = rb.trace(cfg, r[idx], n[idx], w[idx])
+    assert rb.last_trace_stats()["rhs_evals"] == nrhs, "the slot machine evaluates exactly the right-hand sides the reference does"
+    fin = np.isfinite(o.end_ray_vec).all(axis=1)
+    assert np.max(np.abs(g.end_ray_vec[fin, :3] - o.end_ray_vec[fin, :3])) <= 1e-6
+
+
+def test_config5_sharded_profile_is_bitwise_independent_of_the_sharding():
+    """a 65 536-ray slice of the config-5 deposition fan: the fixed-point profile summed over 1, 2, 3 and 8 interleaved shards is the
+    same int64 vector, and it equals the oracle's ray-ordered double sum to 1e-12 of the largest bin"""
+    cfg = init_case("axisym_deposition_fan.in", nstep_max=400)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=256, delta_rindex_theta=0.4 / 255, n_rindex_phi=256, delta_rindex_phi=0.35 / 255, cap=70000)
+    assert r.shape[0] >= 60000
+    rb.set_config(cfg)
+    nb = 501
+    accs = {}
+    for world in (1, 2, 3, 8):
+        tot = np.zeros(nb, dtype=np.int64)
+        for rank in range(world):
+            rb.fan_upload(r, n, w)
+            rb.fan_shard(rank, world)
+            rb.trace_device(store=False, bins=(nb, 0.0, 1.0))
+            acc, unit, prof, q = rb.deposition_fixed(nb, 0.0, 1.0)
+            assert np.array_equal(prof, acc.astype(np.float64) * unit)
+            tot += acc
+        accs[world] = tot
+    for world in (2, 3, 8):
+        assert np.array_equal(accs[world], accs[1]), f"profile of {world} shards differs from the unsharded one"
+    # twice the same trace: the same bits (no order dependence inside one GPU either)
+    rb.fan_upload(r, n, w)
+    rb.trace_device(store=False, bins=(nb, 0.0, 1.0))
+    acc2, unit, _, _ = rb.deposition_fixed(nb, 0.0, 1.0)
+    assert np.array_equal(acc2, accs[1])
+    # against the oracle (doubles summed in ray order, deposition_profiles_m.f90:244-257) on a 4096-ray sub-slice
+    idx = np.arange(0, r.shape[0], 16)
+    o, st, _ = orc.trace(cfg, r[idx], n[idx], w[idx], nthreads=0)
+    po, qo = orc.deposition(cfg, o, nb, 0.0, 1.0)
+    rb.fan_upload(r[idx], n[idx], w[idx])
+    rb.deposition_set_total_weight(float(np.sum(np.abs(w))))   # the unit of the whole fan, as a host with pre-sharded fans would set it
+    rb.trace_device(store=False, bins=(nb, 0.0, 1.0))
+    pg, qg = rb.deposition(nb, 0.0, 1.0)
+    assert np.max(np.abs(pg - po)) <= 1e-10 * np.max(np.abs(po))   # exp() of the Z function is CUDA's: rounding level, not bitwise
+    assert abs(qg - qo) <= 1e-10 * abs(qo)
+
+
+def test_summaries_pack_matches_the_downloaded_summaries():
+    import torch
+    cfg = init_case("axisym_deposition_fan.in", nstep_max=200)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=16, delta_rindex_theta=0.025, n_rindex_phi=16, delta_rindex_phi=0.02)
+    rb.set_config(cfg)
+    rb.fan_upload(r, n, w)
+    rb.trace_device(store=False)
+    nv = int(cfg.nv)
+    rows, rd = rb.summaries_pack()
+    assert rows == r.shape[0] and rd == 6 + 2 * nv
+    t = torch.zeros((rows, rd), dtype=torch.float64, device="cuda")
+    rb.summaries_pack(t.data_ptr(), rows)
+    res = rb.results_download(rows, nv, int(cfg.nstep_max) + 1, store=False)
+    h = t.cpu().numpy()
+    assert np.array_equal(h[:, 0], res.npoints) and np.array_equal(h[:, 1], res.ray_stop_code)
+    assert np.array_equal(h[:, 2], res.initial_ray_power) and np.array_equal(h[:, 5], res.end_ray_parameter, equal_nan=True)
+    assert np.array_equal(h[:, 6:6 + nv], res.start_ray_vec, equal_nan=True) and np.array_equal(h[:, 6 + nv:], res.end_ray_vec, equal_nan=True)
