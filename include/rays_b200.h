@@ -321,6 +321,24 @@ int rays_b200_summaries_pack(void *d_out, int64_t rows_capacity, int64_t *rows, 
 /* Same, fused into the trace: bins while tracing, no trajectory storage needed. */
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories);
 
+/* ======================= one host process, several GPUs ============ */
+/* `program rays` is a single host process (RAYS_code/RAYS.f90:9-15) whose `call trace_rays` (ray_tracing.f90:62-64: one OpenMP
+ * loop over all rays) has no notion of ranks, so the library itself drives the GPUs of the box: rays_b200_init_multi creates one
+ * context + stream per GPU and an NCCL communicator over them (ncclCommInitAll; NCCL is dlopen'ed, a 1-GPU host needs none);
+ * ngpu <= 0 takes every visible GPU.  rays_b200_trace_multi is rays_b200_trace over all of them: GPU g integrates rays
+ * g, g + ngpu, ... (interleaved: ray length varies smoothly along the launch loops), no traffic during integration, results land
+ * in the caller's arrays in fan order.  rays_b200_trace_multi_binned traces without trajectory storage (res->ray_vec =
+ * res->residual = NULL), bins the deposition on every GPU while tracing and finishes with the two collectives of the north star:
+ * ONE ncclReduce (int64 sum, exact) of the n_bins fixed-point bins to GPU 0 -> dep->profile, dep->Q_sum, and ONE ncclAllGather of
+ * the packed per-ray summaries (rays_b200_summaries_pack rows), which rays_b200_multi_summaries exposes per GPU (device pointer:
+ * ngpu blocks of *rows_per_gpu rows, block g = rays g, g + ngpu, ...). */
+int rays_b200_init_multi(int ngpu);
+int rays_b200_ngpu(void);
+int rays_b200_trace_multi(const rays_cfg *cfg, const rays_fan *fan, rays_results *res);
+int rays_b200_trace_multi_binned(const rays_cfg *cfg, const rays_fan *fan, rays_results *res, rays_deposition *dep);
+const double *rays_b200_multi_summaries(int gpu, int64_t *rows_per_gpu, int32_t *row_doubles);
+int rays_b200_finalize_multi(void);
+
 /* ======================= O-X mode conversion analysis (row f4) ============================ */
 /* One record per ray: type OX_conv + the per-ray outcome flags of analyze_OX_conv
  * (post_process_lib/OX_conv_analysis_m.f90:32-47, 91-198). */

@@ -217,6 +217,35 @@ def trace(cfg: Cfg | None, rvec0, rindex_vec0, ray_pwr_wt=None, store: bool = Tr
     return res
 
 
+def init_multi(ngpu: int = 0) -> int:
+    """One host process, every GPU of the box (rays_b200.h): contexts + NCCL communicator; returns the GPU count."""
+    _ck(_lib().rays_b200_init_multi(int(ngpu)))
+    return int(_lib().rays_b200_ngpu())
+
+
+def finalize_multi() -> None:
+    _ck(_lib().rays_b200_finalize_multi())
+
+
+def trace_multi(cfg: Cfg | None, rvec0, rindex_vec0, ray_pwr_wt=None, store: bool = True, out: ResultArrays | None = None,
+                bins: tuple | None = None):
+    """rays_b200_trace_multi / _binned: the fan sharded iray % ngpu over the GPUs of init_multi, results in fan order.
+    bins=(n_bins, grid_min, grid_max): fused deposition + NCCL reduce / all-gather; returns (results, profile, Q_sum)."""
+    cfg = cfg if cfg is not None else host_cfg()
+    fan, keep = make_fan(rvec0, rindex_vec0, ray_pwr_wt)
+    res = out if out is not None else ResultArrays(int(fan.nray), int(cfg.nv), int(cfg.nstep_max) + 1, store and bins is None)
+    if bins is None:
+        _ck(_lib().rays_b200_trace_multi(C.byref(cfg), C.byref(fan), C.byref(res.c)))
+        del keep
+        return res
+    prof = np.zeros(int(bins[0]))
+    d = Deposition()
+    d.n_bins, d.grid_min, d.grid_max, d.profile = int(bins[0]), float(bins[1]), float(bins[2]), _dp(prof)
+    _ck(_lib().rays_b200_trace_multi_binned(C.byref(cfg), C.byref(fan), C.byref(res.c), C.byref(d)))
+    del keep
+    return res, prof, float(d.Q_sum)
+
+
 def fan_upload(rvec0, rindex_vec0, ray_pwr_wt=None) -> int:
     fan, keep = make_fan(rvec0, rindex_vec0, ray_pwr_wt)
     _ck(_lib().rays_b200_fan_upload(C.byref(fan)))

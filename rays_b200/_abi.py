@@ -155,6 +155,7 @@ ABI_SYMBOLS = [
     "rays_b200_fp64_peak", "rays_b200_host_alloc", "rays_b200_host_free", "rays_b200_stream", "rays_b200_version",
     "rays_b200_struct_sizes", "rays_b200_selftest_arith", "rays_b200_last_trace_breakdown", "rays_b200_mirror_brz_grid", "rays_b200_ox_conv_analysis",
     "rays_b200_deposition_fixed", "rays_b200_deposition_set_total_weight", "rays_b200_summaries_pack",
+    "rays_b200_init_multi", "rays_b200_ngpu", "rays_b200_trace_multi", "rays_b200_trace_multi_binned", "rays_b200_multi_summaries", "rays_b200_finalize_multi",
 ]
 HOST_SYMBOLS = [
     "rays_host_initialize", "rays_host_trace_rays", "rays_host_finalize_run", "rays_host_deallocate", "rays_host_last_error",
@@ -199,6 +200,9 @@ def load() -> C.CDLL:
         "rays_b200_deposition": (i, [P(Deposition), vp]), "rays_b200_trace_device_binned": (i, [i, dbl, dbl, i]),
         "rays_b200_deposition_fixed": (i, [P(Deposition), P(i64), vp, P(dbl)]), "rays_b200_deposition_set_total_weight": (i, [dbl]),
         "rays_b200_summaries_pack": (i, [vp, i64, P(i64), P(C.c_int32)]),
+        "rays_b200_init_multi": (i, [i]), "rays_b200_ngpu": (i, []), "rays_b200_finalize_multi": (i, []),
+        "rays_b200_trace_multi": (i, [P(Cfg), P(Fan), P(Results)]), "rays_b200_trace_multi_binned": (i, [P(Cfg), P(Fan), P(Results), P(Deposition)]),
+        "rays_b200_multi_summaries": (vp, [i, P(i64), P(C.c_int32)]),
         "rays_b200_probe_equilibrium": (i, [i64, c_double_p, c_double_p, c_int32_p]),
         "rays_b200_probe_rhs": (i, [i64, c_double_p, c_double_p, c_int32_p]),
         "rays_b200_probe_check_save": (i, [i64, c_double_p, c_double_p, c_int32_p]),

@@ -515,7 +515,8 @@ struct TraceArgs {
     // ([grid*block][npoints_alloc][nv]) and the warp copies each finished ray to the host as it ends
     double *host_ray_vec, *host_residual;
     int host_npoints_alloc;
-    long long host_ray0;            // index of this launch's first ray in the host arrays
+    long long host_ray0;            // row of this launch's first ray in the host arrays ...
+    long long host_ray_stride;      // ... and the row distance of consecutive rays (1; ngpu for the interleaved shards of rays_b200_trace_multi)
     int *npoints;                   // [nray]
     int *stop_code;                 // [nray]
     double *initial_ray_power, *end_residuals, *max_residuals, *end_ray_parameter;  // [nray]
@@ -703,12 +704,12 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
         const unsigned long long rw = __shfl_sync(0xffffffffu, (unsigned long long)row, l);
         if (a.host_ray_vec) {
             const double *src = a.ray_vec + (size_t)rw * a.npoints_alloc * nv;
-            double *dst = a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv;
+            double *dst = a.host_ray_vec + ((size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf) * nv;
             copy_row_to_host(dst, src, np * nv, lane);
         }
         if (a.host_residual) {
             const double *src = a.residual + (size_t)rw * a.npoints_alloc;
-            double *dst = a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf;
+            double *dst = a.host_residual + (size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf;
             copy_row_to_host(dst, src, np, lane);
         }
     }

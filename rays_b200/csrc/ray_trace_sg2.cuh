@@ -377,9 +377,9 @@ template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double
 // streaming copy-out of one finished ray by the whole warp: out of line, it runs once per ray
 static RD_NOINLINE void sg2_flush_row(const TraceArgs &a, long long ir, int np, int pf, size_t rw, int nv, unsigned lane) {
     if (a.host_ray_vec)
-        copy_row_to_host(a.host_ray_vec + ((size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf) * nv, a.ray_vec + rw * a.npoints_alloc * nv, np * nv, lane);
+        copy_row_to_host(a.host_ray_vec + ((size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf) * nv, a.ray_vec + rw * a.npoints_alloc * nv, np * nv, lane);
     if (a.host_residual)
-        copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
+        copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
 }
 
 template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgWarps * kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }

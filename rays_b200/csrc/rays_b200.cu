@@ -5,7 +5,10 @@
 // when no GPU is present.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -35,7 +38,7 @@ using namespace rays_dev;
 
 namespace {
 
-std::string g_err;
+thread_local std::string g_err;   // per host thread: rays_b200_trace_multi drives one GPU per thread
 int set_err(int code, const std::string &m) { g_err = m; return code; }
 #define CK(call)                                                                                              \
     do {                                                                                                      \
@@ -109,9 +112,15 @@ struct Ctx {
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
-} g;
+};
+// One context per GPU.  Every entry point works on the CURRENT context of the calling host thread: context 0 unless
+// rays_b200_*_multi selected another one (each of its worker threads drives one GPU).
+constexpr int kMaxGpus = 16;
+Ctx g_ctx[kMaxGpus];
+thread_local Ctx *g_cur = &g_ctx[0];
+inline Ctx &cx() { return *g_cur; }
 
-int need_init() { return g.inited ? 0 : set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_init has not been called"); }
+int need_init() { return cx().inited ? 0 : set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_init has not been called"); }
 
 const char *kStopStrings[RAYS_STOP_CODE_MAX] = {
     "", "sout > s_max", " nstep > nstep_max", "infinite Vg", "ray stalled", "dispersion_residual",
@@ -123,7 +132,7 @@ const char *kStopStrings[RAYS_STOP_CODE_MAX] = {
 
 int upload_table(DevBuf<double> &b, const double *src, size_t n) {
     CK(b.reserve(n));
-    CK(cudaMemcpyAsync(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
     return 0;
 }
 
@@ -147,6 +156,7 @@ int validate_cfg(const rays_cfg &c) {
         const rays_mirror_eq &m = c.mirror;
         if (!m.Br_spline.fspl || !m.Bz_spline.fspl || !m.Aphi_spline.fspl || !m.Br_spline.x_grid || !m.Br_spline.y_grid)
             return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: spline tables missing");
+        if (m.Br_spline.nx < 2 || m.Br_spline.ny < 2) return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: spline grids need nx, ny >= 2");
         if (m.Bz_spline.nx != m.Br_spline.nx || m.Aphi_spline.nx != m.Br_spline.nx || m.Bz_spline.ny != m.Br_spline.ny || m.Aphi_spline.ny != m.Br_spline.ny)
             return set_err(RAYS_ERR_INVALID_CONFIG, "multiple_mirror: Br, Bz, Aphi must share one (r,z) grid");
     }
@@ -413,77 +423,78 @@ __global__ void fp64_peak_kernel(double *out, int iters, double a, double b) {
 }
 
 int ensure_results(long long nray, int nv, int npa, bool traj) {
-    CK(g.npoints.reserve((size_t)nray));
-    CK(g.stop.reserve((size_t)nray));
-    CK(g.pwr.reserve((size_t)nray));
-    CK(g.endres.reserve((size_t)nray));
-    CK(g.maxres.reserve((size_t)nray));
-    CK(g.endpar.reserve((size_t)nray));
-    CK(g.startv.reserve((size_t)nray * nv));
-    CK(g.endv.reserve((size_t)nray * nv));
-    CK(g.queue.reserve(8));
+    CK(cx().npoints.reserve((size_t)nray));
+    CK(cx().stop.reserve((size_t)nray));
+    CK(cx().pwr.reserve((size_t)nray));
+    CK(cx().endres.reserve((size_t)nray));
+    CK(cx().maxres.reserve((size_t)nray));
+    CK(cx().endpar.reserve((size_t)nray));
+    CK(cx().startv.reserve((size_t)nray * nv));
+    CK(cx().endv.reserve((size_t)nray * nv));
+    CK(cx().queue.reserve(8));
     if (traj) {
-        CK(g.ray_vec.reserve((size_t)nray * npa * nv));
-        CK(g.residual.reserve((size_t)nray * npa));
+        CK(cx().ray_vec.reserve((size_t)nray * npa * nv));
+        CK(cx().residual.reserve((size_t)nray * npa));
     }
-    g.res_nray = nray; g.res_nv = nv; g.res_npa = npa; g.have_traj = traj;
+    cx().res_nray = nray; cx().res_nv = nv; cx().res_npa = npa; cx().have_traj = traj;
     return 0;
 }
 
 // launch the trace kernel over rays [first, first+count) of the device fan into result slots [first..)
 // trajectories go to traj_base (indexed from 0 for ray `first`) when non-null
-struct HostOut { double *ray_vec = nullptr, *residual = nullptr; int npa = 0; };   // device-accessible pinned host arrays
+struct HostOut { double *ray_vec = nullptr, *residual = nullptr; int npa = 0; long long row0 = 0, stride = 1; };   // device-accessible pinned host arrays
 
 int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned, const HostOut *host = nullptr) {
-    const rays_cfg &c = g.dc.c;
+    const rays_cfg &c = cx().dc.c;
     const TuOps *ops = tu_ops(c.equilib_model, c.ode_solver);
     if (!ops) return set_err(RAYS_ERR_INVALID_CONFIG, "no kernel for this equilibrium/ode pair");
     TraceArgs a{};
     a.nray = count;
-    a.rvec0 = g.rvec0.p + 3 * first;
-    a.rindex_vec0 = g.nvec0.p + 3 * first;
-    a.ray_pwr_wt = g.wt.p + first;
+    a.rvec0 = cx().rvec0.p + 3 * first;
+    a.rindex_vec0 = cx().nvec0.p + 3 * first;
+    a.ray_pwr_wt = cx().wt.p + first;
     a.ray_vec = traj_base;
     a.residual = resid_base;
-    a.npoints_alloc = g.res_npa;
-    a.npoints = g.npoints.p + first;
-    a.stop_code = g.stop.p + first;
-    a.initial_ray_power = g.pwr.p + first;
-    a.end_residuals = g.endres.p + first;
-    a.max_residuals = g.maxres.p + first;
-    a.end_ray_parameter = g.endpar.p + first;
-    a.start_ray_vec = g.startv.p + (size_t)first * g.res_nv;
-    a.end_ray_vec = g.endv.p + (size_t)first * g.res_nv;
-    a.queue = g.queue.p;
-    a.counters = g.queue.p + 1;
-    a.dep_acc = binned ? g.dep.p : nullptr;
-    a.n_bins = g.dep_bins; a.grid_min = g.dep_min; a.grid_max = g.dep_max; a.dep_scale = g.dep_scale;
-    a.dep_smem = (binned && (size_t)g.dep_bins * 8 <= 40 * 1024) ? g.dep_bins * 8 : 0;
-    int bps = g.cached_bps;
-    const char *name = g.cached_name;
-    if (bps <= 0 || g.cached_ops != ops) {   // occupancy of the selected specialisation: queried once per configuration
+    a.npoints_alloc = cx().res_npa;
+    a.npoints = cx().npoints.p + first;
+    a.stop_code = cx().stop.p + first;
+    a.initial_ray_power = cx().pwr.p + first;
+    a.end_residuals = cx().endres.p + first;
+    a.max_residuals = cx().maxres.p + first;
+    a.end_ray_parameter = cx().endpar.p + first;
+    a.start_ray_vec = cx().startv.p + (size_t)first * cx().res_nv;
+    a.end_ray_vec = cx().endv.p + (size_t)first * cx().res_nv;
+    a.queue = cx().queue.p;
+    a.counters = cx().queue.p + 1;
+    a.dep_acc = binned ? cx().dep.p : nullptr;
+    a.n_bins = cx().dep_bins; a.grid_min = cx().dep_min; a.grid_max = cx().dep_max; a.dep_scale = cx().dep_scale;
+    a.dep_smem = (binned && (size_t)cx().dep_bins * 8 <= 40 * 1024) ? cx().dep_bins * 8 : 0;
+    int bps = cx().cached_bps;
+    const char *name = cx().cached_name;
+    if (bps <= 0 || cx().cached_ops != ops) {   // occupancy of the selected specialisation: queried once per configuration
         size_t sgb = 0;
-        CK(ops->trace(g.sel, a, 0, g.stream, &bps, &name, &sgb));
+        CK(ops->trace(cx().sel, a, 0, cx().stream, &bps, &name, &sgb));
         if (bps < 1) bps = 1;
-        g.cached_bps = bps; g.cached_name = name; g.cached_ops = ops; g.cached_sgb = sgb;
+        cx().cached_bps = bps; cx().cached_name = name; cx().cached_ops = ops; cx().cached_sgb = sgb;
     }
-    if (g.cached_sgb) {   // Shampine-Gordon slot machine: slot memory for every CTA of the largest grid
-        CK(g.sg_state.reserve(((size_t)g.num_sms * bps * g.cached_sgb + 7) / 8));
-        a.sg_state = g.sg_state.p;
+    if (cx().cached_sgb) {   // Shampine-Gordon slot machine: slot memory for every CTA of the largest grid
+        CK(cx().sg_state.reserve(((size_t)cx().num_sms * bps * cx().cached_sgb + 7) / 8));
+        a.sg_state = cx().sg_state.p;
     }
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;   // (an SG CTA holds twice that many rays; a small fan still spreads over the SMs)
-    int grid = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>(blocks_needed, 1));
-    const int rays_per_cta = g.cached_sgb ? kSgWarps * kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: 64 slots per warp)
+    int grid = (int)std::min<long long>((long long)cx().num_sms * bps, std::max<long long>(blocks_needed, 1));
+    const int rays_per_cta = cx().cached_sgb ? kSgWarps * kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: 64 slots per warp)
     if (host) {   // streaming copy-out: per-lane (per-slot) staging rows, finished rays go straight to the caller's arrays
         const size_t lanes = (size_t)grid * rays_per_cta;
-        if (host->ray_vec) { CK(g.ray_vec.reserve(lanes * g.res_npa * g.res_nv)); a.ray_vec = g.ray_vec.p; a.host_ray_vec = host->ray_vec; }
-        if (host->residual) { CK(g.residual.reserve(lanes * g.res_npa)); a.residual = g.residual.p; a.host_residual = host->residual; }
+        if (host->ray_vec) { CK(cx().ray_vec.reserve(lanes * cx().res_npa * cx().res_nv)); a.ray_vec = cx().ray_vec.p; a.host_ray_vec = host->ray_vec; }
+        if (host->residual) { CK(cx().residual.reserve(lanes * cx().res_npa)); a.residual = cx().residual.p; a.host_residual = host->residual; }
         a.host_npoints_alloc = host->npa;
-        a.host_ray0 = first;
+        a.host_ray0 = host->row0 + first * host->stride;
+        a.host_ray_stride = host->stride;
     }
     // Time slicing (see TraceArgs): rays are suspended after `slice` steps and the survivors are re-launched packed
     // into full warps, until they fit one per lane.  RAYS_B200_SLICE=0 disables it, =n forces n steps.
-    const long long lanes = (long long)g.num_sms * bps * rays_per_cta;
+    const long long lanes = (long long)cx().num_sms * bps * rays_per_cta;
     int slice = 0;
     if (count >= 2 * lanes) slice = std::max(64, c.nstep_max / 4);
     bool forced = false;   // an explicit RAYS_B200_SLICE applies to fans of any size (tests), every pass
@@ -491,83 +502,114 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     // every pass keep the warps packed (1M-ray Solov'ev fan, tol 1e-6: 250 -> 64 steps: 5.15e7 -> 5.65e7 ray-steps/s)
     // (the per-lane SG kernel of round 1 needs short slices on every pass to keep its warps packed; the slot machine regroups
     // its slots every iteration and slices like RK4)
-    if (c.ode_solver == RAYS_ODE_SG && g.sel.sg_lanes && count >= 2 * lanes) { slice = 64; forced = true; }
+    if (c.ode_solver == RAYS_ODE_SG && cx().sel.sg_lanes && count >= 2 * lanes) { slice = 64; forced = true; }
     if (const char *env = getenv("RAYS_B200_SLICE")) { if (env[0]) { slice = atoi(env); forced = true; } }
     a.sg_align = 1;        // measurement aid: RAYS_B200_SG_ALIGN=0 lets the SG lanes run free (results are identical)
     if (const char *env = getenv("RAYS_B200_SG_ALIGN")) { if (env[0]) a.sg_align = atoi(env) != 0; }
     if (slice > 0) {
-        CK(g.cont_state.reserve((size_t)count * kContStride));
-        CK(g.cont_list[0].reserve((size_t)count)); CK(g.cont_list[1].reserve((size_t)count));
+        CK(cx().cont_state.reserve((size_t)count * kContStride));
+        CK(cx().cont_list[0].reserve((size_t)count)); CK(cx().cont_list[1].reserve((size_t)count));
     }
     long long n_this = count;
     for (int phase = 0;; ++phase) {
         a.nray = n_this;
         a.slice_steps = (slice > 0 && (forced || n_this > lanes)) ? slice : 0;      // survivors that fit one per lane run to the end
         a.resume = phase > 0 ? 1 : 0;
-        a.order = phase > 0 ? g.cont_list[(phase - 1) & 1].p : nullptr;
-        a.cont_state = g.cont_state.p;
-        a.cont_list = g.cont_list[phase & 1].p;
-        a.cont_count = g.queue.p + 3;
-        CK(cudaMemsetAsync(g.queue.p, 0, sizeof(unsigned long long), g.stream));
-        CK(cudaMemsetAsync(g.queue.p + 3, 0, sizeof(unsigned long long), g.stream));
-        const int grid_p = (int)std::min<long long>((long long)g.num_sms * bps, std::max<long long>((n_this + kTraceBlock - 1) / kTraceBlock, 1));
-        CK(cudaEventRecord(g.ev_m0, g.stream));
-        CK(ops->trace(g.sel, a, grid_p, g.stream, nullptr, nullptr, nullptr));
-        CK(cudaEventRecord(g.ev_m1, g.stream));
-        g.last_launches += 1;
-        g.last_phases = phase + 1;
-        if (a.slice_steps == 0) { g.main_pending = true; g.main_is_resume = phase > 0; break; }
+        a.order = phase > 0 ? cx().cont_list[(phase - 1) & 1].p : nullptr;
+        a.cont_state = cx().cont_state.p;
+        a.cont_list = cx().cont_list[phase & 1].p;
+        a.cont_count = cx().queue.p + 3;
+        CK(cudaMemsetAsync(cx().queue.p, 0, sizeof(unsigned long long), cx().stream));
+        CK(cudaMemsetAsync(cx().queue.p + 3, 0, sizeof(unsigned long long), cx().stream));
+        const int grid_p = (int)std::min<long long>((long long)cx().num_sms * bps, std::max<long long>((n_this + kTraceBlock - 1) / kTraceBlock, 1));
+        CK(cudaEventRecord(cx().ev_m0, cx().stream));
+        CK(ops->trace(cx().sel, a, grid_p, cx().stream, nullptr, nullptr, nullptr));
+        CK(cudaEventRecord(cx().ev_m1, cx().stream));
+        cx().last_launches += 1;
+        cx().last_phases = phase + 1;
+        if (a.slice_steps == 0) { cx().main_pending = true; cx().main_is_resume = phase > 0; break; }
         unsigned long long n_susp = 0;
-        CK(cudaMemcpyAsync(&n_susp, g.queue.p + 3, sizeof(n_susp), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaMemcpyAsync(&n_susp, cx().queue.p + 3, sizeof(n_susp), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, g.ev_m0, g.ev_m1));
-        (phase > 0 ? g.last_resume_ms : g.last_first_ms) += ms;
+        CK(cudaEventElapsedTime(&ms, cx().ev_m0, cx().ev_m1));
+        (phase > 0 ? cx().last_resume_ms : cx().last_first_ms) += ms;
         if (n_susp == 0) break;
         n_this = (long long)n_susp;
     }
-    g.last_kernel = name; g.last_grid = grid; g.last_bps = bps;
+    cx().last_kernel = name; cx().last_grid = grid; cx().last_bps = bps;
     return 0;
 }
 
 int fetch_counters() {
     unsigned long long h[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(h, g.queue.p, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    if (g.main_pending) {   // duration of the (last) trace kernel itself
+    CK(cudaMemcpyAsync(h, cx().queue.p, sizeof(h), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    if (cx().main_pending) {   // duration of the (last) trace kernel itself
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g.ev_m0, g.ev_m1) == cudaSuccess) (g.main_is_resume ? g.last_resume_ms : g.last_first_ms) += ms;
-        g.main_pending = false;
+        if (cudaEventElapsedTime(&ms, cx().ev_m0, cx().ev_m1) == cudaSuccess) (cx().main_is_resume ? cx().last_resume_ms : cx().last_first_ms) += ms;
+        cx().main_pending = false;
     }
-    g.last_steps = (long long)h[1];
-    g.last_rhs = (long long)h[2];
+    cx().last_steps = (long long)h[1];
+    cx().last_rhs = (long long)h[2];
     return 0;
 }
 
-int copy_small_results(rays_results *res, long long first, long long count) {
-    const int nv = g.res_nv;
-    auto cp = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
-        if (!dst || bytes == 0) return cudaSuccess;
-        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream);
+// Where the rays of a device fan live in the caller's result arrays: local ray i is row row0 + i*stride
+// (row0 = 0, stride = 1 for a whole fan; row0 = gpu, stride = ngpu for the interleaved shards of rays_b200_trace_multi)
+struct RowMap { long long row0 = 0, stride = 1; };
+
+int copy_small_results(rays_results *res, long long first, long long count, RowMap rm = RowMap{}) {
+    const int nv = cx().res_nv;
+    if (rm.stride == 1) {
+        const long long o = rm.row0 + first;
+        auto cp = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+            if (!dst || bytes == 0) return cudaSuccess;
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cx().stream);
+        };
+        CK(cp(res->npoints ? res->npoints + o : nullptr, cx().npoints.p + first, count * sizeof(int)));
+        CK(cp(res->ray_stop_code ? res->ray_stop_code + o : nullptr, cx().stop.p + first, count * sizeof(int)));
+        CK(cp(res->initial_ray_power ? res->initial_ray_power + o : nullptr, cx().pwr.p + first, count * sizeof(double)));
+        CK(cp(res->end_residuals ? res->end_residuals + o : nullptr, cx().endres.p + first, count * sizeof(double)));
+        CK(cp(res->max_residuals ? res->max_residuals + o : nullptr, cx().maxres.p + first, count * sizeof(double)));
+        CK(cp(res->end_ray_parameter ? res->end_ray_parameter + o : nullptr, cx().endpar.p + first, count * sizeof(double)));
+        CK(cp(res->start_ray_vec ? res->start_ray_vec + (size_t)o * nv : nullptr, cx().startv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
+        CK(cp(res->end_ray_vec ? res->end_ray_vec + (size_t)o * nv : nullptr, cx().endv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
+        return 0;
+    }
+    // interleaved shard: one contiguous D2H per array, scattered to the strided rows on the host
+    std::vector<int> hi((size_t)count);
+    std::vector<double> hd((size_t)count * nv);
+    auto geti = [&](int32_t *dst, const int *src) -> int {
+        if (!dst) return 0;
+        CK(cudaMemcpyAsync(hi.data(), src + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
+        for (long long i = 0; i < count; ++i) dst[rm.row0 + (first + i) * rm.stride] = hi[(size_t)i];
+        return 0;
     };
-    CK(cp(res->npoints ? res->npoints + first : nullptr, g.npoints.p + first, count * sizeof(int)));
-    CK(cp(res->ray_stop_code ? res->ray_stop_code + first : nullptr, g.stop.p + first, count * sizeof(int)));
-    CK(cp(res->initial_ray_power ? res->initial_ray_power + first : nullptr, g.pwr.p + first, count * sizeof(double)));
-    CK(cp(res->end_residuals ? res->end_residuals + first : nullptr, g.endres.p + first, count * sizeof(double)));
-    CK(cp(res->max_residuals ? res->max_residuals + first : nullptr, g.maxres.p + first, count * sizeof(double)));
-    CK(cp(res->end_ray_parameter ? res->end_ray_parameter + first : nullptr, g.endpar.p + first, count * sizeof(double)));
-    CK(cp(res->start_ray_vec ? res->start_ray_vec + (size_t)first * nv : nullptr, g.startv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
-    CK(cp(res->end_ray_vec ? res->end_ray_vec + (size_t)first * nv : nullptr, g.endv.p + (size_t)first * nv, (size_t)count * nv * sizeof(double)));
+    auto getd = [&](double *dst, const double *src, int w) -> int {
+        if (!dst) return 0;
+        CK(cudaMemcpyAsync(hd.data(), src + (size_t)first * w, (size_t)count * w * sizeof(double), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
+        for (long long i = 0; i < count; ++i)
+            for (int k = 0; k < w; ++k) dst[(size_t)(rm.row0 + (first + i) * rm.stride) * w + k] = hd[(size_t)i * w + k];
+        return 0;
+    };
+    int rc;
+    if ((rc = geti(res->npoints, cx().npoints.p)) || (rc = geti(res->ray_stop_code, cx().stop.p))) return rc;
+    if ((rc = getd(res->initial_ray_power, cx().pwr.p, 1)) || (rc = getd(res->end_residuals, cx().endres.p, 1)) ||
+        (rc = getd(res->max_residuals, cx().maxres.p, 1)) || (rc = getd(res->end_ray_parameter, cx().endpar.p, 1)) ||
+        (rc = getd(res->start_ray_vec, cx().startv.p, nv)) || (rc = getd(res->end_ray_vec, cx().endv.p, nv))) return rc;
     return 0;
 }
 
-void fill_flags(rays_results *res, const std::vector<int> &codes, long long first) {
+void fill_flags(rays_results *res, const std::vector<int> &codes, long long first, RowMap rm = RowMap{}) {
     if (!res->ray_stop_flag) return;
     char table[RAYS_STOP_CODE_MAX][RAYS_FLAG_LEN];
     for (int c = 0; c < RAYS_STOP_CODE_MAX; ++c) rays_b200_stop_string(c, table[c], RAYS_FLAG_LEN);
     for (size_t i = 0; i < codes.size(); ++i) {
         const int c = (codes[i] >= 0 && codes[i] < RAYS_STOP_CODE_MAX) ? codes[i] : 0;
-        std::memcpy(res->ray_stop_flag + (size_t)(first + (long long)i) * RAYS_FLAG_LEN, table[c], RAYS_FLAG_LEN);
+        std::memcpy(res->ray_stop_flag + (size_t)(rm.row0 + (first + (long long)i) * rm.stride) * RAYS_FLAG_LEN, table[c], RAYS_FLAG_LEN);
     }
 }
 
@@ -576,7 +618,7 @@ void fill_flags(rays_results *res, const std::vector<int> &codes, long long firs
 // neighbouring groups of equal width share one cudaMemcpy2DAsync.  (A fan whose longest ray hits
 // nstep_max would otherwise move every ray at full length.)
 int copy_trajectories(rays_results *res, const std::vector<int> &np, long long first, long long count, const double *tv, const double *tr,
-                      int npa, int nv, cudaStream_t st) {
+                      int npa, int nv, cudaStream_t st, RowMap rm = RowMap{}) {
     const long long G = 64;
     long long run0 = first;
     int w0 = -1;
@@ -584,10 +626,10 @@ int copy_trajectories(rays_results *res, const std::vector<int> &np, long long f
         if (b <= a || w <= 0) return cudaSuccess;
         cudaError_t e = cudaSuccess;
         if (res->ray_vec)
-            e = cudaMemcpy2DAsync(res->ray_vec + (size_t)a * res->npoints_alloc * nv, (size_t)res->npoints_alloc * nv * 8,
+            e = cudaMemcpy2DAsync(res->ray_vec + (size_t)(rm.row0 + a * rm.stride) * res->npoints_alloc * nv, (size_t)rm.stride * res->npoints_alloc * nv * 8,
                                   tv + (size_t)(a - first) * npa * nv, (size_t)npa * nv * 8, (size_t)w * nv * 8, (size_t)(b - a), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && res->residual)
-            e = cudaMemcpy2DAsync(res->residual + (size_t)a * res->npoints_alloc, (size_t)res->npoints_alloc * 8, tr + (size_t)(a - first) * npa,
+            e = cudaMemcpy2DAsync(res->residual + (size_t)(rm.row0 + a * rm.stride) * res->npoints_alloc, (size_t)rm.stride * res->npoints_alloc * 8, tr + (size_t)(a - first) * npa,
                                   (size_t)npa * 8, (size_t)w * 8, (size_t)(b - a), cudaMemcpyDeviceToHost, st);
         return e;
     };
@@ -633,78 +675,79 @@ int rays_b200_init(int device) {
     if (e != cudaSuccess || ndev == 0)
         return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
     if (device < 0 || device >= ndev) return set_err(RAYS_ERR_CUDA, "rays_b200_init: device index out of range");
-    if (g.inited && g.device == device) return 0;
-    if (g.inited) rays_b200_finalize();
+    if (cx().inited && cx().device == device) return 0;
+    if (cx().inited) rays_b200_finalize();
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init: kernels are built for sm_100a only; found ") + prop.name);
-    g.device = device;
-    g.num_sms = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&g.ev0));
-    CK(cudaEventCreate(&g.ev1));
-    CK(cudaEventCreate(&g.ev_m0));
-    CK(cudaEventCreate(&g.ev_m1));
+    cx().device = device;
+    cx().num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&cx().stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&cx().copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&cx().ev0));
+    CK(cudaEventCreate(&cx().ev1));
+    CK(cudaEventCreate(&cx().ev_m0));
+    CK(cudaEventCreate(&cx().ev_m1));
     for (int i = 0; i < 2; ++i) {
-        CK(cudaEventCreateWithFlags(&g.ev_batch[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cx().ev_batch[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cx().ev_copy[i], cudaEventDisableTiming));
     }
-    g.inited = true;
+    cx().inited = true;
     return 0;
 }
 
 int rays_b200_finalize(void) {
-    if (!g.inited) return 0;
-    cudaSetDevice(g.device);
+    if (!cx().inited) return 0;
+    cudaSetDevice(cx().device);
     cudaDeviceSynchronize();
-    DevBuf<double> *bufs[] = {&g.zx, &g.zf, &g.rgrid, &g.zgrid, &g.br, &g.bz, &g.aphi, &g.prof_grid[0], &g.prof_grid[1], &g.prof_grid[2],
-                              &g.prof_fspl[0], &g.prof_fspl[1], &g.prof_fspl[2], &g.eq_rgrid, &g.eq_zgrid, &g.eq_psi, &g.eq_T, &g.rvec0, &g.nvec0, &g.wt, &g.ray_vec,
-                              &g.residual, &g.pwr, &g.endres, &g.maxres, &g.endpar, &g.startv, &g.endv};
+    DevBuf<double> *bufs[] = {&cx().zx, &cx().zf, &cx().rgrid, &cx().zgrid, &cx().br, &cx().bz, &cx().aphi, &cx().prof_grid[0], &cx().prof_grid[1], &cx().prof_grid[2],
+                              &cx().prof_fspl[0], &cx().prof_fspl[1], &cx().prof_fspl[2], &cx().eq_rgrid, &cx().eq_zgrid, &cx().eq_psi, &cx().eq_T, &cx().rvec0, &cx().nvec0, &cx().wt, &cx().ray_vec,
+                              &cx().residual, &cx().pwr, &cx().endres, &cx().maxres, &cx().endpar, &cx().startv, &cx().endv};
     for (auto *b : bufs) b->release();
-    g.npoints.release(); g.stop.release(); g.queue.release(); g.dep.release();
-    g.cont_state.release(); g.cont_list[0].release(); g.cont_list[1].release(); g.sg_state.release();
-    cudaEventDestroy(g.ev_m0); cudaEventDestroy(g.ev_m1);
-    if (g.pinned) cudaFreeHost(g.pinned);
-    g.pinned = nullptr; g.pinned_bytes = 0;
-    cudaEventDestroy(g.ev0); cudaEventDestroy(g.ev1);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(g.ev_batch[i]); cudaEventDestroy(g.ev_copy[i]); }
-    cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream);
-    g = Ctx{};
+    cx().npoints.release(); cx().stop.release(); cx().queue.release(); cx().dep.release();
+    cx().cont_state.release(); cx().cont_list[0].release(); cx().cont_list[1].release(); cx().sg_state.release();
+    cudaEventDestroy(cx().ev_m0); cudaEventDestroy(cx().ev_m1);
+    if (cx().pinned) cudaFreeHost(cx().pinned);
+    cx().pinned = nullptr; cx().pinned_bytes = 0;
+    cudaEventDestroy(cx().ev0); cudaEventDestroy(cx().ev1);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(cx().ev_batch[i]); cudaEventDestroy(cx().ev_copy[i]); }
+    cudaStreamDestroy(cx().stream); cudaStreamDestroy(cx().copy_stream);
+    cx() = Ctx{};
     return 0;
 }
 
-void *rays_b200_stream(void) { return g.inited ? (void *)g.stream : nullptr; }
+void *rays_b200_stream(void) { return cx().inited ? (void *)cx().stream : nullptr; }
 
 int rays_b200_set_config(const rays_cfg *cfg) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!cfg) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_set_config: null config");
     int rc = validate_cfg(*cfg);
     if (rc) return rc;
-    CK(cudaSetDevice(g.device));
-    DevCfg &d = g.dc;
+    CK(cudaSetDevice(cx().device));
+    cx().cfg_set = false;      // a failed upload below must not leave a half-updated configuration usable
+    DevCfg &d = cx().dc;
     d.c = *cfg;
     rays_cfg &c = d.c;
     // tables -> HBM; the struct then carries device pointers
     if (c.damping_model == RAYS_DAMP_FUND_ECH) {
-        if ((rc = upload_table(g.zx, cfg->zfun_re.x_grid, (size_t)cfg->zfun_re.nx))) return rc;
-        if ((rc = upload_table(g.zf, cfg->zfun_re.fspl, (size_t)4 * cfg->zfun_re.nx))) return rc;
-        c.zfun_re.x_grid = g.zx.p; c.zfun_re.fspl = g.zf.p;
+        if ((rc = upload_table(cx().zx, cfg->zfun_re.x_grid, (size_t)cfg->zfun_re.nx))) return rc;
+        if ((rc = upload_table(cx().zf, cfg->zfun_re.fspl, (size_t)4 * cfg->zfun_re.nx))) return rc;
+        c.zfun_re.x_grid = cx().zx.p; c.zfun_re.fspl = cx().zf.p;
     } else { c.zfun_re.x_grid = nullptr; c.zfun_re.fspl = nullptr; c.zfun_re.nx = 0; }
     if (c.equilib_model == RAYS_EQ_MULTIPLE_MIRROR) {
         const rays_mirror_eq &m = cfg->mirror;
         const size_t nx = (size_t)m.Br_spline.nx, ny = (size_t)m.Br_spline.ny;
-        if ((rc = upload_table(g.rgrid, m.Br_spline.x_grid, nx))) return rc;
-        if ((rc = upload_table(g.zgrid, m.Br_spline.y_grid, ny))) return rc;
-        if ((rc = upload_table(g.br, m.Br_spline.fspl, 16 * nx * ny))) return rc;
-        if ((rc = upload_table(g.bz, m.Bz_spline.fspl, 16 * nx * ny))) return rc;
-        if ((rc = upload_table(g.aphi, m.Aphi_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(cx().rgrid, m.Br_spline.x_grid, nx))) return rc;
+        if ((rc = upload_table(cx().zgrid, m.Br_spline.y_grid, ny))) return rc;
+        if ((rc = upload_table(cx().br, m.Br_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(cx().bz, m.Bz_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(cx().aphi, m.Aphi_spline.fspl, 16 * nx * ny))) return rc;
         rays_spline2d base = m.Br_spline;
-        base.x_grid = g.rgrid.p; base.y_grid = g.zgrid.p;
-        c.mirror.Br_spline = base; c.mirror.Br_spline.fspl = g.br.p;
-        c.mirror.Bz_spline = base; c.mirror.Bz_spline.fspl = g.bz.p;
-        c.mirror.Aphi_spline = base; c.mirror.Aphi_spline.fspl = g.aphi.p;
+        base.x_grid = cx().rgrid.p; base.y_grid = cx().zgrid.p;
+        c.mirror.Br_spline = base; c.mirror.Br_spline.fspl = cx().br.p;
+        c.mirror.Bz_spline = base; c.mirror.Bz_spline.fspl = cx().bz.p;
+        c.mirror.Aphi_spline = base; c.mirror.Aphi_spline.fspl = cx().aphi.p;
     } else {
         rays_spline2d none{};
         c.mirror.Br_spline = none; c.mirror.Bz_spline = none; c.mirror.Aphi_spline = none;
@@ -722,23 +765,23 @@ int rays_b200_set_config(const rays_cfg *cfg) {
             *sp[k] = rays_spline1d{};
             if (!used[k]) continue;
             const size_t nx = (size_t)src[k]->nx;
-            if ((rc = upload_table(g.prof_grid[k], src[k]->x_grid, nx))) return rc;
-            if ((rc = upload_table(g.prof_fspl[k], src[k]->fspl, 4 * nx))) return rc;
-            sp[k]->nx = src[k]->nx; sp[k]->x_grid = g.prof_grid[k].p; sp[k]->fspl = g.prof_fspl[k].p;
+            if ((rc = upload_table(cx().prof_grid[k], src[k]->x_grid, nx))) return rc;
+            if ((rc = upload_table(cx().prof_fspl[k], src[k]->fspl, 4 * nx))) return rc;
+            sp[k]->nx = src[k]->nx; sp[k]->x_grid = cx().prof_grid[k].p; sp[k]->fspl = cx().prof_fspl[k].p;
         }
     }
     c.axisym.Psi_spline = rays_spline2d{}; c.axisym.T_spline = rays_spline1d{};
     if (c.equilib_model == RAYS_EQ_AXISYM_TOROID && c.axisym.magnetics_model == RAYS_MAG_EQDSK_SPLINE) {
         const rays_axisym_eq &a = cfg->axisym;   // eqdsk_magnetics_spline_interp_m: Psi_profile (bicubic), T_profile (cubic)
         const size_t nx = (size_t)a.Psi_spline.nx, ny = (size_t)a.Psi_spline.ny, nt = (size_t)a.T_spline.nx;
-        if ((rc = upload_table(g.eq_rgrid, a.Psi_spline.x_grid, nx))) return rc;
-        if ((rc = upload_table(g.eq_zgrid, a.Psi_spline.y_grid, ny))) return rc;
-        if ((rc = upload_table(g.eq_psi, a.Psi_spline.fspl, 16 * nx * ny))) return rc;
-        if ((rc = upload_table(g.eq_T, a.T_spline.fspl, 4 * nt))) return rc;
+        if ((rc = upload_table(cx().eq_rgrid, a.Psi_spline.x_grid, nx))) return rc;
+        if ((rc = upload_table(cx().eq_zgrid, a.Psi_spline.y_grid, ny))) return rc;
+        if ((rc = upload_table(cx().eq_psi, a.Psi_spline.fspl, 16 * nx * ny))) return rc;
+        if ((rc = upload_table(cx().eq_T, a.T_spline.fspl, 4 * nt))) return rc;
         c.axisym.Psi_spline.nx = a.Psi_spline.nx; c.axisym.Psi_spline.ny = a.Psi_spline.ny;
-        c.axisym.Psi_spline.x_grid = g.eq_rgrid.p; c.axisym.Psi_spline.y_grid = g.eq_zgrid.p; c.axisym.Psi_spline.fspl = g.eq_psi.p;
-        c.axisym.T_spline.nx = a.T_spline.nx; c.axisym.T_spline.fspl = g.eq_T.p;
-        if (a.T_spline.x_grid == a.Psi_spline.x_grid && nt == nx) c.axisym.T_spline.x_grid = g.eq_rgrid.p;
+        c.axisym.Psi_spline.x_grid = cx().eq_rgrid.p; c.axisym.Psi_spline.y_grid = cx().eq_zgrid.p; c.axisym.Psi_spline.fspl = cx().eq_psi.p;
+        c.axisym.T_spline.nx = a.T_spline.nx; c.axisym.T_spline.fspl = cx().eq_T.p;
+        if (a.T_spline.x_grid == a.Psi_spline.x_grid && nt == nx) c.axisym.T_spline.x_grid = cx().eq_rgrid.p;
         else return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid: T_profile must be splined on the g-file's R grid (eqdsk_magnetics_spline_interp_m.f90:184)");
     }
     // constant products, formed with the same IEEE operations the reference performs per call
@@ -785,69 +828,69 @@ int rays_b200_set_config(const rays_cfg *cfg) {
         d.need_temp = need ? 1 : 0;
     }
     // kernel selection: the two-species specialisations cover electron + one ion without per-species damping slots
-    g.sel.ray_deriv = c.ray_deriv;
-    g.sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
-    g.sel.damp = c.damping_model != RAYS_DAMP_NONE;
-    g.sel.grads = c.integrate_eq_gradients != 0;
-    g.sel.sg_lanes = false;   // measurement aid: RAYS_B200_SG_LANES=1 runs the per-lane SG state machine (identical results)
-    if (const char *env = getenv("RAYS_B200_SG_LANES")) g.sel.sg_lanes = env[0] && atoi(env) != 0;
-    g.cached_bps = 0; g.cached_ops = nullptr;
+    cx().sel.ray_deriv = c.ray_deriv;
+    cx().sel.generic = !(c.nspec == 1 && !c.multi_spec_damping);
+    cx().sel.damp = c.damping_model != RAYS_DAMP_NONE;
+    cx().sel.grads = c.integrate_eq_gradients != 0;
+    cx().sel.sg_lanes = false;   // measurement aid: RAYS_B200_SG_LANES=1 runs the per-lane SG state machine (identical results)
+    if (const char *env = getenv("RAYS_B200_SG_LANES")) cx().sel.sg_lanes = env[0] && atoi(env) != 0;
+    cx().cached_bps = 0; cx().cached_ops = nullptr;
     for (int ode = 1; ode <= 2; ++ode) {
         const TuOps *ops = tu_ops(c.equilib_model, ode);
-        if (ops) CK(ops->upload(&d, g.stream));
+        if (ops) CK(ops->upload(&d, cx().stream));
     }
-    CK(cudaMemcpyToSymbolAsync(g_dc, &d, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, g.stream));   // this TU: deposition kernel
-    CK(cudaStreamSynchronize(g.stream));
-    g.cfg_set = true;
+    CK(cudaMemcpyToSymbolAsync(g_dc, &d, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, cx().stream));   // this TU: deposition kernel
+    CK(cudaStreamSynchronize(cx().stream));
+    cx().cfg_set = true;
     return 0;
 }
 
 int rays_b200_fan_upload(const rays_fan *fan) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!fan || fan->nray < 0 || (fan->nray > 0 && (!fan->rvec0 || !fan->rindex_vec0))) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_fan_upload: bad fan");
-    CK(cudaSetDevice(g.device));
+    CK(cudaSetDevice(cx().device));
     const size_t n = (size_t)fan->nray;
-    CK(g.rvec0.reserve(3 * n)); CK(g.nvec0.reserve(3 * n)); CK(g.wt.reserve(n));
+    CK(cx().rvec0.reserve(3 * n)); CK(cx().nvec0.reserve(3 * n)); CK(cx().wt.reserve(n));
     if (n) {
-        CK(cudaMemcpyAsync(g.rvec0.p, fan->rvec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-        CK(cudaMemcpyAsync(g.nvec0.p, fan->rindex_vec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-        if (fan->ray_pwr_wt) CK(cudaMemcpyAsync(g.wt.p, fan->ray_pwr_wt, n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-        else CK(cudaMemsetAsync(g.wt.p, 0, n * sizeof(double), g.stream));
+        CK(cudaMemcpyAsync(cx().rvec0.p, fan->rvec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
+        CK(cudaMemcpyAsync(cx().nvec0.p, fan->rindex_vec0, 3 * n * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
+        if (fan->ray_pwr_wt) CK(cudaMemcpyAsync(cx().wt.p, fan->ray_pwr_wt, n * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
+        else CK(cudaMemsetAsync(cx().wt.p, 0, n * sizeof(double), cx().stream));
     }
-    CK(cudaStreamSynchronize(g.stream));
-    g.nray = fan->nray;
+    CK(cudaStreamSynchronize(cx().stream));
+    cx().nray = fan->nray;
     double wsum = 0.0;
     if (fan->ray_pwr_wt) for (size_t i = 0; i < n; ++i) wsum += std::fabs(fan->ray_pwr_wt[i]);
-    g.fan_weight = wsum;
+    cx().fan_weight = wsum;
     return 0;
 }
 
 int rays_b200_fan_download(double *rvec0, double *rindex_vec0, double *ray_pwr_wt) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    const size_t n = (size_t)g.nray;
+    const size_t n = (size_t)cx().nray;
     if (n == 0) return 0;
-    if (rvec0) CK(cudaMemcpyAsync(rvec0, g.rvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    if (rindex_vec0) CK(cudaMemcpyAsync(rindex_vec0, g.nvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    if (ray_pwr_wt) CK(cudaMemcpyAsync(ray_pwr_wt, g.wt.p, n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    if (rvec0) CK(cudaMemcpyAsync(rvec0, cx().rvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cx().stream));
+    if (rindex_vec0) CK(cudaMemcpyAsync(rindex_vec0, cx().nvec0.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, cx().stream));
+    if (ray_pwr_wt) CK(cudaMemcpyAsync(ray_pwr_wt, cx().wt.p, n * sizeof(double), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     return 0;
 }
 
 int rays_b200_fan_shard(int rank, int world) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (world < 1 || rank < 0 || rank >= world) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_fan_shard: bad rank/world");
-    if (world == 1 || g.nray == 0) return 0;
-    const long long n_out = (g.nray - rank + world - 1) / world;
+    if (world == 1 || cx().nray == 0) return 0;
+    const long long n_out = (cx().nray - rank + world - 1) / world;
     DevBuf<double> rv, nv, w;
     CK(rv.reserve((size_t)3 * std::max<long long>(n_out, 1))); CK(nv.reserve((size_t)3 * std::max<long long>(n_out, 1))); CK(w.reserve((size_t)std::max<long long>(n_out, 1)));
     if (n_out > 0) {
-        fan_shard_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, g.stream>>>(n_out, rank, world, g.rvec0.p, g.nvec0.p, g.wt.p, rv.p, nv.p, w.p);
+        fan_shard_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, cx().stream>>>(n_out, rank, world, cx().rvec0.p, cx().nvec0.p, cx().wt.p, rv.p, nv.p, w.p);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(g.stream));
-    std::swap(g.rvec0, rv); std::swap(g.nvec0, nv); std::swap(g.wt, w);
+    CK(cudaStreamSynchronize(cx().stream));
+    std::swap(cx().rvec0, rv); std::swap(cx().nvec0, nv); std::swap(cx().wt, w);
     rv.release(); nv.release(); w.release();
-    g.nray = n_out;
+    cx().nray = n_out;
     return 0;
 }
 
@@ -855,40 +898,40 @@ int rays_b200_fan_shard(int rank, int world) {
 // 2^e > sum |ray_pwr_wt| every partial sum stays below 2^62 units of 2^(e-62)
 static void set_dep_scale() {
     int e = 0;
-    if (g.fan_weight > 0.0 && std::isfinite(g.fan_weight)) e = std::ilogb(g.fan_weight) + 1;
-    g.dep_scale = std::ldexp(1.0, 62 - e);
+    if (cx().fan_weight > 0.0 && std::isfinite(cx().fan_weight)) e = std::ilogb(cx().fan_weight) + 1;
+    cx().dep_scale = std::ldexp(1.0, 62 - e);
 }
 
 static int trace_device_impl(int store_trajectories, bool binned) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    CK(cudaSetDevice(g.device));
-    const rays_cfg &c = g.dc.c;
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    CK(cudaSetDevice(cx().device));
+    const rays_cfg &c = cx().dc.c;
     const int npa = c.nstep_max + 1;
-    if (store_trajectories && (g.ray_vec.n < (size_t)g.nray * npa * c.nv || g.residual.n < (size_t)g.nray * npa)) {   // buffers must grow
+    if (store_trajectories && (cx().ray_vec.n < (size_t)cx().nray * npa * c.nv || cx().residual.n < (size_t)cx().nray * npa)) {   // buffers must grow
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const double need = (double)g.nray * npa * (c.nv + 1) * 8.0;
-        const double have = (double)free_b + (double)(g.ray_vec.n + g.residual.n) * 8.0;
+        const double need = (double)cx().nray * npa * (c.nv + 1) * 8.0;
+        const double have = (double)free_b + (double)(cx().ray_vec.n + cx().residual.n) * 8.0;
         if (need > 0.92 * have)
             return set_err(RAYS_ERR_ALLOC, "rays_b200_trace_device: trajectories of this fan do not fit in HBM; trace without storage (binned) or use rays_b200_trace, which batches");
     }
-    int rc = ensure_results(g.nray, c.nv, npa, store_trajectories != 0);
+    int rc = ensure_results(cx().nray, c.nv, npa, store_trajectories != 0);
     if (rc) return rc;
-    g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
-    CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
-    if (binned) CK(cudaMemsetAsync(g.dep.p, 0, (size_t)g.dep_bins * sizeof(unsigned long long), g.stream));
-    CK(cudaEventRecord(g.ev0, g.stream));
-    if (g.nray > 0) {
-        rc = launch_trace(0, g.nray, store_trajectories ? g.ray_vec.p : nullptr, store_trajectories ? g.residual.p : nullptr, binned);
+    cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
+    CK(cudaMemsetAsync(cx().queue.p, 0, 3 * sizeof(unsigned long long), cx().stream));
+    if (binned) CK(cudaMemsetAsync(cx().dep.p, 0, (size_t)cx().dep_bins * sizeof(unsigned long long), cx().stream));
+    CK(cudaEventRecord(cx().ev0, cx().stream));
+    if (cx().nray > 0) {
+        rc = launch_trace(0, cx().nray, store_trajectories ? cx().ray_vec.p : nullptr, store_trajectories ? cx().residual.p : nullptr, binned);
         if (rc) return rc;
     }
-    CK(cudaEventRecord(g.ev1, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaEventRecord(cx().ev1, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
-    g.last_ms = ms;
-    g.dep_fused = binned;
+    CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
+    cx().last_ms = ms;
+    cx().dep_fused = binned;
     return fetch_counters();
 }
 
@@ -896,67 +939,67 @@ int rays_b200_trace_device(int store_trajectories) { return trace_device_impl(st
 
 int rays_b200_trace_device_binned(int n_bins, double grid_min, double grid_max, int store_trajectories) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
     if (n_bins < 1 || !(grid_max > grid_min)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad grid");
-    const rays_cfg &c = g.dc.c;
+    const rays_cfg &c = cx().dc.c;
     if (c.damping_model == RAYS_DAMP_NONE) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: needs a damping model (v(8) = absorbed power)");
     if (c.equilib_model != RAYS_EQ_SLAB && c.equilib_model != RAYS_EQ_AXISYM_TOROID)
         return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
-    CK(g.dep.reserve((size_t)n_bins));
-    g.dep_bins = n_bins; g.dep_min = grid_min; g.dep_max = grid_max;
+    CK(cx().dep.reserve((size_t)n_bins));
+    cx().dep_bins = n_bins; cx().dep_min = grid_min; cx().dep_max = grid_max;
     set_dep_scale();
     return trace_device_impl(store_trajectories, true);
 }
 
 int rays_b200_last_trace_stats(double *kernel_ms, int64_t *ray_steps, int32_t *n_launches) {
-    if (kernel_ms) *kernel_ms = g.last_ms;
-    if (ray_steps) *ray_steps = g.last_steps;
-    if (n_launches) *n_launches = g.last_launches;
+    if (kernel_ms) *kernel_ms = cx().last_ms;
+    if (ray_steps) *ray_steps = cx().last_steps;
+    if (n_launches) *n_launches = cx().last_launches;
     return 0;
 }
 // extra stats for bench/profiles: RHS evaluations, kernel name, grid, resident CTAs per SM
 int rays_b200_last_trace_info(int64_t *rhs_evals, char *kernel_name, int name_len, int32_t *grid, int32_t *blocks_per_sm) {
-    if (rhs_evals) *rhs_evals = g.last_rhs;
-    if (kernel_name && name_len > 0) { std::strncpy(kernel_name, g.last_kernel, (size_t)name_len - 1); kernel_name[name_len - 1] = 0; }
-    if (grid) *grid = g.last_grid;
-    if (blocks_per_sm) *blocks_per_sm = g.last_bps;
+    if (rhs_evals) *rhs_evals = cx().last_rhs;
+    if (kernel_name && name_len > 0) { std::strncpy(kernel_name, cx().last_kernel, (size_t)name_len - 1); kernel_name[name_len - 1] = 0; }
+    if (grid) *grid = cx().last_grid;
+    if (blocks_per_sm) *blocks_per_sm = cx().last_bps;
     return 0;
 }
 
 // kernel time of the last trace: first pass over the fan, resume passes over the suspended rays, launch count
 int rays_b200_last_trace_breakdown(double *first_pass_ms, double *resume_pass_ms, int32_t *n_passes) {
-    if (first_pass_ms) *first_pass_ms = g.last_first_ms;
-    if (resume_pass_ms) *resume_pass_ms = g.last_resume_ms;
-    if (n_passes) *n_passes = g.last_phases;
+    if (first_pass_ms) *first_pass_ms = cx().last_first_ms;
+    if (resume_pass_ms) *resume_pass_ms = cx().last_resume_ms;
+    if (n_passes) *n_passes = cx().last_phases;
     return 0;
 }
 
 int rays_b200_results_download(rays_results *res) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!res) return set_err(RAYS_ERR_INVALID_CONFIG, "null results");
-    if (res->nray < g.res_nray || res->nv != g.res_nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: result arrays do not match the last trace");
-    const long long n = g.res_nray;
-    const int nv = g.res_nv;
+    if (res->nray < cx().res_nray || res->nv != cx().res_nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: result arrays do not match the last trace");
+    const long long n = cx().res_nray;
+    const int nv = cx().res_nv;
     int rc = copy_small_results(res, 0, n);
     if (rc) return rc;
     std::vector<int> np((size_t)n), codes((size_t)n);
     if (n) {
-        CK(cudaMemcpyAsync(np.data(), g.npoints.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaMemcpyAsync(codes.data(), g.stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaMemcpyAsync(np.data(), cx().npoints.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaMemcpyAsync(codes.data(), cx().stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
     }
-    CK(cudaStreamSynchronize(g.stream));
-    if (g.have_traj && n && (res->ray_vec || res->residual)) {
+    CK(cudaStreamSynchronize(cx().stream));
+    if (cx().have_traj && n && (res->ray_vec || res->residual)) {
         if (res->npoints_alloc < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "npoints_alloc < 1");
         for (long long i = 0; i < n; ++i)
             if (np[(size_t)i] > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
-        zero_tail_kernel<<<(unsigned)n, 64, 0, g.stream>>>(res->ray_vec ? g.ray_vec.p : nullptr, res->residual ? g.residual.p : nullptr, g.npoints.p, g.res_npa, nv, n);
+        zero_tail_kernel<<<(unsigned)n, 64, 0, cx().stream>>>(res->ray_vec ? cx().ray_vec.p : nullptr, res->residual ? cx().residual.p : nullptr, cx().npoints.p, cx().res_npa, nv, n);
         CK(cudaGetLastError());
-        if ((rc = copy_trajectories(res, np, 0, n, g.ray_vec.p, g.residual.p, g.res_npa, nv, g.stream))) return rc;
-        CK(cudaStreamSynchronize(g.stream));
+        if ((rc = copy_trajectories(res, np, 0, n, cx().ray_vec.p, cx().residual.p, cx().res_npa, nv, cx().stream))) return rc;
+        CK(cudaStreamSynchronize(cx().stream));
     }
     fill_flags(res, codes, 0);
-    res->total_trace_time = g.last_ms * 1e-3;
-    res->total_ray_steps = g.last_steps;
+    res->total_trace_time = cx().last_ms * 1e-3;
+    res->total_ray_steps = cx().last_steps;
     if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = n ? res->total_trace_time / (double)n : 0.0;
     return 0;
 }
@@ -985,21 +1028,24 @@ static double *device_view_of_host(double *p, size_t bytes, std::vector<void *> 
 // trace_rays with HOST buffers (ray_tracing.f90:1-290): H2D of the fan, trace in batches sized to HBM with
 // two trajectory buffers so that the copy-out of batch b overlaps the integration of batch b+1, results
 // land in the caller's arrays in the reference layout.
-int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res) {
+static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_results *res, RowMap rm);
+int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res) { return trace_host_impl(cfg, fan, res, RowMap{}); }
+// res describes the WHOLE result arrays (res->nray rows); the rays of `fan` go to the rows rm selects
+static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_results *res, RowMap rm) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!fan || !res) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: null argument");
     int rc;
     if (cfg) { if ((rc = rays_b200_set_config(cfg))) return rc; }
-    else if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_trace: no config");
-    const rays_cfg &c = g.dc.c;
-    if (res->nray < fan->nray || res->nv != c.nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: result arrays do not match fan/nv");
+    else if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_trace: no config");
+    const rays_cfg &c = cx().dc.c;
+    if ((fan->nray > 0 && res->nray < rm.row0 + (fan->nray - 1) * rm.stride + 1) || res->nv != c.nv) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: result arrays do not match fan/nv");
     if (!res->npoints) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: npoints array is required");
     const bool want_traj = res->ray_vec != nullptr || res->residual != nullptr;
     const int npa = c.nstep_max + 1;
     if (want_traj && res->npoints_alloc < npa) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace: npoints_alloc < nstep_max+1");
-    CK(cudaEventRecord(g.ev0, g.stream));
+    CK(cudaEventRecord(cx().ev0, cx().stream));
     if ((rc = rays_b200_fan_upload(fan))) return rc;
-    const long long n = g.nray;
+    const long long n = cx().nray;
     const int nv = c.nv;
     // Preferred path: the result arrays are (or can be made) page-locked: finished rays are copied out by
     // the trace kernel itself, overlapped with the integration; HBM holds only one staging row per lane.
@@ -1008,31 +1054,31 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
     std::vector<void *> temp_registered;
     struct Unreg { std::vector<void *> &v; ~Unreg() { for (void *q : v) cudaHostUnregister(q); } } unreg{temp_registered};
     if (want_traj && n > 0) {
-        hv.npa = res->npoints_alloc;
+        hv.npa = res->npoints_alloc; hv.row0 = rm.row0; hv.stride = rm.stride;
         hv.ray_vec = device_view_of_host(res->ray_vec, (size_t)res->nray * res->npoints_alloc * nv * 8, temp_registered);
         hv.residual = device_view_of_host(res->residual, (size_t)res->nray * res->npoints_alloc * 8, temp_registered);
         streaming = (res->ray_vec == nullptr || hv.ray_vec) && (res->residual == nullptr || hv.residual);
     }
     if (streaming) {
         if ((rc = ensure_results(n, nv, npa, false))) return rc;
-        g.have_traj = false;
-        g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
-        CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
+        cx().have_traj = false;
+        cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
+        CK(cudaMemsetAsync(cx().queue.p, 0, 3 * sizeof(unsigned long long), cx().stream));
         if ((rc = launch_trace(0, n, nullptr, nullptr, false, &hv))) return rc;
         std::vector<int> codes((size_t)n);
-        CK(cudaMemcpyAsync(codes.data(), g.stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-        if ((rc = copy_small_results(res, 0, n))) return rc;
-        CK(cudaEventRecord(g.ev1, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaMemcpyAsync(codes.data(), cx().stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        if ((rc = copy_small_results(res, 0, n, rm))) return rc;
+        CK(cudaEventRecord(cx().ev1, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
-        g.last_ms = ms;
+        CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
+        cx().last_ms = ms;
         if ((rc = fetch_counters())) return rc;
-        fill_flags(res, codes, 0);
-        res->total_trace_time = g.last_ms * 1e-3;
-        res->total_ray_steps = g.last_steps;
-        if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = res->total_trace_time / (double)n;
-        g.dep_fused = false;
+        fill_flags(res, codes, 0, rm);
+        res->total_trace_time = cx().last_ms * 1e-3;
+        res->total_ray_steps = cx().last_steps;
+        if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[rm.row0 + i * rm.stride] = res->total_trace_time / (double)n;
+        cx().dep_fused = false;
         return 0;
     }
     // Fallback (pageable arrays that cannot be registered): batches sized to HBM, two trajectory buffers
@@ -1040,7 +1086,7 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
     if (want_traj && n > 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const double avail = 0.70 * ((double)free_b + (double)(g.ray_vec.n + g.residual.n) * 8.0);
+        const double avail = 0.70 * ((double)free_b + (double)(cx().ray_vec.n + cx().residual.n) * 8.0);
         const double per_ray = (double)npa * (nv + 1) * 8.0;
         if ((double)n * per_ray > avail) {
             batch = (long long)(avail / (2.0 * per_ray));
@@ -1050,49 +1096,49 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
     const int nbuf = (batch < n) ? 2 : 1;
     if ((rc = ensure_results(n, nv, npa, false))) return rc;
     if (want_traj) {
-        CK(g.ray_vec.reserve((size_t)nbuf * batch * npa * nv));
-        CK(g.residual.reserve((size_t)nbuf * batch * npa));
-        g.have_traj = (nbuf == 1);
+        CK(cx().ray_vec.reserve((size_t)nbuf * batch * npa * nv));
+        CK(cx().residual.reserve((size_t)nbuf * batch * npa));
+        cx().have_traj = (nbuf == 1);
     }
-    g.last_launches = 0; g.last_first_ms = 0; g.last_resume_ms = 0; g.last_phases = 0;
-    CK(cudaMemsetAsync(g.queue.p, 0, 3 * sizeof(unsigned long long), g.stream));
+    cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
+    CK(cudaMemsetAsync(cx().queue.p, 0, 3 * sizeof(unsigned long long), cx().stream));
     std::vector<int> np((size_t)std::max<long long>(n, 1)), codes((size_t)std::max<long long>(n, 1));
     int ib = 0;
     for (long long first = 0; first < n; first += batch, ++ib) {
         const long long count = std::min(batch, n - first);
         const int b = ib % nbuf;
-        double *tv = want_traj ? g.ray_vec.p + (size_t)b * batch * npa * nv : nullptr;
-        double *tr = want_traj ? g.residual.p + (size_t)b * batch * npa : nullptr;
-        if (ib >= nbuf) CK(cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0));   // buffer b free again
+        double *tv = want_traj ? cx().ray_vec.p + (size_t)b * batch * npa * nv : nullptr;
+        double *tr = want_traj ? cx().residual.p + (size_t)b * batch * npa : nullptr;
+        if (ib >= nbuf) CK(cudaStreamWaitEvent(cx().stream, cx().ev_copy[b], 0));   // buffer b free again
         if ((rc = launch_trace(first, count, tv, tr, false))) return rc;
         if (want_traj) {
-            zero_tail_kernel<<<(unsigned)count, 64, 0, g.stream>>>(res->ray_vec ? tv : nullptr, res->residual ? tr : nullptr, g.npoints.p + first, npa, nv, count);
+            zero_tail_kernel<<<(unsigned)count, 64, 0, cx().stream>>>(res->ray_vec ? tv : nullptr, res->residual ? tr : nullptr, cx().npoints.p + first, npa, nv, count);
             CK(cudaGetLastError());
         }
-        CK(cudaMemcpyAsync(np.data() + first, g.npoints.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaMemcpyAsync(codes.data() + first, g.stop.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-        CK(cudaEventRecord(g.ev_batch[b], g.stream));
+        CK(cudaMemcpyAsync(np.data() + first, cx().npoints.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaMemcpyAsync(codes.data() + first, cx().stop.p + first, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaEventRecord(cx().ev_batch[b], cx().stream));
         if (want_traj) {
-            CK(cudaEventSynchronize(g.ev_batch[b]));   // npoints of this batch are on the host: trim the copy
-            if ((rc = copy_trajectories(res, np, first, count, tv, tr, npa, nv, g.copy_stream))) return rc;
-            CK(cudaEventRecord(g.ev_copy[b], g.copy_stream));
+            CK(cudaEventSynchronize(cx().ev_batch[b]));   // npoints of this batch are on the host: trim the copy
+            if ((rc = copy_trajectories(res, np, first, count, tv, tr, npa, nv, cx().copy_stream, rm))) return rc;
+            CK(cudaEventRecord(cx().ev_copy[b], cx().copy_stream));
         }
     }
-    if ((rc = copy_small_results(res, 0, n))) return rc;
-    CK(cudaEventRecord(g.ev1, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    CK(cudaStreamSynchronize(g.copy_stream));
+    if ((rc = copy_small_results(res, 0, n, rm))) return rc;
+    CK(cudaEventRecord(cx().ev1, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cudaStreamSynchronize(cx().copy_stream));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
-    g.last_ms = ms;
+    CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
+    cx().last_ms = ms;
     if ((rc = fetch_counters())) return rc;
     if (res->ray_stop_code == nullptr) { /* codes only needed for the strings */ }
     codes.resize((size_t)n);
-    fill_flags(res, codes, 0);
-    res->total_trace_time = g.last_ms * 1e-3;
-    res->total_ray_steps = g.last_steps;
-    if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[i] = n ? res->total_trace_time / (double)n : 0.0;
-    g.dep_fused = false;
+    fill_flags(res, codes, 0, rm);
+    res->total_trace_time = cx().last_ms * 1e-3;
+    res->total_ray_steps = cx().last_steps;
+    if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[rm.row0 + i * rm.stride] = n ? res->total_trace_time / (double)n : 0.0;
+    cx().dep_fused = false;
     return 0;
 }
 
@@ -1100,21 +1146,21 @@ int rays_b200_trace(const rays_cfg *cfg, const rays_fan *fan, rays_results *res)
 static int run_launch_fan(int kind, long long npos, const std::vector<double> &pos_host, const double *dir_host, int n_a, int n_b, double a0,
                           double da, double b0, double db, int64_t *nray_out) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    CK(cudaSetDevice(g.device));
-    const rays_cfg &c = g.dc.c;
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    CK(cudaSetDevice(cx().device));
+    const rays_cfg &c = cx().dc.c;
     const TuOps *ops = tu_ops(c.equilib_model, RAYS_ODE_RK4);
     const long long ncand = kind == 4 ? npos : npos * n_a * n_b;
-    if (ncand <= 0) { g.nray = 0; if (nray_out) *nray_out = 0; return 0; }
+    if (ncand <= 0) { cx().nray = 0; if (nray_out) *nray_out = 0; return 0; }
     if (ncand >= (1LL << 31)) return set_err(RAYS_ERR_INVALID_CONFIG, "launch fan: more than 2^31 candidates on one GPU");
     DevBuf<double> pos, dir, rv, nv;
     DevBuf<int> valid, counts;
     DevBuf<long long> total;
     CK(pos.reserve(pos_host.size()));
-    CK(cudaMemcpyAsync(pos.p, pos_host.data(), pos_host.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(pos.p, pos_host.data(), pos_host.size() * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
     if (kind == 4) {
         CK(dir.reserve((size_t)3 * ncand));
-        CK(cudaMemcpyAsync(dir.p, dir_host, (size_t)3 * ncand * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(dir.p, dir_host, (size_t)3 * ncand * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
     }
     const int nblocks = (int)((ncand + kScanBlock - 1) / kScanBlock);
     CK(rv.reserve((size_t)3 * ncand)); CK(nv.reserve((size_t)3 * ncand)); CK(valid.reserve((size_t)ncand));
@@ -1122,35 +1168,35 @@ static int run_launch_fan(int kind, long long npos, const std::vector<double> &p
     FanLaunchArgs f{};
     f.kind = kind; f.ncand = ncand; f.rvec_in = pos.p; f.nvec_in = dir.p; f.n_a = n_a; f.n_b = n_b;
     f.a0 = a0; f.da = da; f.b0 = b0; f.db = db; f.rvec_out = rv.p; f.nvec_out = nv.p; f.valid = valid.p;
-    CK(ops->launch_fan(g.sel, f, g.stream));
-    fan_count_kernel<<<nblocks, kScanBlock, 0, g.stream>>>(valid.p, ncand, counts.p);
+    CK(ops->launch_fan(cx().sel, f, cx().stream));
+    fan_count_kernel<<<nblocks, kScanBlock, 0, cx().stream>>>(valid.p, ncand, counts.p);
     CK(cudaGetLastError());
-    fan_offsets_kernel<<<1, 1024, 0, g.stream>>>(counts.p, nblocks, total.p);
+    fan_offsets_kernel<<<1, 1024, 0, cx().stream>>>(counts.p, nblocks, total.p);
     CK(cudaGetLastError());
     long long nray = 0;
-    CK(cudaMemcpyAsync(&nray, total.p, sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    CK(g.rvec0.reserve((size_t)3 * std::max<long long>(nray, 1))); CK(g.nvec0.reserve((size_t)3 * std::max<long long>(nray, 1)));
-    CK(g.wt.reserve((size_t)std::max<long long>(nray, 1)));
+    CK(cudaMemcpyAsync(&nray, total.p, sizeof(long long), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    CK(cx().rvec0.reserve((size_t)3 * std::max<long long>(nray, 1))); CK(cx().nvec0.reserve((size_t)3 * std::max<long long>(nray, 1)));
+    CK(cx().wt.reserve((size_t)std::max<long long>(nray, 1)));
     if (nray > 0) {
-        fan_scatter_kernel<<<nblocks, kScanBlock, 0, g.stream>>>(valid.p, ncand, counts.p, rv.p, nv.p, g.rvec0.p, g.nvec0.p);
+        fan_scatter_kernel<<<nblocks, kScanBlock, 0, cx().stream>>>(valid.p, ncand, counts.p, rv.p, nv.p, cx().rvec0.p, cx().nvec0.p);
         CK(cudaGetLastError());
         double w = 1.0 / (double)nray;
         if (kind == 1) w = 1.0 / (double)nray / (double)nray;   // (R) divided by nray twice (simple_slab_ray_init_m.f90:179,182)
-        fill_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, g.stream>>>(g.wt.p, nray, w);
+        fill_kernel<<<(unsigned)((nray + 255) / 256), 256, 0, cx().stream>>>(cx().wt.p, nray, w);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(cx().stream));
     pos.release(); dir.release(); rv.release(); nv.release(); valid.release(); counts.release(); total.release();
-    g.nray = nray;
-    g.fan_weight = nray > 0 ? (kind == 1 ? 1.0 / (double)nray : 1.0) : 0.0;
+    cx().nray = nray;
+    cx().fan_weight = nray > 0 ? (kind == 1 ? 1.0 / (double)nray : 1.0) : 0.0;
     if (nray_out) *nray_out = nray;
     return 0;
 }
 
 int rays_b200_launch_fan_slab(const rays_slab_launch *p, int64_t *nray_out) {
     if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
-    if (g.cfg_set && g.dc.c.equilib_model != RAYS_EQ_SLAB) return set_err(RAYS_ERR_INVALID_CONFIG, "simple_slab ray init needs equilib_model 'slab'");
+    if (cx().cfg_set && cx().dc.c.equilib_model != RAYS_EQ_SLAB) return set_err(RAYS_ERR_INVALID_CONFIG, "simple_slab ray init needs equilib_model 'slab'");
     std::vector<double> pos;
     for (int iz = 1; iz <= p->n_z_launch; ++iz)
         for (int iy = 1; iy <= p->n_y_launch; ++iy)
@@ -1164,10 +1210,10 @@ int rays_b200_launch_fan_slab(const rays_slab_launch *p, int64_t *nray_out) {
 }
 int rays_b200_launch_fan_solovev(const rays_solovev_launch *p, int64_t *nray_out) {
     if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    if (g.dc.c.equilib_model != RAYS_EQ_SOLOVEV) return set_err(RAYS_ERR_INVALID_CONFIG, "solovev ray init needs equilib_model 'solovev'");
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (cx().dc.c.equilib_model != RAYS_EQ_SOLOVEV) return set_err(RAYS_ERR_INVALID_CONFIG, "solovev ray init needs equilib_model 'solovev'");
     std::vector<double> pos;
-    const double rmaj = g.dc.c.solovev.rmaj;
+    const double rmaj = cx().dc.c.solovev.rmaj;
     for (int ir = 1; ir <= p->n_r_launch; ++ir)
         for (int it = 1; it <= p->n_theta_launch; ++it) {
             const double theta = p->theta_launch0 + (it - 1) * p->dtheta_launch;
@@ -1181,8 +1227,8 @@ int rays_b200_launch_fan_solovev(const rays_solovev_launch *p, int64_t *nray_out
 }
 int rays_b200_launch_fan_axisym(const rays_axisym_launch *p, int64_t *nray_out) {
     if (!p) return set_err(RAYS_ERR_INVALID_CONFIG, "null launch parameters");
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    if (g.dc.c.equilib_model != RAYS_EQ_AXISYM_TOROID) return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid ray init needs equilib_model 'axisym_toroid'");
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (cx().dc.c.equilib_model != RAYS_EQ_AXISYM_TOROID) return set_err(RAYS_ERR_INVALID_CONFIG, "axisym_toroid ray init needs equilib_model 'axisym_toroid'");
     std::vector<double> pos;
     for (int iR = 1; iR <= p->n_R_launch; ++iR)
         for (int iZ = 1; iZ <= p->n_Z_launch; ++iZ) {   // (R) every (i_R, i_Z) launches from the same point
@@ -1204,36 +1250,36 @@ int rays_b200_launch_fan_directions(int64_t n_in, const double *rvec_in, const d
 static int deposition_impl(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!dep || dep->n_bins < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad arguments");
-    const rays_cfg &c = g.dc.c;
+    const rays_cfg &c = cx().dc.c;
     const int nb = dep->n_bins;
-    if (g.dep_fused) {
-        if (nb != g.dep_bins || dep->grid_min != g.dep_min || dep->grid_max != g.dep_max)
+    if (cx().dep_fused) {
+        if (nb != cx().dep_bins || dep->grid_min != cx().dep_min || dep->grid_max != cx().dep_max)
             return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: n_bins / grid differ from the binned trace");
     } else {
-        if (!g.have_traj) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: no stored trajectories; trace with storage or use rays_b200_trace_device_binned");
+        if (!cx().have_traj) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: no stored trajectories; trace with storage or use rays_b200_trace_device_binned");
         if (c.damping_model == RAYS_DAMP_NONE) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: needs a damping model");
         if (c.equilib_model != RAYS_EQ_SLAB && c.equilib_model != RAYS_EQ_AXISYM_TOROID)
             return set_err(RAYS_ERR_INVALID_CONFIG, "deposition profiles exist for slab (Ptotal_x) and axisym_toroid (Ptotal_psi) only");
         if (!(dep->grid_max > dep->grid_min)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad grid");
-        CK(g.dep.reserve((size_t)nb));
-        g.dep_bins = nb; g.dep_min = dep->grid_min; g.dep_max = dep->grid_max;
+        CK(cx().dep.reserve((size_t)nb));
+        cx().dep_bins = nb; cx().dep_min = dep->grid_min; cx().dep_max = dep->grid_max;
         set_dep_scale();
-        CK(cudaMemsetAsync(g.dep.p, 0, (size_t)nb * sizeof(unsigned long long), g.stream));
-        if (g.res_nray > 0) {
-            const unsigned grid = (unsigned)((g.res_nray + 127) / 128);
-            const DepBins bins{g.dep.p, nb, dep->grid_min, dep->grid_max, g.dep_scale};
+        CK(cudaMemsetAsync(cx().dep.p, 0, (size_t)nb * sizeof(unsigned long long), cx().stream));
+        if (cx().res_nray > 0) {
+            const unsigned grid = (unsigned)((cx().res_nray + 127) / 128);
+            const DepBins bins{cx().dep.p, nb, dep->grid_min, dep->grid_max, cx().dep_scale};
             if (c.equilib_model == RAYS_EQ_SLAB)
-                deposition_kernel<RAYS_EQ_SLAB><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, bins);
+                deposition_kernel<RAYS_EQ_SLAB><<<grid, 128, 0, cx().stream>>>(cx().res_nray, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, cx().pwr.p, bins);
             else
-                deposition_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 128, 0, g.stream>>>(g.res_nray, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, g.pwr.p, bins);
+                deposition_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 128, 0, cx().stream>>>(cx().res_nray, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, cx().pwr.p, bins);
             CK(cudaGetLastError());
         }
     }
     std::vector<long long> h((size_t)nb);
-    CK(cudaMemcpyAsync(h.data(), g.dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
-    if (d_acc_out) CK(cudaMemcpyAsync(d_acc_out, g.dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToDevice, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    const double u = 1.0 / g.dep_scale;   // a power of two: the conversions below are exact scalings
+    CK(cudaMemcpyAsync(h.data(), cx().dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToHost, cx().stream));
+    if (d_acc_out) CK(cudaMemcpyAsync(d_acc_out, cx().dep.p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToDevice, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    const double u = 1.0 / cx().dep_scale;   // a power of two: the conversions below are exact scalings
     long long q = 0;
     for (int b = 0; b < nb; ++b) {
         if (dep->profile) dep->profile[b] = (double)h[(size_t)b] * u;
@@ -1249,90 +1295,318 @@ int rays_b200_deposition(rays_deposition *dep, double *d_profile_out) {
     if (rc || !d_profile_out) return rc;
     std::vector<double> h((size_t)dep->n_bins + 1);   // this GPU's partial profile + Q_sum as doubles (exact: power-of-two unit)
     std::vector<long long> raw((size_t)dep->n_bins);
-    CK(cudaMemcpyAsync(raw.data(), g.dep.p, raw.size() * sizeof(long long), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    for (int b = 0; b < dep->n_bins; ++b) h[(size_t)b] = (double)raw[(size_t)b] / g.dep_scale;
+    CK(cudaMemcpyAsync(raw.data(), cx().dep.p, raw.size() * sizeof(long long), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    for (int b = 0; b < dep->n_bins; ++b) h[(size_t)b] = (double)raw[(size_t)b] / cx().dep_scale;
     h[(size_t)dep->n_bins] = dep->Q_sum;
-    CK(cudaMemcpyAsync(d_profile_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(d_profile_out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     return 0;
 }
 int rays_b200_deposition_fixed(rays_deposition *dep, int64_t *acc_out, void *d_acc_out, double *unit) { return deposition_impl(dep, acc_out, d_acc_out, unit); }
 int rays_b200_deposition_set_total_weight(double total_weight) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
     if (!(total_weight >= 0.0)) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: total weight must be >= 0");
-    g.fan_weight = total_weight;
+    cx().fan_weight = total_weight;
     return 0;
 }
 
 int rays_b200_summaries_pack(void *d_out, int64_t rows_capacity, int64_t *rows, int32_t *row_doubles) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (rows) *rows = g.res_nray;
-    if (row_doubles) *row_doubles = 6 + 2 * g.res_nv;
+    if (rows) *rows = cx().res_nray;
+    if (row_doubles) *row_doubles = 6 + 2 * cx().res_nv;
     if (!d_out) return 0;
-    if (rows_capacity < g.res_nray) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_summaries_pack: output smaller than the last trace");
-    CK(cudaSetDevice(g.device));
-    if (g.res_nray > 0) {
-        pack_summaries_kernel<<<(unsigned)((g.res_nray + 255) / 256), 256, 0, g.stream>>>(g.res_nray, g.res_nv, g.npoints.p, g.stop.p, g.pwr.p, g.endres.p, g.maxres.p,
-                                                                                             g.endpar.p, g.startv.p, g.endv.p, (double *)d_out);
+    if (rows_capacity < cx().res_nray) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_summaries_pack: output smaller than the last trace");
+    CK(cudaSetDevice(cx().device));
+    if (cx().res_nray > 0) {
+        pack_summaries_kernel<<<(unsigned)((cx().res_nray + 255) / 256), 256, 0, cx().stream>>>(cx().res_nray, cx().res_nv, cx().npoints.p, cx().stop.p, cx().pwr.p, cx().endres.p, cx().maxres.p,
+                                                                                             cx().endpar.p, cx().startv.p, cx().endv.p, (double *)d_out);
         CK(cudaGetLastError());
     }
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(cx().stream));
+    return 0;
+}
+
+// ======================= one host process, several GPUs ==========================================================
+// program rays is a single process (RAYS_code/RAYS.f90:9-15), so the library drives the GPUs of the box itself: one context and
+// one host worker thread per GPU, the fan sharded iray mod ngpu (ray length varies smoothly along the launch loops),
+// no traffic during integration; afterwards ONE ncclReduce of the fixed-point deposition bins and ONE ncclAllGather of the packed
+// per-ray summaries over an NCCL communicator created with ncclCommInitAll.  NCCL is loaded with dlopen (libnccl.so.2 of the
+// image, or the one already mapped into the process), so a single-GPU host needs no NCCL at all.
+}  // extern "C"
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+} nccl;
+constexpr int kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;   // nccl.h: ncclDataType_t / ncclRedOp_t
+struct MultiCtx {
+    int n = 0;
+    void *comm[kMaxGpus] = {};
+    DevBuf<long long> acc[kMaxGpus];      // per GPU: its fixed-point bins (GPU 0: the reduced profile)
+    DevBuf<double> summ[kMaxGpus], gathered[kMaxGpus];
+    long long gathered_rows_per_gpu = 0;
+    int gathered_row_doubles = 0;
+} mg;
+
+int load_nccl() {
+    if (nccl.h) return 0;
+    const char *cands[] = {getenv("RAYS_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *c : cands) { if (c && c[0] && (h = dlopen(c, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!h) return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init_multi: cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+    auto sym = [&](const char *n) { return dlsym(h, n); };
+    nccl.CommInitAll = (int (*)(void **, int, const int *))sym("ncclCommInitAll");
+    nccl.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+    nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    nccl.Reduce = (int (*)(const void *, void *, size_t, int, int, int, void *, cudaStream_t))sym("ncclReduce");
+    nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))sym("ncclAllGather");
+    nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    if (!nccl.CommInitAll || !nccl.CommDestroy || !nccl.GroupStart || !nccl.GroupEnd || !nccl.Reduce || !nccl.AllGather)
+        return set_err(RAYS_ERR_CUDA, "rays_b200_init_multi: NCCL library lacks a required symbol");
+    nccl.h = h;
+    return 0;
+}
+#define NCK(call)                                                                                                   \
+    do {                                                                                                            \
+        int r_ = (call);                                                                                            \
+        if (r_ != 0) return set_err(RAYS_ERR_CUDA, std::string(#call) + ": " + (nccl.GetErrorString ? nccl.GetErrorString(r_) : "NCCL error")); \
+    } while (0)
+
+// run fn(gpu) on one host thread per GPU, each with its GPU's context current; returns the first non-zero status
+template <class F> int on_every_gpu(F fn) {
+    std::vector<int> rc((size_t)mg.n, 0);
+    std::vector<std::string> err((size_t)mg.n);
+    std::vector<std::thread> th;
+    for (int i = 0; i < mg.n; ++i)
+        th.emplace_back([&, i] {
+            g_cur = &g_ctx[i];
+            cudaSetDevice(g_ctx[i].device);
+            rc[(size_t)i] = fn(i);
+            if (rc[(size_t)i]) err[(size_t)i] = g_err;
+        });
+    for (auto &t : th) t.join();
+    for (int i = 0; i < mg.n; ++i)
+        if (rc[(size_t)i]) return set_err(rc[(size_t)i], "GPU " + std::to_string(i) + ": " + err[(size_t)i]);
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int rays_b200_init_multi(int ngpu) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(RAYS_ERR_CUDA, std::string("rays_b200_init_multi: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    int n = ngpu <= 0 ? ndev : ngpu;
+    if (n > ndev) return set_err(RAYS_ERR_CUDA, "rays_b200_init_multi: more GPUs requested than visible");
+    if (n > kMaxGpus) n = kMaxGpus;
+    if (mg.n == n && mg.comm[0]) return 0;
+    Ctx *keep = g_cur;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; ++i) { g_cur = &g_ctx[i]; rc = rays_b200_init(i); }
+    g_cur = keep;
+    if (rc) return rc;
+    mg.n = n;
+    if (n > 1) {
+        if ((rc = load_nccl())) return rc;
+        int devs[kMaxGpus];
+        for (int i = 0; i < n; ++i) devs[i] = i;
+        NCK(nccl.CommInitAll(mg.comm, n, devs));
+    }
+    CK(cudaSetDevice(g_ctx[0].device));
+    return 0;
+}
+int rays_b200_ngpu(void) { return mg.n > 0 ? mg.n : (g_ctx[0].inited ? 1 : 0); }
+
+// trace_rays over every GPU of rays_b200_init_multi: GPU g integrates rays g, g + n, g + 2n, ... of the fan and writes their
+// trajectories and summaries straight into the caller's arrays (rows g + i*n); optionally binning the deposition while tracing
+static int trace_multi_impl(const rays_cfg *cfg, const rays_fan *fan, rays_results *res, rays_deposition *dep) {
+    if (mg.n < 1) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_init_multi has not been called");
+    if (!cfg || !fan || !res) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace_multi: null argument");
+    const int n = mg.n;
+    const long long nray = fan->nray;
+    if (res->nray < nray) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace_multi: result arrays smaller than the fan");
+    const bool want_traj = res->ray_vec != nullptr || res->residual != nullptr;
+    if (dep && want_traj) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace_multi_binned: bins while tracing, without trajectory arrays (ray_vec = residual = NULL)");
+    if (dep && (dep->n_bins < 1 || !(dep->grid_max > dep->grid_min))) return set_err(RAYS_ERR_INVALID_CONFIG, "deposition: bad grid");
+    // page-lock pageable trajectory arrays ONCE for all GPUs (each worker would otherwise try to register the same range)
+    std::vector<void *> registered;
+    struct Unreg { std::vector<void *> &v; ~Unreg() { for (void *q : v) cudaHostUnregister(q); } } unreg{registered};
+    if (want_traj) {
+        const char *env = getenv("RAYS_B200_REGISTER_HOST");
+        double *arrs[2] = {res->ray_vec, res->residual};
+        const size_t bytes[2] = {(size_t)res->nray * res->npoints_alloc * res->nv * 8, (size_t)res->nray * res->npoints_alloc * 8};
+        for (int k = 0; k < 2; ++k) {
+            if (!arrs[k]) continue;
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, arrs[k]) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (at.type == cudaMemoryTypeUnregistered && !(env && env[0] == '0') && bytes[k] <= (size_t(1) << 30)) {
+                if (cudaHostRegister(arrs[k], bytes[k], cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) registered.push_back(arrs[k]);
+                else cudaGetLastError();
+            }
+        }
+    }
+    double wsum = 0.0;
+    if (fan->ray_pwr_wt) for (long long i = 0; i < nray; ++i) wsum += std::fabs(fan->ray_pwr_wt[i]);
+    std::vector<rays_results> part((size_t)n, *res);
+    std::vector<long long> steps((size_t)n, 0);
+    std::vector<double> ms((size_t)n, 0.0);
+    int rc = on_every_gpu([&](int g) -> int {
+        const long long m = nray > g ? (nray - g + n - 1) / n : 0;
+        std::vector<double> r((size_t)3 * std::max<long long>(m, 1)), k((size_t)3 * std::max<long long>(m, 1)), w((size_t)std::max<long long>(m, 1));
+        for (long long i = 0; i < m; ++i) {
+            const long long j = g + i * n;
+            for (int q = 0; q < 3; ++q) { r[(size_t)3 * i + q] = fan->rvec0[3 * j + q]; k[(size_t)3 * i + q] = fan->rindex_vec0[3 * j + q]; }
+            w[(size_t)i] = fan->ray_pwr_wt ? fan->ray_pwr_wt[j] : 0.0;
+        }
+        rays_fan f{m, r.data(), k.data(), w.data()};
+        RowMap rm; rm.row0 = g; rm.stride = n;
+        int e2;
+        if (!dep) {
+            if ((e2 = trace_host_impl(cfg, &f, &part[(size_t)g], rm))) return e2;
+        } else {   // fused binning: summaries to the host, bins stay on the GPU for the reduce
+            if ((e2 = rays_b200_set_config(cfg)) || (e2 = rays_b200_fan_upload(&f))) return e2;
+            cx().fan_weight = wsum;                      // the unit of the bins is the whole fan's, the same on every GPU
+            if ((e2 = rays_b200_trace_device_binned(dep->n_bins, dep->grid_min, dep->grid_max, 0))) return e2;
+            std::vector<int> codes((size_t)m);
+            if (m) CK(cudaMemcpyAsync(codes.data(), cx().stop.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+            if ((e2 = copy_small_results(&part[(size_t)g], 0, m, rm))) return e2;
+            CK(cudaStreamSynchronize(cx().stream));
+            fill_flags(&part[(size_t)g], codes, 0, rm);
+            part[(size_t)g].total_ray_steps = cx().last_steps;
+            part[(size_t)g].total_trace_time = cx().last_ms * 1e-3;
+            CK(mg.acc[g].reserve((size_t)dep->n_bins));
+            CK(cudaMemcpyAsync(mg.acc[g].p, cx().dep.p, (size_t)dep->n_bins * sizeof(long long), cudaMemcpyDeviceToDevice, cx().stream));
+            // packed summaries for the all-gather (rows padded to the largest shard)
+            const long long mmax = (nray + n - 1) / n;
+            const int rd = 6 + 2 * cx().res_nv;
+            CK(mg.summ[g].reserve((size_t)std::max<long long>(mmax, 1) * rd));
+            CK(cudaMemsetAsync(mg.summ[g].p, 0, (size_t)std::max<long long>(mmax, 1) * rd * sizeof(double), cx().stream));
+            if ((e2 = rays_b200_summaries_pack(mg.summ[g].p, mmax, nullptr, nullptr))) return e2;
+            if (n > 1) CK(mg.gathered[g].reserve((size_t)n * std::max<long long>(mmax, 1) * rd));
+            CK(cudaStreamSynchronize(cx().stream));
+        }
+        steps[(size_t)g] = part[(size_t)g].total_ray_steps;
+        ms[(size_t)g] = part[(size_t)g].total_trace_time;
+        return 0;
+    });
+    if (rc) return rc;
+    res->total_ray_steps = 0;
+    res->total_trace_time = 0.0;
+    for (int g = 0; g < n; ++g) { res->total_ray_steps += steps[(size_t)g]; res->total_trace_time = std::max(res->total_trace_time, ms[(size_t)g]); }
+    if (dep) {
+        const int nb = dep->n_bins;
+        const long long mmax = std::max<long long>((nray + n - 1) / n, 1);
+        const int rd = 6 + 2 * g_ctx[0].res_nv;
+        if (n > 1) {   // the two collectives of the run, one NCCL group over the GPUs of this process
+            NCK(nccl.GroupStart());
+            for (int g = 0; g < n; ++g) NCK(nccl.Reduce(mg.acc[g].p, mg.acc[g].p, (size_t)nb, kNcclInt64, kNcclSum, 0, mg.comm[g], g_ctx[g].stream));
+            NCK(nccl.GroupEnd());
+            NCK(nccl.GroupStart());
+            for (int g = 0; g < n; ++g) NCK(nccl.AllGather(mg.summ[g].p, mg.gathered[g].p, (size_t)mmax * rd, kNcclFloat64, mg.comm[g], g_ctx[g].stream));
+            NCK(nccl.GroupEnd());
+            for (int g = 0; g < n; ++g) { CK(cudaSetDevice(g_ctx[g].device)); CK(cudaStreamSynchronize(g_ctx[g].stream)); }
+        }
+        mg.gathered_rows_per_gpu = mmax; mg.gathered_row_doubles = rd;
+        CK(cudaSetDevice(g_ctx[0].device));
+        std::vector<long long> h((size_t)nb);
+        CK(cudaMemcpy(h.data(), mg.acc[0].p, (size_t)nb * sizeof(long long), cudaMemcpyDeviceToHost));
+        const double u = 1.0 / g_ctx[0].dep_scale;
+        long long q = 0;
+        for (int b = 0; b < nb; ++b) { if (dep->profile) dep->profile[b] = (double)h[(size_t)b] * u; q += h[(size_t)b]; }
+        dep->Q_sum = (double)q * u;
+    }
+    CK(cudaSetDevice(g_ctx[0].device));
+    return 0;
+}
+int rays_b200_trace_multi(const rays_cfg *cfg, const rays_fan *fan, rays_results *res) { return trace_multi_impl(cfg, fan, res, nullptr); }
+int rays_b200_trace_multi_binned(const rays_cfg *cfg, const rays_fan *fan, rays_results *res, rays_deposition *dep) {
+    if (!dep) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_trace_multi_binned: null deposition");
+    return trace_multi_impl(cfg, fan, res, dep);
+}
+// the all-gathered summaries on GPU `gpu` after rays_b200_trace_multi_binned: ngpu blocks of *rows_per_gpu rows (block g = the rays
+// g, g + ngpu, ... in order; rows past a shard's length are zero), *row_doubles doubles each (layout: rays_b200_summaries_pack)
+const double *rays_b200_multi_summaries(int gpu, int64_t *rows_per_gpu, int32_t *row_doubles) {
+    if (gpu < 0 || gpu >= mg.n) return nullptr;
+    if (rows_per_gpu) *rows_per_gpu = mg.gathered_rows_per_gpu;
+    if (row_doubles) *row_doubles = mg.gathered_row_doubles;
+    return mg.n > 1 ? mg.gathered[gpu].p : mg.summ[gpu].p;
+}
+int rays_b200_finalize_multi(void) {
+    Ctx *keep = g_cur;
+    for (int i = 0; i < mg.n; ++i) {
+        g_cur = &g_ctx[i];
+        if (g_ctx[i].inited) cudaSetDevice(g_ctx[i].device);
+        mg.acc[i].release(); mg.summ[i].release(); mg.gathered[i].release();
+        if (mg.comm[i] && nccl.CommDestroy) nccl.CommDestroy(mg.comm[i]);
+        mg.comm[i] = nullptr;
+        rays_b200_finalize();
+    }
+    g_cur = keep;
+    mg.n = 0;
     return 0;
 }
 
 // ======================= probes ==============================================================================
 static int run_probe(int which, int64_t n, const double *in, size_t in_per, double *out, size_t out_per, int32_t *code) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
     if (n <= 0) return 0;
-    CK(cudaSetDevice(g.device));
-    const TuOps *ops = tu_ops(g.dc.c.equilib_model, RAYS_ODE_RK4);
+    CK(cudaSetDevice(cx().device));
+    const TuOps *ops = tu_ops(cx().dc.c.equilib_model, RAYS_ODE_RK4);
     DevBuf<double> din, dout;
     DevBuf<int> dcode;
     CK(din.reserve((size_t)n * in_per)); CK(dout.reserve((size_t)n * out_per)); CK(dcode.reserve((size_t)n));
-    CK(cudaMemcpyAsync(din.p, in, (size_t)n * in_per * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(din.p, in, (size_t)n * in_per * sizeof(double), cudaMemcpyHostToDevice, cx().stream));
     cudaError_t e;
-    if (which == 0) e = ops->probe_equilibrium(g.sel, n, din.p, dout.p, dcode.p, g.stream);
-    else if (which == 1) e = ops->probe_rhs(g.sel, n, din.p, dout.p, dcode.p, g.stream);
-    else e = ops->probe_check_save(g.sel, n, din.p, dout.p, dcode.p, g.stream);
+    if (which == 0) e = ops->probe_equilibrium(cx().sel, n, din.p, dout.p, dcode.p, cx().stream);
+    else if (which == 1) e = ops->probe_rhs(cx().sel, n, din.p, dout.p, dcode.p, cx().stream);
+    else e = ops->probe_check_save(cx().sel, n, din.p, dout.p, dcode.p, cx().stream);
     CK(e);
-    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaMemcpyAsync(code, dcode.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)n * out_per * sizeof(double), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaMemcpyAsync(code, dcode.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     din.release(); dout.release(); dcode.release();
     return 0;
 }
 int rays_b200_probe_equilibrium(int64_t n, const double *rvec, double *out, int32_t *err) { return run_probe(0, n, rvec, 3, out, RAYS_EQ_OUT, err); }
 int rays_b200_probe_rhs(int64_t n, const double *v, double *dvds, int32_t *stop) {
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    return run_probe(1, n, v, (size_t)g.dc.c.nv, dvds, (size_t)g.dc.c.nv, stop);
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    return run_probe(1, n, v, (size_t)cx().dc.c.nv, dvds, (size_t)cx().dc.c.nv, stop);
 }
 int rays_b200_probe_check_save(int64_t n, const double *v, double *resid, int32_t *stop) {
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
-    return run_probe(2, n, v, (size_t)g.dc.c.nv, resid, 1, stop);
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    return run_probe(2, n, v, (size_t)cx().dc.c.nv, resid, 1, stop);
 }
 
 // ======================= O-X conversion analysis (row f4) ======================================================
 int rays_b200_ox_conv_analysis(rays_ox_conv *out, int64_t *n_converted) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    if (!g.cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
+    if (!cx().cfg_set) return set_err(RAYS_ERR_NOT_INITIALIZED, "rays_b200_set_config has not been called");
     if (!out) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_ox_conv_analysis: null output");
-    if (!g.have_traj || g.res_nray <= 0) return set_err(RAYS_ERR_INVALID_CONFIG, "analyze_OX_conv needs the trajectories of a stored device trace (trace_device with store)");
-    CK(cudaSetDevice(g.device));
-    const long long n = g.res_nray;
+    if (!cx().have_traj || cx().res_nray <= 0) return set_err(RAYS_ERR_INVALID_CONFIG, "analyze_OX_conv needs the trajectories of a stored device trace (trace_device with store)");
+    CK(cudaSetDevice(cx().device));
+    const long long n = cx().res_nray;
     rays_ox_conv *d_out = nullptr;
     CK(cudaMalloc(&d_out, sizeof(rays_ox_conv) * (size_t)n));
     const unsigned grid = (unsigned)((n + 63) / 64);
-    switch (g.dc.c.equilib_model) {
-        case RAYS_EQ_SLAB: ox_conv_kernel<RAYS_EQ_SLAB><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
-        case RAYS_EQ_SOLOVEV: ox_conv_kernel<RAYS_EQ_SOLOVEV><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
-        case RAYS_EQ_AXISYM_TOROID: ox_conv_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
-        default: ox_conv_kernel<RAYS_EQ_MULTIPLE_MIRROR><<<grid, 64, 0, g.stream>>>(n, g.res_nv, g.res_npa, g.ray_vec.p, g.npoints.p, d_out); break;
+    switch (cx().dc.c.equilib_model) {
+        case RAYS_EQ_SLAB: ox_conv_kernel<RAYS_EQ_SLAB><<<grid, 64, 0, cx().stream>>>(n, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, d_out); break;
+        case RAYS_EQ_SOLOVEV: ox_conv_kernel<RAYS_EQ_SOLOVEV><<<grid, 64, 0, cx().stream>>>(n, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, d_out); break;
+        case RAYS_EQ_AXISYM_TOROID: ox_conv_kernel<RAYS_EQ_AXISYM_TOROID><<<grid, 64, 0, cx().stream>>>(n, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, d_out); break;
+        default: ox_conv_kernel<RAYS_EQ_MULTIPLE_MIRROR><<<grid, 64, 0, cx().stream>>>(n, cx().res_nv, cx().res_npa, cx().ray_vec.p, cx().npoints.p, d_out); break;
     }
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(rays_ox_conv) * (size_t)n, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(rays_ox_conv) * (size_t)n, cudaMemcpyDeviceToHost, cx().stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cx().stream);
     cudaFree(d_out);
     CK(e);
     int64_t nc = 0;
@@ -1349,7 +1623,7 @@ int rays_b200_mirror_brz_grid(const rays_coil *coils, int32_t n_coils, int32_t n
     for (int i = 0; i < n_coils; ++i)
         if (coils[i].n_r_layers < 1 || coils[i].n_z_slices < 1 || !(coils[i].inner_radius > 0.0) || !(coils[i].outer_radius >= coils[i].inner_radius))
             return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_mirror_brz_grid: coil needs n_r_layers, n_z_slices >= 1 and 0 < inner_radius <= outer_radius");
-    CK(cudaSetDevice(g.device));
+    CK(cudaSetDevice(cx().device));
     // grids exactly as calculate_B_on_rz_grid forms them (mirror_magnetics_m.f90:340-356)
     std::vector<double> rg((size_t)n_r), zg((size_t)n_z);
     if (n_r == 1) rg[0] = r_min; else for (int i = 1; i <= n_r; ++i) rg[(size_t)i - 1] = r_min + (r_max - r_min) * (i - 1) / (n_r - 1);
@@ -1363,17 +1637,17 @@ int rays_b200_mirror_brz_grid(const rays_coil *coils, int32_t n_coils, int32_t n
     rays_coil *d_coils = nullptr;
     CK(d_r.reserve((size_t)n_r)); CK(d_z.reserve((size_t)n_z)); CK(d_out.reserve(3 * n));
     CK(cudaMalloc(&d_coils, sizeof(rays_coil) * (size_t)n_coils));
-    cudaError_t e = cudaMemcpyAsync(d_coils, coils, sizeof(rays_coil) * (size_t)n_coils, cudaMemcpyHostToDevice, g.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r.p, rg.data(), sizeof(double) * (size_t)n_r, cudaMemcpyHostToDevice, g.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_z.p, zg.data(), sizeof(double) * (size_t)n_z, cudaMemcpyHostToDevice, g.stream);
+    cudaError_t e = cudaMemcpyAsync(d_coils, coils, sizeof(rays_coil) * (size_t)n_coils, cudaMemcpyHostToDevice, cx().stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r.p, rg.data(), sizeof(double) * (size_t)n_r, cudaMemcpyHostToDevice, cx().stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_z.p, zg.data(), sizeof(double) * (size_t)n_z, cudaMemcpyHostToDevice, cx().stream);
     if (e == cudaSuccess) {
-        mirror_Brz_grid_kernel<<<(unsigned)((n + 63) / 64), 64, 0, g.stream>>>(d_coils, n_coils, K, n_r, n_z, d_r.p, d_z.p, d_out.p, d_out.p + n, d_out.p + 2 * n);
+        mirror_Brz_grid_kernel<<<(unsigned)((n + 63) / 64), 64, 0, cx().stream>>>(d_coils, n_coils, K, n_r, n_z, d_r.p, d_z.p, d_out.p, d_out.p + n, d_out.p + 2 * n);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(Br, d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(Bz, d_out.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(Aphi, d_out.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Br, d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, cx().stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Bz, d_out.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, cx().stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Aphi, d_out.p + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, cx().stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cx().stream);
     cudaFree(d_coils);
     d_r.release(); d_z.release(); d_out.release();
     CK(e);
@@ -1385,21 +1659,21 @@ int rays_b200_mirror_brz_grid(const rays_coil *coils, int32_t n_coils, int32_t n
 // ======================= measurement helpers =================================================================
 int rays_b200_fp64_peak(double *tflops, double *sm_mhz) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    CK(cudaSetDevice(g.device));
-    const int threads = 256, blocks = g.num_sms * 8, iters = 1 << 16;
+    CK(cudaSetDevice(cx().device));
+    const int threads = 256, blocks = cx().num_sms * 8, iters = 1 << 16;
     DevBuf<double> out;
     CK(out.reserve((size_t)threads * blocks));
-    fp64_peak_kernel<<<blocks, threads, 0, g.stream>>>(out.p, 1024, 1.0000001, 1e-9);   // warm-up
+    fp64_peak_kernel<<<blocks, threads, 0, cx().stream>>>(out.p, 1024, 1.0000001, 1e-9);   // warm-up
     CK(cudaGetLastError());
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
-        CK(cudaEventRecord(g.ev0, g.stream));
-        fp64_peak_kernel<<<blocks, threads, 0, g.stream>>>(out.p, iters, 1.0000001, 1e-9);
+        CK(cudaEventRecord(cx().ev0, cx().stream));
+        fp64_peak_kernel<<<blocks, threads, 0, cx().stream>>>(out.p, iters, 1.0000001, 1e-9);
         CK(cudaGetLastError());
-        CK(cudaEventRecord(g.ev1, g.stream));
-        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaEventRecord(cx().ev1, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+        CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
         const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
@@ -1407,7 +1681,7 @@ int rays_b200_fp64_peak(double *tflops, double *sm_mhz) {
     if (tflops) *tflops = best;
     if (sm_mhz) {
         int khz = 0;
-        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, cx().device);
         *sm_mhz = khz / 1000.0;   // maximum SM clock; bench.py samples the clock under load with nvidia-smi
     }
     return 0;
@@ -1418,17 +1692,17 @@ int rays_b200_fp64_peak(double *tflops, double *sm_mhz) {
 // mismatch[3] = reciprocals of all-ones-significand divisors that are 1 ulp off (the documented exception)
 int rays_b200_selftest_arith(int64_t n, uint64_t seed, int64_t *mismatch) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    CK(cudaSetDevice(g.device));
+    CK(cudaSetDevice(cx().device));
     DevBuf<unsigned long long> d;
     CK(d.reserve(4));
-    CK(cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), g.stream));
-    const int threads = 256, blocks = g.num_sms * 4;
+    CK(cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), cx().stream));
+    const int threads = 256, blocks = cx().num_sms * 4;
     const int per_thread = (int)std::max<int64_t>(1, n / ((int64_t)threads * blocks));
-    selftest_arith_kernel<<<blocks, threads, 0, g.stream>>>(seed, per_thread, d.p);
+    selftest_arith_kernel<<<blocks, threads, 0, cx().stream>>>(seed, per_thread, d.p);
     CK(cudaGetLastError());
     unsigned long long h[4];
-    CK(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, cx().stream));
+    CK(cudaStreamSynchronize(cx().stream));
     d.release();
     for (int i = 0; i < 4; ++i) mismatch[i] = (int64_t)h[i];
     return 0;
@@ -1437,7 +1711,7 @@ int rays_b200_selftest_arith(int64_t n, uint64_t seed, int64_t *mismatch) {
 // pinned host memory for result arrays (so the trajectory copy-out runs at full PCIe rate)
 int rays_b200_host_alloc(void **p, size_t bytes) {
     if (need_init()) return RAYS_ERR_NOT_INITIALIZED;
-    CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc(p, bytes, cudaHostAllocPortable | cudaHostAllocMapped));   // usable from every GPU of rays_b200_init_multi
     return 0;
 }
 int rays_b200_host_free(void *p) {

@@ -451,3 +451,30 @@ def test_summaries_pack_matches_the_downloaded_summaries():
     assert np.array_equal(h[:, 0], res.npoints) and np.array_equal(h[:, 1], res.ray_stop_code)
     assert np.array_equal(h[:, 2], res.initial_ray_power) and np.array_equal(h[:, 5], res.end_ray_parameter, equal_nan=True)
     assert np.array_equal(h[:, 6:6 + nv], res.start_ray_vec, equal_nan=True) and np.array_equal(h[:, 6 + nv:], res.end_ray_vec, equal_nan=True)
+
+
+def test_trace_multi_one_process_all_gpus():
+    """rays_b200_init_multi / rays_b200_trace_multi (one host process drives every visible GPU, rays iray % ngpu): the caller's arrays
+    receive exactly what the single-GPU call delivers; the binned variant's NCCL-reduced profile equals the single-GPU fixed-point one"""
+    ngpu = rb.init_multi(0)
+    assert ngpu >= 1
+    cfg = init_case("solovev_fan_1M.in", nstep_max=150)
+    r, n, w, _, _ = oracle_fan(cfg, n_r_launch=2, n_theta_launch=4, n_rindex_theta=16, n_rindex_phi=16, dtheta_launch=0.2,
+                               delta_rindex_theta=0.025, delta_rindex_phi=0.02)
+    g1 = rb.trace(cfg, r, n, w)
+    gm = rb.trace_multi(cfg, r, n, w)
+    assert np.array_equal(gm.npoints, g1.npoints) and np.array_equal(gm.ray_stop_code, g1.ray_stop_code) and gm.ray_stop_flag == g1.ray_stop_flag
+    assert np.array_equal(gm.ray_vec, g1.ray_vec, equal_nan=True) and np.array_equal(gm.residual, g1.residual, equal_nan=True)
+    assert np.array_equal(gm.end_ray_vec, g1.end_ray_vec, equal_nan=True) and np.array_equal(gm.start_ray_vec, g1.start_ray_vec, equal_nan=True)
+    assert gm.total_ray_steps == g1.total_ray_steps
+    # config 5 in small: fused binning on every GPU + ncclReduce (int64) + ncclAllGather of the summaries
+    cfg = init_case("axisym_deposition_fan.in", nstep_max=300)
+    r, n, w, _, _ = oracle_fan(cfg, n_rindex_theta=48, delta_rindex_theta=0.4 / 47, n_rindex_phi=48, delta_rindex_phi=0.35 / 47)
+    res, prof, q = rb.trace_multi(cfg, r, n, w, bins=(501, 0.0, 1.0))
+    rb.set_config(cfg)
+    rb.fan_upload(r, n, w)
+    rb.trace_device(store=False, bins=(501, 0.0, 1.0))
+    acc, unit, p1, q1 = rb.deposition_fixed(501, 0.0, 1.0)
+    assert np.array_equal(prof, p1) and q == q1, "the reduced profile does not depend on the number of GPUs"
+    s1 = rb.results_download(r.shape[0], int(cfg.nv), int(cfg.nstep_max) + 1, store=False)
+    assert np.array_equal(res.npoints, s1.npoints) and np.array_equal(res.end_ray_vec, s1.end_ray_vec, equal_nan=True)
