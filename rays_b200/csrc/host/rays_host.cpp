@@ -956,7 +956,7 @@ int rays_host_write_deposition_profiles(const char *outdir, int n_profiles, cons
         return fail("write_deposition_profiles_NC: bad arguments");
     State &S = *g;
     NcWriter w;
-    const int d_prof = w.def_dim("n_profiles", 0);          // NF90_UNLIMITED
+    const int d_prof = w.def_unlimited_dim("n_profiles");   // NF90_UNLIMITED
     const int d_bins = w.def_dim("n_bins", n_bins);
     const int d_bp1 = w.def_dim("n_bins_p1", n_bins + 1);
     const int d20 = w.def_dim("d20", 20);
@@ -1073,6 +1073,7 @@ int rays_host_finalize_run(const char *outdir) {
     const int nv = r.nv, np = r.max_number_of_points;
     int amax = 0;
     for (int64_t i = 0; i < nray; ++i) amax = std::max(amax, (int)r.npoints[i]);  // actual_max_npoints
+    if (nray < 1 || amax < 1) return fail("write_results_NC: no rays to write (number_of_rays = 0): the classic format has no zero-length fixed dimension");
     NcWriter w;
     int d_rays = w.def_dim("number_of_rays", nray);
     int d_pts = w.def_dim("max_number_of_points", amax);

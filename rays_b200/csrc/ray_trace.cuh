@@ -637,11 +637,8 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 }
 
 constexpr int kTraceBlock = 128;
-// Shampine-Gordon slot machine (ray_trace_sg2.cuh): every warp of a CTA owns kSgSlots ray slots
-#ifndef RAYS_SG_SLOTS
-#define RAYS_SG_SLOTS 64
-#endif
-constexpr int kSgSlots = RAYS_SG_SLOTS;
+// Shampine-Gordon slot machine (ray_trace_sg2.cuh): a CTA owns kSgSlots ray slots, two per thread
+constexpr int kSgSlots = 2 * kTraceBlock;
 constexpr int kSgWarps = kTraceBlock / 32;
 constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, resid_prev/last/max, dep_x, dep_Q, rel_err, abs_err
 

@@ -24,7 +24,7 @@
 namespace rays_dev {
 
 // kSgSlots (slots per warp, 32 < kSgSlots <= 64: lane l keeps the books of slots l and l + 32) and kSgWarps: ray_trace.cuh
-static_assert(kSgSlots > 32 && kSgSlots <= 64, "a lane keeps the kinds of two slots");
+static_assert(kSgSlots == 2 * kTraceBlock, "a thread keeps the kinds of two slots");
 
 enum SgKind : int { K_IDLE = 0, K_PRED, K_CORR, K_CHECK, K_START, K_BEGIN, K_FIN };
 enum SgBits : int { B_FIRST = 1, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
@@ -374,6 +374,212 @@ template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double
     for (int l = 0; l < NV; ++l) if (l < neqn) W.v(l) = W.yy(l) + hi * yo[l];
 }
 
+// ---- register-resident fast path: order k <= kSgKM, no propagated-roundoff control (99.95 % of the internal steps of the bench
+// fans).  The live state of the slot is loaded in one burst (independent loads: one memory latency instead of one per loop
+// iteration), the statements of sg2_predict / sg2_after_predict / sg2_after_correct run on register arrays with loops bounded by
+// the compile-time kSgKM and predicated on the run-time k / ns (same operations on the same operands in the same order, so the
+// results are the general path's bit for bit; tests compare the two), and the modified state is stored in one burst.
+constexpr int kSgKM = 3;
+#define SG3_FOR(i, lo, hi) _Pragma("unroll") for (int i = (lo); i <= (hi); ++i)
+#define SG3_L(l) _Pragma("unroll") for (int l = 0; l < NV; ++l)
+
+template <int NV> RD_INLINE void sg3_predict(const SgSlot<NV> &W, double (&p)[NV]) {
+    using L = SgLayout<NV>;
+    constexpr int KM = kSgKM;
+    const int k = W.i(L::K), kold = W.i(L::KOLD);
+    int ns = W.i(L::NS);
+    const double h = W.f(L::H), hold = W.f(L::HOLD), x = W.f(L::X);
+    const int kp1 = k + 1, kp2 = k + 2;
+    double psi[KM + 2], alpha[KM + 2], beta[KM + 2], sig[KM + 3], vv[KM + 3], ww[KM + 3], g[KM + 3];
+    double phi[KM + 3][NV], yy[NV];
+    SG3_FOR(i, 1, KM) { psi[i] = W.psi(i); alpha[i] = W.alpha(i); beta[i] = W.beta(i); vv[i] = W.vv(i); }
+    SG3_FOR(i, 1, KM + 1) { sig[i] = W.sig(i); g[i] = W.g(i); }
+    SG3_FOR(i, 1, KM + 1) SG3_L(l) phi[i][l] = W.phi(i, l);
+    SG3_L(l) yy[l] = W.yy(l);
+    vv[KM + 1] = 0.0; ww[KM + 1] = 0.0; ww[KM + 2] = 0.0; sig[KM + 2] = 0.0; g[KM + 2] = 0.0; psi[KM + 1] = 0.0; alpha[KM + 1] = 0.0; beta[KM + 1] = 0.0;
+    SG3_FOR(i, 1, KM) ww[i] = 0.0;
+    if (h != hold) ns = 0;
+    if (ns <= kold) ns = ns + 1;
+    const int nsp1 = ns + 1;
+    if (ns <= k) {
+        SG3_FOR(i, 1, KM) if (i == ns) { beta[i] = 1.0; alpha[i] = kSGinv[i]; }
+        double temp1 = h * (double)ns;
+        SG3_FOR(i, 2, KM + 1) if (i == nsp1) sig[i] = 1.0;
+        SG3_FOR(i, 2, KM) if (i >= nsp1 && i <= k) {
+            const double temp2 = psi[i - 1];
+            psi[i - 1] = temp1;
+            beta[i] = sg_div(beta[i - 1] * psi[i - 1], temp2);
+            temp1 = temp2 + h;
+            alpha[i] = sg_div(h, temp1);
+            sig[i + 1] = (double)i * alpha[i] * sig[i];
+        }
+        SG3_FOR(i, 1, KM) if (i == k) psi[i] = temp1;
+        if (ns <= 1) {
+            SG3_FOR(iq, 1, KM) if (iq <= k) { vv[iq] = kSGinvTri[iq]; ww[iq] = vv[iq]; }
+        } else {
+            if (kold < k) {
+                SG3_FOR(i, 1, KM) if (i == k) vv[i] = kSGinvTri[i];
+                SG3_FOR(j, 1, KM - 1) if (j <= ns - 2) {       // i = k - j: v(i) = v(i) - alpha(j+1)*v(i+1)
+                    SG3_FOR(i, 1, KM - 1) if (i == k - j) vv[i] = vv[i] - alpha[j + 1] * vv[i + 1];
+                }
+            }
+            double alns = 0.0;
+            SG3_FOR(i, 1, KM) if (i == ns) alns = alpha[i];
+            SG3_FOR(iq, 1, KM) if (iq <= kp1 - ns) { vv[iq] = vv[iq] - alns * vv[iq + 1]; ww[iq] = vv[iq]; }
+            SG3_FOR(i, 2, KM + 1) if (i == nsp1) g[i] = ww[1];
+        }
+        SG3_FOR(i, 3, KM + 1) if (i >= ns + 2 && i <= kp1) {
+            SG3_FOR(iq, 1, KM) if (iq <= kp2 - i) ww[iq] = ww[iq] - alpha[i - 1] * ww[iq + 1];
+            g[i] = ww[1];
+        }
+    }
+    SG3_FOR(i, 2, KM) if (i >= nsp1 && i <= k) SG3_L(l) phi[i][l] = beta[i] * phi[i][l];
+    double up[NV];
+    SG3_L(l) { p[l] = 0.0; up[l] = 0.0; }
+    // phi(kp2) = phi(kp1); phi(kp1) = 0
+    SG3_FOR(i, 2, KM + 1) if (i == kp1) SG3_L(l) { phi[i + 1][l] = phi[i][l]; phi[i][l] = 0.0; }
+    _Pragma("unroll") for (int i = KM; i >= 1; --i) if (i <= k) {
+        SG3_L(l) {
+            const double f = phi[i][l];
+            p[l] = p[l] + f * g[i];
+            up[l] = f + up[l];
+            phi[i][l] = up[l];
+        }
+    }
+    SG3_L(l) p[l] = yy[l] + h * p[l];
+    // burst store of what changed
+    W.i(L::NS) = ns;
+    SG3_FOR(i, 1, KM) if (i <= k) { W.psi(i) = psi[i]; W.alpha(i) = alpha[i]; W.beta(i) = beta[i]; W.vv(i) = vv[i]; }
+    SG3_FOR(i, 1, KM + 1) if (i <= kp1) { W.sig(i) = sig[i]; W.g(i) = g[i]; }
+    SG3_FOR(i, 1, KM + 2) if (i <= kp2) SG3_L(l) W.phi(i, l) = phi[i][l];
+    W.f(L::XOLD) = x;
+    W.f(L::X) = x + h;
+    W.f(L::ABSH) = fabs(h);
+}
+
+template <int NV> RD_INLINE int sg3_after_predict(const SgSlot<NV> &W, double &eps, int &bits, const double (&p)[NV], const double (&yp)[NV]) {
+    using L = SgLayout<NV>;
+    constexpr int KM = kSgKM;
+    const double fouru = 4.0 * DBL_EPSILON;
+    const int k = W.i(L::K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
+    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), xold = W.f(L::XOLD);
+    const int ifail0 = W.i(L::IFAIL);
+    double sig[KM + 2], g[KM + 2], beta[KM + 1], psi[KM + 1], wt[NV], phi[KM + 2][NV];
+    SG3_FOR(i, 1, KM + 1) { sig[i] = W.sig(i); g[i] = W.g(i); }
+    SG3_FOR(i, 1, KM) { beta[i] = W.beta(i); psi[i] = W.psi(i); }
+    SG3_L(l) wt[l] = W.wt(l);
+    SG3_FOR(i, 1, KM + 1) SG3_L(l) phi[i][l] = W.phi(i, l);
+    double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
+    double dl[NV];
+    SG3_L(l) {
+        const Rcp wl = rcp_of(wt[l]);   // up to three quotients by the same weight
+        const double ph1 = phi[1][l];
+        if (0 < km2) { const double q = sg_quot(phi[KM - 1][l] + yp[l] - ph1, wl); erkm2 = erkm2 + q * q; }   // k = KM = 3: km1 = 2
+        if (0 <= km2) { const double phk = k == 2 ? phi[2][l] : phi[KM][l]; const double q = sg_quot(phk + yp[l] - ph1, wl); erkm1 = erkm1 + q * q; }
+        dl[l] = yp[l] - ph1;
+        const double q = sg_quot(dl[l], wl);
+        erk = erk + q * q;
+    }
+    double sig_km1 = 0.0, sig_k = 0.0, sig_kp1 = 0.0, g_k = 0.0, g_kp1 = 0.0;
+    SG3_FOR(i, 1, KM + 1) { if (i == km1) sig_km1 = sig[i]; if (i == k) { sig_k = sig[i]; g_k = g[i]; } if (i == kp1) { sig_kp1 = sig[i]; g_kp1 = g[i]; } }
+    if (0 < km2) erkm2 = absh * sig_km1 * kSGgstr[km2] * sg_sqrt(erkm2);
+    if (0 <= km2) erkm1 = absh * sig_k * kSGgstr[km1] * sg_sqrt(erkm1);
+    const double rt_erk = sg_sqrt(erk);
+    const double err = absh * rt_erk * (g_k - g_kp1);
+    erk = absh * rt_erk * sig_kp1 * kSGgstr[k];
+    int knew = k;
+    if (0 < km2) {
+        if (fmax(erkm1, erkm2) <= erk) knew = km1;
+    } else if (0 == km2) {
+        if (erkm1 <= 0.5 * erk) knew = km1;
+    }
+    W.i(L::KNEW) = knew; W.f(L::ERK) = erk; W.f(L::ERKM1) = erkm1;
+    if (err <= eps) {   // accepted: correct (:1123-1141)
+        W.i(L::KOLD) = k;
+        W.f(L::HOLD) = h;
+        SG3_L(l) W.yy(l) = p[l] + h * g_kp1 * dl[l];
+        return 0;
+    }
+    // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
+    bits &= ~B_PHASE1;
+    W.f(L::X) = xold;
+    SG3_FOR(i, 1, KM) if (i <= k) {        // ascending: row i + 1 is still the unrestored one when row i reads it
+        const Rcp bi = rcp_of(beta[i]);
+        SG3_L(l) phi[i][l] = sg_quot(phi[i][l] - phi[i + 1][l], bi);
+    }
+    SG3_FOR(i, 2, KM) if (i <= k) psi[i - 1] = psi[i] - h;
+    SG3_FOR(i, 1, KM) if (i <= k) SG3_L(l) W.phi(i, l) = phi[i][l];
+    SG3_FOR(i, 1, KM - 1) if (i <= k - 1) W.psi(i) = psi[i];
+    const int ifail = ifail0 + 1;
+    W.i(L::IFAIL) = ifail;
+    double temp2 = 0.5;
+    if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sg_sqrt(sg_div(p5eps, erk)); }
+    if (3 <= ifail) knew = 1;
+    const double hn = temp2 * h;
+    W.i(L::K) = knew;
+    if (fabs(hn) < fouru * fabs(xold)) {
+        W.f(L::H) = copysign(fouru * fabs(xold), hn);
+        eps = eps + eps;
+        return 2;
+    }
+    W.f(L::H) = hn;
+    return 1;
+}
+
+template <int NV> RD_INLINE void sg3_after_correct(const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
+    using L = SgLayout<NV>;
+    constexpr int KM = kSgKM;
+    const double fouru = 4.0 * DBL_EPSILON;
+    int k = W.i(L::K);
+    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.i(L::KNEW), ns = W.i(L::NS);
+    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), erkm1 = W.f(L::ERKM1), x = W.f(L::X);
+    double erk = W.f(L::ERK);
+    double phi[KM + 3][NV], wt[NV];
+    SG3_FOR(i, 1, KM + 2) SG3_L(l) phi[i][l] = W.phi(i, l);
+    SG3_L(l) wt[l] = W.wt(l);
+    if (knew == km1 || k == 12) bits &= ~B_PHASE1;
+    const bool phase1 = (bits & B_PHASE1) != 0;
+    const bool want_erkp1 = !phase1 && knew != km1 && kp1 <= ns;
+    double erkp1 = 0.0;
+    SG3_L(l) {
+        const double d = yp[l] - phi[1][l];
+        double old2 = 0.0;
+        SG3_FOR(i, 3, KM + 2) if (i == kp2) old2 = phi[i][l];
+        const double e2 = d - old2;
+        SG3_FOR(i, 2, KM + 1) if (i == kp1) { phi[i][l] = d; phi[i + 1][l] = e2; }
+        SG3_FOR(i, 1, KM) if (i <= k) phi[i][l] = phi[i][l] + d;
+        if (want_erkp1) { const double q = sg_div(e2, wt[l]); erkp1 = erkp1 + q * q; }
+    }
+    SG3_FOR(i, 1, KM + 2) if (i <= kp2) SG3_L(l) W.phi(i, l) = phi[i][l];
+    if (phase1) {
+        k = kp1; erk = 0.0;
+    } else if (knew == km1) {
+        k = km1; erk = erkm1;
+    } else if (kp1 <= ns) {
+        erkp1 = absh * kSGgstr[kp1] * sg_sqrt(erkp1);
+        if (k == 1) {
+            if (erkp1 < 0.5 * erk) { k = kp1; erk = erkp1; }
+        } else if (erkm1 <= fmin(erk, erkp1)) {
+            k = km1; erk = erkm1;
+        } else if (erkp1 < erk && k < 12) {
+            k = kp1; erk = erkp1;
+        }
+    }
+    double hnew = h + h;
+    if (!phase1) {
+        if (p5eps < erk * kSGtwo[k + 1]) {
+            hnew = h;
+            if (p5eps < erk) {
+                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
+                hnew = absh * fmax(0.5, fmin((double)0.9f, r));
+                hnew = copysign(fmax(hnew, fouru * fabs(x)), h);
+            }
+        }
+    }
+    W.i(L::K) = k;
+    W.f(L::H) = hnew;
+}
+
 // streaming copy-out of one finished ray by the whole warp: out of line, it runs once per ray
 static RD_NOINLINE void sg2_flush_row(const TraceArgs &a, long long ir, int np, int pf, size_t rw, int nv, unsigned lane) {
     if (a.host_ray_vec)
@@ -382,9 +588,12 @@ static RD_NOINLINE void sg2_flush_row(const TraceArgs &a, long long ir, int np, 
         copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
 }
 
-template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgWarps * kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
+template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------------
+#ifndef RAYS_SG_FAST
+#define RAYS_SG_FAST 1
+#endif
 #ifndef RAYS_SG2_MIN_CTAS
 #define RAYS_SG2_MIN_CTAS 2
 #endif
@@ -392,73 +601,82 @@ template <class T>
 __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
-    constexpr int S = kSgSlots;
+    constexpr int S = kSgSlots;                 // slots per CTA: two per thread
+    constexpr int NT = kTraceBlock;
+    constexpr int NW = kSgWarps;
     using L = SgLayout<NV>;
     const int nv = T::nv();
     const rays_cfg &c = g_dc.c;
-    const unsigned lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31;
+    const int warp = tid >> 5;
     const int maxnum = 500;
     const double fouru = 4.0 * DBL_EPSILON;
-    __shared__ int s_kind_all[kSgWarps][S];
-    int *const s_kind = s_kind_all[warp];
-    const size_t gwarp = (size_t)blockIdx.x * kSgWarps + warp;                 // this warp's slot group
-    const size_t nwarps = (size_t)gridDim.x * kSgWarps;
-    double *const D = a.sg_state + gwarp * L::NDBL * S;
-    int *const I = reinterpret_cast<int *>(a.sg_state + nwarps * L::NDBL * S) + gwarp * L::NINT * S;
+    __shared__ int s_kind[S];
+    __shared__ int s_list[NT];
+    __shared__ int s_wcnt[NW][2][4];
+    __shared__ unsigned long long s_base;
+    const size_t gcta = blockIdx.x;
+    double *const D = a.sg_state + gcta * L::NDBL * S;
+    int *const I = reinterpret_cast<int *>(a.sg_state + (size_t)gridDim.x * L::NDBL * S) + gcta * L::NINT * S;
     const bool binning = a.dep_acc != nullptr && T::damp();
     const DepBins dbins = dep_begin(a, binning);
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
-    const bool own1 = (int)lane + 32 < S;      // this lane also keeps the books of slot lane + 32
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
     unsigned iter = 0;
-    bool exhausted = false;
-    s_kind[lane] = K_IDLE;
-    if (own1) s_kind[lane + 32] = K_IDLE;
-    __syncwarp();
+    bool exhausted = false;                     // CTA-uniform
+    s_kind[tid] = K_IDLE;
+    s_kind[tid + NT] = K_IDLE;
+    __syncthreads();
 
     for (;; ++iter) {
-        int k0 = s_kind[lane], k1 = own1 ? s_kind[lane + 32] : -1;
-        // ---- 1. rays that ended: streaming copy-out by the whole warp, the slot becomes idle
-        {
-            const unsigned f0 = __ballot_sync(0xffffffffu, k0 == K_FIN), f1 = __ballot_sync(0xffffffffu, k1 == K_FIN);
-            if (f0 | f1) {
-                if (streaming) {
-                    for (int half = 0; half < 2; ++half) {
-                        unsigned m = half ? f1 : f0;
-                        while (m) {
-                            const int sl = __ffs(m) - 1 + 32 * half;
-                            m &= m - 1;
-                            const SgSlot<NV> F{D + sl, I + sl};
-                            const long long ir = (long long)F.f(L::IRAY);
-                            const int np = F.i(L::FINNP), pf = F.i(L::P0);
-                            sg2_flush_row(a, ir, np, pf, gwarp * S + sl, nv, lane);
-                        }
+        // thread t keeps the books of slots t and t + NT
+        int k0 = s_kind[tid], k1 = s_kind[tid + NT];
+        // ---- 1. rays that ended: streaming copy-out by the warp that keeps the slot's books, the slot becomes idle
+        if (__syncthreads_or(k0 == K_FIN || k1 == K_FIN)) {
+            if (streaming) {
+                const unsigned f0 = __ballot_sync(0xffffffffu, k0 == K_FIN), f1 = __ballot_sync(0xffffffffu, k1 == K_FIN);
+                for (int half = 0; half < 2; ++half) {
+                    unsigned m = half ? f1 : f0;
+                    while (m) {
+                        const int sl = warp * 32 + __ffs(m) - 1 + NT * half;
+                        m &= m - 1;
+                        const SgSlot<NV> F{D + sl, I + sl};
+                        const long long ir = (long long)F.f(L::IRAY);
+                        const int np = F.i(L::FINNP), pf = F.i(L::P0);
+                        sg2_flush_row(a, ir, np, pf, gcta * S + sl, nv, lane);
                     }
                 }
-                if (k0 == K_FIN) k0 = K_IDLE;
-                if (k1 == K_FIN) k1 = K_IDLE;
             }
+            if (k0 == K_FIN) k0 = K_IDLE;
+            if (k1 == K_FIN) k1 = K_IDLE;
         }
-        // ---- 2. refill idle slots from the work queue: one atomic per warp
+        // ---- 2. refill idle slots from the work queue: one atomic per CTA
         if (!exhausted) {
             const unsigned w0 = __ballot_sync(0xffffffffu, k0 == K_IDLE), w1 = __ballot_sync(0xffffffffu, k1 == K_IDLE);
-            const int total = __popc(w0) + __popc(w1);
+            if (lane == 0) { s_wcnt[warp][0][0] = __popc(w0); s_wcnt[warp][1][0] = __popc(w1); }
+            __syncthreads();
+            int total = 0, before0 = 0, before1 = 0;     // slots are handed out in slot order: half 0 of every warp, then half 1
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { total += s_wcnt[w][0][0] + s_wcnt[w][1][0]; if (w < warp) { before0 += s_wcnt[w][0][0]; before1 += s_wcnt[w][1][0]; } }
+            int all0 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) all0 += s_wcnt[w][0][0];
             if (total > 0) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
+                if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
+                __syncthreads();
+                const unsigned long long base = s_base;
                 for (int half = 0; half < 2; ++half) {
                     const bool want = half ? (k1 == K_IDLE) : (k0 == K_IDLE);
                     const unsigned wb = half ? w1 : w0;
                     if (want) {
-                        const long long idx = (long long)(base + (unsigned long long)((half ? __popc(w0) : 0) + __popc(wb & ((1u << lane) - 1u))));
+                        const long long idx = (long long)(base + (unsigned long long)((half ? all0 + before1 : before0) + __popc(wb & ((1u << lane) - 1u))));
                         if (idx < a.nray) {
-                            const int sl = (int)lane + 32 * half;
+                            const int sl = tid + NT * half;
                             const SgSlot<NV> W{D + sl, I + sl};
                             const long long iray = a.order ? (long long)a.order[idx] : idx;
-                            const size_t row = streaming ? gwarp * S + sl : (size_t)iray;
+                            const size_t row = streaming ? gcta * S + sl : (size_t)iray;
                             W.f(L::IRAY) = (double)iray;
                             W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
                             W.i(L::SLICE) = 0;
@@ -493,9 +711,11 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                 if (base + (unsigned long long)total >= (unsigned long long)a.nray) exhausted = true;
             }
         }
-        // ---- 3. what do the slots of this warp need next?  Take the kind most of them wait for (restarts after a tolerance
-        // raise are rare and get their turn every 16th iteration), lane j takes the j-th slot of that kind
+        // ---- 3. what do the slots of this CTA need next?  The whole CTA takes the KIND most slots wait for (restarts after a
+        // tolerance raise are rare and get their turn every 16th iteration): thread j runs the j-th slot of that kind, so every
+        // warp executes the same code for about the same time
         int slot = -1;
+        int kind_q = 0;
         {
             unsigned b0[4], b1[4];
 #pragma unroll
@@ -504,24 +724,48 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                 b0[q] = __ballot_sync(0xffffffffu, k0 == kq || (q == 3 && k0 == K_BEGIN));
                 b1[q] = __ballot_sync(0xffffffffu, k1 == kq || (q == 3 && k1 == K_BEGIN));
             }
-            const int cP = __popc(b0[0]) + __popc(b1[0]), cC = __popc(b0[1]) + __popc(b1[1]), cK = __popc(b0[2]) + __popc(b1[2]), cR = __popc(b0[3]) + __popc(b1[3]);
-            if (cP + cC + cK + cR == 0 && exhausted) break;     // every slot idle, queue empty
-            int q = 0, best = cP;
-            if (cC > best) { q = 1; best = cC; }
-            if (cK > best) { q = 2; best = cK; }
-            if (cR > 0 && (best == 0 || (iter & 15u) == 0u)) q = 3;
+            __syncthreads();     // everybody is done with s_wcnt / s_base of step 2 and with s_list of the last iteration
+            if (lane < 4) { s_wcnt[warp][0][lane] = __popc(b0[lane]); s_wcnt[warp][1][lane] = __popc(b1[lane]); }
+            s_kind[tid] = k0;
+            s_kind[tid + NT] = k1;
+            __syncthreads();
+            int tot[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                tot[q] = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tot[q] += s_wcnt[w][0][q] + s_wcnt[w][1][q];
+            }
+            if (tot[0] + tot[1] + tot[2] + tot[3] == 0 && exhausted) break;     // every slot idle, queue empty
+            int q = 0, best = tot[0];
+            if (tot[1] > best) { q = 1; best = tot[1]; }
+            if (tot[2] > best) { q = 2; best = tot[2]; }
+            if (tot[3] > 0 && (best == 0 || (iter & 15u) == 0u)) q = 3;
+            kind_q = q;
+            // position of my slots among the slots of kind q, in slot order (half 0 of all warps first)
+            int bef0 = 0, bef1 = 0, allh0 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int c0 = q == 0 ? s_wcnt[w][0][0] : (q == 1 ? s_wcnt[w][0][1] : (q == 2 ? s_wcnt[w][0][2] : s_wcnt[w][0][3]));
+                const int c1 = q == 0 ? s_wcnt[w][1][0] : (q == 1 ? s_wcnt[w][1][1] : (q == 2 ? s_wcnt[w][1][2] : s_wcnt[w][1][3]));
+                allh0 += c0;
+                if (w < warp) { bef0 += c0; bef1 += c1; }
+            }
             const unsigned m0 = q == 0 ? b0[0] : (q == 1 ? b0[1] : (q == 2 ? b0[2] : b0[3]));
             const unsigned m1 = q == 0 ? b1[0] : (q == 1 ? b1[1] : (q == 2 ? b1[2] : b1[3]));
-            const int n0 = __popc(m0);
-            if ((int)lane < n0) slot = (int)__fns(m0, 0, (int)lane + 1);
-            else if ((int)lane - n0 < __popc(m1)) slot = 32 + (int)__fns(m1, 0, (int)lane - n0 + 1);
+            const unsigned below = (1u << lane) - 1u;
+            if (m0 & (1u << lane)) { const int pos = bef0 + __popc(m0 & below); if (pos < NT) s_list[pos] = tid; }
+            if (m1 & (1u << lane)) { const int pos = allh0 + bef1 + __popc(m1 & below); if (pos < NT) s_list[pos] = tid + NT; }
+            __syncthreads();
+            const int cnt_q = q == 0 ? tot[0] : (q == 1 ? tot[1] : (q == 2 ? tot[2] : tot[3]));
+            if (tid < (cnt_q < NT ? cnt_q : NT)) slot = s_list[tid];
         }
         // ---- 4. one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
         int next = -1;
-        const int ka = __shfl_sync(0xffffffffu, k0, slot & 31), kb = __shfl_sync(0xffffffffu, k1, slot & 31);   // kinds are kept by lane slot % 32
+        (void)kind_q;
         if (slot >= 0) {
             const SgSlot<NV> W{D + slot, I + slot};
-            const int kind = slot < 32 ? ka : kb;
+            const int kind = s_kind[slot];
             int bits = W.i(L::BITS);
             next = kind;
             int req = 0;   // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
@@ -531,11 +775,16 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
             int flag = W.i(L::FLAG);
             double eps = W.f(L::EPS);
             const long long iray = (long long)W.f(L::IRAY);
-            const size_t row = streaming ? gwarp * S + slot : (size_t)iray;
+            const size_t row = streaming ? gcta * S + slot : (size_t)iray;
             double uu[NV], ff[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) { uu[i] = 0.0; ff[i] = 0.0; }
-            if (kind == K_PRED) { sg2_predict<NV>(nv, W, bits, uu); req = 2; }
+            bool fastk = false;   // this macro-step runs the register-resident bookkeeping
+            if (kind == K_PRED) {
+                fastk = !T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND);
+                if (fastk) sg3_predict<NV>(W, uu); else sg2_predict<NV>(nv, W, bits, uu);
+                req = 2;
+            }
             else if (kind == K_CORR) req = 3;
             else if (kind == K_START) req = 1;
             else if (kind == K_BEGIN) enter = true;
@@ -638,12 +887,13 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                         if (code) { flag = code; W.f(L::SOUT) = W.f(L::S_); stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
                         else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits, ff); next = K_PRED; }
                         else if (req == 2) {
-                            const int r = sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
+                            const int r = fastk ? sg3_after_predict<NV>(W, eps, bits, uu, ff) : sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
                             if (r == 0) next = K_CORR;
                             else if (r == 1) next = K_PRED;   // failed: predict again with the reduced step
                             else crashed = true;
                         } else {
-                            sg2_after_correct<NV>(nv, W, eps, bits, ff);
+                            if (!T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND)) sg3_after_correct<NV>(W, eps, bits, ff);
+                            else sg2_after_correct<NV>(nv, W, eps, bits, ff);
                             const int nostep = W.i(L::NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
                             W.i(L::NOSTEP) = nostep;
                             int kle4 = W.i(L::KLE4) + 1;
@@ -743,13 +993,9 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                 next = K_FIN;
             }
         }
-        // ---- 5. books: the kinds the macro-steps left behind (and the refills of step 2) go back to the warp's table
-        __syncwarp();
-        s_kind[lane] = k0;
-        if (own1) s_kind[lane + 32] = k1;
-        __syncwarp();
+        // ---- 5. books: the kinds the macro-steps left behind
         if (slot >= 0) s_kind[slot] = next;
-        __syncwarp();
+        __syncthreads();
     }
     dep_end(a, binning);
     unsigned long long stt = my_steps, rh = my_rhs;

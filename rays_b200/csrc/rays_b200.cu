@@ -483,7 +483,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     }
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;   // (an SG CTA holds twice that many rays; a small fan still spreads over the SMs)
     int grid = (int)std::min<long long>((long long)cx().num_sms * bps, std::max<long long>(blocks_needed, 1));
-    const int rays_per_cta = cx().cached_sgb ? kSgWarps * kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: 64 slots per warp)
+    const int rays_per_cta = cx().cached_sgb ? kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: two slots per thread)
     if (host) {   // streaming copy-out: per-lane (per-slot) staging rows, finished rays go straight to the caller's arrays
         const size_t lanes = (size_t)grid * rays_per_cta;
         if (host->ray_vec) { CK(cx().ray_vec.reserve(lanes * cx().res_npa * cx().res_nv)); a.ray_vec = cx().ray_vec.p; a.host_ray_vec = host->ray_vec; }
