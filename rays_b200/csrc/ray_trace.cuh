@@ -637,9 +637,13 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 }
 
 constexpr int kTraceBlock = 128;
-// Shampine-Gordon slot machine (ray_trace_sg2.cuh): a CTA owns kSgSlots ray slots, two per thread
-constexpr int kSgSlots = 2 * kTraceBlock;
-constexpr int kSgWarps = kTraceBlock / 32;
+// Shampine-Gordon slot machine (ray_trace_sg2.cuh): CTAs of kSgBlock threads own kSgSlots ray slots, two per thread
+#ifndef RAYS_SG_BLOCK
+#define RAYS_SG_BLOCK 128
+#endif
+constexpr int kSgBlock = RAYS_SG_BLOCK;
+constexpr int kSgSlots = 2 * kSgBlock;
+constexpr int kSgWarps = kSgBlock / 32;
 constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, resid_prev/last/max, dep_x, dep_Q, rel_err, abs_err
 
 // one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the

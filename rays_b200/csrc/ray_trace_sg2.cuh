@@ -24,7 +24,7 @@
 namespace rays_dev {
 
 // kSgSlots (slots per warp, 32 < kSgSlots <= 64: lane l keeps the books of slots l and l + 32) and kSgWarps: ray_trace.cuh
-static_assert(kSgSlots == 2 * kTraceBlock, "a thread keeps the kinds of two slots");
+static_assert(kSgSlots == 2 * kSgBlock, "a thread keeps the kinds of two slots");
 
 enum SgKind : int { K_IDLE = 0, K_PRED, K_CORR, K_CHECK, K_START, K_BEGIN, K_FIN };
 enum SgBits : int { B_FIRST = 1, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
@@ -32,7 +32,7 @@ enum SgBits : int { B_FIRST = 1, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIF
 // field-major slot memory of one warp: double field f of slot j at D[f * kSgSlots + j]
 template <int NV> struct SgLayout {
     enum : int {
-        V = 0, YY = V + NV, WT = YY + NV, PHI = WT + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16
+        V = 0, YY = V + NV, WT = YY + NV, P = WT + NV, YP = P + NV, PHI = YP + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16; P, YP: general path only
         ALPHA = PHI + 17 * NV, BETA = ALPHA + 13, SIG = BETA + 13, VV = SIG + 14, WW = VV + 13, G = WW + 14, PSI = G + 14,
         S_ = PSI + 13, SOUT, REL, ABS, RPREV, RLAST, RMAX, DEPX, DEPQ, PWR, EPS, ABSDEL, TEND, RELEPS, ABSEPS, T0, X, H, HOLD,
         ROUND, ABSH, XOLD, ERK, ERKM1, IRAY, NDBL
@@ -54,6 +54,8 @@ template <int NV> struct SgSlot {
     RD_INLINE double &v(int l) const { return f(L::V + l); }
     RD_INLINE double &yy(int l) const { return f(L::YY + l); }
     RD_INLINE double &wt(int l) const { return f(L::WT + l); }
+    RD_INLINE double &p(int l) const { return f(L::P + l); }
+    RD_INLINE double &yp(int l) const { return f(L::YP + l); }
     RD_INLINE double &phi(int i_, int l) const { return f(L::PHI + i_ * NV + l); }
     RD_INLINE double &alpha(int i_) const { return f(L::ALPHA + i_); }
     RD_INLINE double &beta(int i_) const { return f(L::BETA + i_); }
@@ -374,6 +376,29 @@ template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double
     for (int l = 0; l < NV; ++l) if (l < neqn) W.v(l) = W.yy(l) + hi * yo[l];
 }
 
+// The general path (order k > kSgKM, or propagated-roundoff control on) runs for a few steps in ten thousand: it is kept OUT OF LINE,
+// away from the hot loop's instruction-cache footprint, and exchanges p / yp with the caller through the slot (no array
+// references cross the call, which would force the caller's register arrays into local memory).
+template <int NV> static RD_NOINLINE void sg2_predict_ool(int neqn, const SgSlot<NV> W, int bits) {
+    double p[NV];
+    sg2_predict<NV>(neqn, W, bits, p);
+    for (int l = 0; l < neqn; ++l) W.p(l) = p[l];
+}
+template <int NV> static RD_NOINLINE int sg2_after_predict_ool(int neqn, const SgSlot<NV> W, double eps, int bits) {
+    using L = SgLayout<NV>;
+    double p[NV], yp[NV];
+    for (int l = 0; l < NV; ++l) { p[l] = l < neqn ? W.p(l) : 0.0; yp[l] = l < neqn ? W.yp(l) : 0.0; }
+    const int r = sg2_after_predict<NV>(neqn, W, eps, bits, p, yp);
+    W.f(L::EPS) = eps; W.i(L::BITS) = bits;      // handed back through the slot
+    return r;
+}
+template <int NV> static RD_NOINLINE int sg2_after_correct_ool(int neqn, const SgSlot<NV> W, double eps, int bits) {
+    double yp[NV];
+    for (int l = 0; l < NV; ++l) yp[l] = l < neqn ? W.yp(l) : 0.0;
+    sg2_after_correct<NV>(neqn, W, eps, bits, yp);
+    return bits;
+}
+
 // ---- register-resident fast path: order k <= kSgKM, no propagated-roundoff control (99.95 % of the internal steps of the bench
 // fans).  The live state of the slot is loaded in one burst (independent loads: one memory latency instead of one per loop
 // iteration), the statements of sg2_predict / sg2_after_predict / sg2_after_correct run on register arrays with loops bounded by
@@ -598,11 +623,11 @@ template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kS
 #define RAYS_SG2_MIN_CTAS 2
 #endif
 template <class T>
-__global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     constexpr int S = kSgSlots;                 // slots per CTA: two per thread
-    constexpr int NT = kTraceBlock;
+    constexpr int NT = kSgBlock;
     constexpr int NW = kSgWarps;
     using L = SgLayout<NV>;
     const int nv = T::nv();
@@ -614,7 +639,7 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
     const double fouru = 4.0 * DBL_EPSILON;
     __shared__ int s_kind[S];
     __shared__ int s_list[NT];
-    __shared__ int s_wcnt[NW][2][4];
+    __shared__ int s_wcnt[NW][2][6];
     __shared__ unsigned long long s_base;
     const size_t gcta = blockIdx.x;
     double *const D = a.sg_state + gcta * L::NDBL * S;
@@ -631,14 +656,30 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
     __syncthreads();
 
     for (;; ++iter) {
-        // thread t keeps the books of slots t and t + NT
+        // thread t keeps the books of slots t and t + NT.  ---- 1. census of the CTA's slots: predictor | corrector | segment
+        // boundary | restart | finished | idle.  Three barriers per iteration on the common path (census, list, end of macro-step).
         int k0 = s_kind[tid], k1 = s_kind[tid + NT];
-        // ---- 1. rays that ended: streaming copy-out by the warp that keeps the slot's books, the slot becomes idle
-        if (__syncthreads_or(k0 == K_FIN || k1 == K_FIN)) {
+        unsigned b0[6], b1[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int kq = q == 0 ? K_PRED : (q == 1 ? K_CORR : (q == 2 ? K_CHECK : (q == 3 ? K_START : (q == 4 ? K_FIN : K_IDLE))));
+            b0[q] = __ballot_sync(0xffffffffu, k0 == kq || (q == 3 && k0 == K_BEGIN));
+            b1[q] = __ballot_sync(0xffffffffu, k1 == kq || (q == 3 && k1 == K_BEGIN));
+        }
+        if (lane < 6) { s_wcnt[warp][0][lane] = __popc(b0[lane]); s_wcnt[warp][1][lane] = __popc(b1[lane]); }
+        __syncthreads();
+        int tot[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            tot[q] = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tot[q] += s_wcnt[w][0][q] + s_wcnt[w][1][q];
+        }
+        // ---- 2a. rays that ended (one iteration in ~15): streaming copy-out by the warp that keeps the slot's books; slot idle
+        if (tot[4] > 0) {
             if (streaming) {
-                const unsigned f0 = __ballot_sync(0xffffffffu, k0 == K_FIN), f1 = __ballot_sync(0xffffffffu, k1 == K_FIN);
                 for (int half = 0; half < 2; ++half) {
-                    unsigned m = half ? f1 : f0;
+                    unsigned m = half ? b1[4] : b0[4];
                     while (m) {
                         const int sl = warp * 32 + __ffs(m) - 1 + NT * half;
                         m &= m - 1;
@@ -649,99 +690,74 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                     }
                 }
             }
-            if (k0 == K_FIN) k0 = K_IDLE;
-            if (k1 == K_FIN) k1 = K_IDLE;
-        }
-        // ---- 2. refill idle slots from the work queue: one atomic per CTA
-        if (!exhausted) {
-            const unsigned w0 = __ballot_sync(0xffffffffu, k0 == K_IDLE), w1 = __ballot_sync(0xffffffffu, k1 == K_IDLE);
-            if (lane == 0) { s_wcnt[warp][0][0] = __popc(w0); s_wcnt[warp][1][0] = __popc(w1); }
+            if (k0 == K_FIN) s_kind[tid] = K_IDLE;
+            if (k1 == K_FIN) s_kind[tid + NT] = K_IDLE;
             __syncthreads();
-            int total = 0, before0 = 0, before1 = 0;     // slots are handed out in slot order: half 0 of every warp, then half 1
+            continue;
+        }
+        // ---- 2b. refill idle slots from the work queue: one atomic per CTA
+        if (tot[5] > 0 && !exhausted) {
+            const int total = tot[5];
+            int before0 = 0, before1 = 0, all0 = 0;     // slots are handed out in slot order: half 0 of every warp, then half 1
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { total += s_wcnt[w][0][0] + s_wcnt[w][1][0]; if (w < warp) { before0 += s_wcnt[w][0][0]; before1 += s_wcnt[w][1][0]; } }
-            int all0 = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) all0 += s_wcnt[w][0][0];
-            if (total > 0) {
-                if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
-                __syncthreads();
-                const unsigned long long base = s_base;
-                for (int half = 0; half < 2; ++half) {
-                    const bool want = half ? (k1 == K_IDLE) : (k0 == K_IDLE);
-                    const unsigned wb = half ? w1 : w0;
-                    if (want) {
-                        const long long idx = (long long)(base + (unsigned long long)((half ? all0 + before1 : before0) + __popc(wb & ((1u << lane) - 1u))));
-                        if (idx < a.nray) {
-                            const int sl = tid + NT * half;
-                            const SgSlot<NV> W{D + sl, I + sl};
-                            const long long iray = a.order ? (long long)a.order[idx] : idx;
-                            const size_t row = streaming ? gcta * S + sl : (size_t)iray;
-                            W.f(L::IRAY) = (double)iray;
-                            W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
-                            W.i(L::SLICE) = 0;
-                            double v[NV];
-                            if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
-                                RayCarry k;
-                                resume_ray(a, iray, v, nv, k);
-                                W.f(L::S_) = k.s; W.f(L::SOUT) = k.sout; W.i(L::NSTEP) = k.nstep; W.i(L::FLAG) = k.flag;
-                                W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
-                                W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
-                                W.i(L::P0) = streaming ? k.nstep + 1 : 0;
-                                W.i(L::BITS) = 0;
-                            } else {
-                                W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
-                                W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
-                                W.f(L::RPREV) = 0.0; W.f(L::RLAST) = 0.0; W.f(L::RMAX) = 0.0; W.f(L::DEPX) = 0.0; W.f(L::DEPQ) = 0.0;
-                                initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
-                                if (a.ray_vec) {
-                                    double *dst = a.ray_vec + row * a.npoints_alloc * nv;
-                                    if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
-                                }
-                                if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
-                                if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                                W.i(L::BITS) = B_FIRST;
+            for (int w = 0; w < NW; ++w) { all0 += s_wcnt[w][0][5]; if (w < warp) { before0 += s_wcnt[w][0][5]; before1 += s_wcnt[w][1][5]; } }
+            if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
+            __syncthreads();
+            const unsigned long long base = s_base;
+            for (int half = 0; half < 2; ++half) {
+                const bool want = half ? (k1 == K_IDLE) : (k0 == K_IDLE);
+                const unsigned wb = half ? b1[5] : b0[5];
+                if (want) {
+                    const long long idx = (long long)(base + (unsigned long long)((half ? all0 + before1 : before0) + __popc(wb & ((1u << lane) - 1u))));
+                    if (idx < a.nray) {
+                        const int sl = tid + NT * half;
+                        const SgSlot<NV> W{D + sl, I + sl};
+                        const long long iray = a.order ? (long long)a.order[idx] : idx;
+                        const size_t row = streaming ? gcta * S + sl : (size_t)iray;
+                        W.f(L::IRAY) = (double)iray;
+                        W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
+                        W.i(L::SLICE) = 0;
+                        double v[NV];
+                        if (a.resume) {   // a ray suspended by an earlier launch: its last point is still to be checked and saved
+                            RayCarry k;
+                            resume_ray(a, iray, v, nv, k);
+                            W.f(L::S_) = k.s; W.f(L::SOUT) = k.sout; W.i(L::NSTEP) = k.nstep; W.i(L::FLAG) = k.flag;
+                            W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
+                            W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
+                            W.i(L::P0) = streaming ? k.nstep + 1 : 0;
+                            W.i(L::BITS) = 0;
+                        } else {
+                            W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
+                            W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
+                            W.f(L::RPREV) = 0.0; W.f(L::RLAST) = 0.0; W.f(L::RMAX) = 0.0; W.f(L::DEPX) = 0.0; W.f(L::DEPQ) = 0.0;
+                            initialize_ode_vector<T>(a.rvec0 + 3 * iray, a.rindex_vec0 + 3 * iray, v);
+                            if (a.ray_vec) {
+                                double *dst = a.ray_vec + row * a.npoints_alloc * nv;
+                                if (T::GENERIC) store_point(dst, v, nv); else store_point_fixed<NV>(dst, v);
                             }
-#pragma unroll
-                            for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
-                            if (half) k1 = K_CHECK; else k0 = K_CHECK;
+                            if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
+                            if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
+                            W.i(L::BITS) = B_FIRST;
                         }
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
+                        s_kind[sl] = K_CHECK;
                     }
                 }
-                if (base + (unsigned long long)total >= (unsigned long long)a.nray) exhausted = true;
             }
-        }
-        // ---- 3. what do the slots of this CTA need next?  The whole CTA takes the KIND most slots wait for (restarts after a
-        // tolerance raise are rare and get their turn every 16th iteration): thread j runs the j-th slot of that kind, so every
-        // warp executes the same code for about the same time
-        int slot = -1;
-        int kind_q = 0;
-        {
-            unsigned b0[4], b1[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int kq = q == 0 ? K_PRED : (q == 1 ? K_CORR : (q == 2 ? K_CHECK : K_START));
-                b0[q] = __ballot_sync(0xffffffffu, k0 == kq || (q == 3 && k0 == K_BEGIN));
-                b1[q] = __ballot_sync(0xffffffffu, k1 == kq || (q == 3 && k1 == K_BEGIN));
-            }
-            __syncthreads();     // everybody is done with s_wcnt / s_base of step 2 and with s_list of the last iteration
-            if (lane < 4) { s_wcnt[warp][0][lane] = __popc(b0[lane]); s_wcnt[warp][1][lane] = __popc(b1[lane]); }
-            s_kind[tid] = k0;
-            s_kind[tid + NT] = k1;
+            if (base + (unsigned long long)total >= (unsigned long long)a.nray) exhausted = true;
             __syncthreads();
-            int tot[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                tot[q] = 0;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) tot[q] += s_wcnt[w][0][q] + s_wcnt[w][1][q];
-            }
-            if (tot[0] + tot[1] + tot[2] + tot[3] == 0 && exhausted) break;     // every slot idle, queue empty
+            continue;
+        }
+        if (tot[0] + tot[1] + tot[2] + tot[3] == 0) break;     // every slot idle, queue empty
+        // ---- 3. the whole CTA takes the KIND most slots wait for (restarts after a tolerance raise are rare and get their turn
+        // every 16th iteration): thread j runs the j-th slot of that kind, so every warp executes the same code for about the same time
+        int slot = -1;
+        {
             int q = 0, best = tot[0];
             if (tot[1] > best) { q = 1; best = tot[1]; }
             if (tot[2] > best) { q = 2; best = tot[2]; }
             if (tot[3] > 0 && (best == 0 || (iter & 15u) == 0u)) q = 3;
-            kind_q = q;
             // position of my slots among the slots of kind q, in slot order (half 0 of all warps first)
             int bef0 = 0, bef1 = 0, allh0 = 0;
 #pragma unroll
@@ -762,7 +778,6 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
         }
         // ---- 4. one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
         int next = -1;
-        (void)kind_q;
         if (slot >= 0) {
             const SgSlot<NV> W{D + slot, I + slot};
             const int kind = s_kind[slot];
@@ -782,7 +797,13 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
             bool fastk = false;   // this macro-step runs the register-resident bookkeeping
             if (kind == K_PRED) {
                 fastk = !T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND);
-                if (fastk) sg3_predict<NV>(W, uu); else sg2_predict<NV>(nv, W, bits, uu);
+                if (fastk) sg3_predict<NV>(W, uu);
+                else if (T::GENERIC) sg2_predict<NV>(nv, W, bits, uu);
+                else {
+                    sg2_predict_ool<NV>(nv, W, bits);
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) if (i < nv) uu[i] = W.p(i);
+                }
                 req = 2;
             }
             else if (kind == K_CORR) req = 3;
@@ -887,13 +908,26 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kern
                         if (code) { flag = code; W.f(L::SOUT) = W.f(L::S_); stop = true; }     // SG_ode: stop_ode set in eqn_ray -> sout = s
                         else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits, ff); next = K_PRED; }
                         else if (req == 2) {
-                            const int r = fastk ? sg3_after_predict<NV>(W, eps, bits, uu, ff) : sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
+                            int r;
+                            if (fastk) r = sg3_after_predict<NV>(W, eps, bits, uu, ff);
+                            else if (T::GENERIC) r = sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
+                            else {
+#pragma unroll
+                                for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
+                                r = sg2_after_predict_ool<NV>(nv, W, eps, bits);
+                                eps = W.f(L::EPS); bits = W.i(L::BITS);
+                            }
                             if (r == 0) next = K_CORR;
                             else if (r == 1) next = K_PRED;   // failed: predict again with the reduced step
                             else crashed = true;
                         } else {
                             if (!T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND)) sg3_after_correct<NV>(W, eps, bits, ff);
-                            else sg2_after_correct<NV>(nv, W, eps, bits, ff);
+                            else if (T::GENERIC) sg2_after_correct<NV>(nv, W, eps, bits, ff);
+                            else {
+#pragma unroll
+                                for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
+                                bits = sg2_after_correct_ool<NV>(nv, W, eps, bits);
+                            }
                             const int nostep = W.i(L::NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
                             W.i(L::NOSTEP) = nostep;
                             int kle4 = W.i(L::KLE4) + 1;

@@ -32,7 +32,7 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
 #else
         cudaError_t e = s.sg_lanes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0)
-                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kTraceBlock, 0);
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kSgBlock, 0);
 #endif
         if (e != cudaSuccess) return e;
     }
@@ -42,7 +42,7 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
     trace_rk4_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
 #else
     if (s.sg_lanes) trace_sg_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
-    else trace_sg2_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
+    else trace_sg2_kernel<T><<<grid, kSgBlock, a.dep_smem, st>>>(a);
 #endif
     return cudaGetLastError();
 }
