@@ -608,6 +608,28 @@ def main():
             except MemoryError:
                 e2e_pageable = {"unavailable": "not enough host memory for pageable result arrays"}
 
+    # ---- what the host can take: every rank copies 1 GiB device -> pinned host with the copy engine at the same time.  The
+    # aggregate is the ceiling of any end-to-end number that delivers full trajectories to host memory (PCIe + host DRAM).
+    if e2e is not None:
+        nb = 1 << 30
+        dsrc = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        hdst = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        hdst.copy_(dsrc); torch.cuda.synchronize(); barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            hdst.copy_(dsrc, non_blocking=True)
+        c1.record(); torch.cuda.synchronize()
+        my_gbs = 4 * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        barrier()
+        agg = sum_over_ranks(my_gbs)
+        e2e["d2h_dma_gbs_this_rank"] = my_gbs
+        e2e["d2h_dma_gbs_all_ranks"] = agg
+        e2e["d2h_gbs_achieved_all_ranks"] = sum_over_ranks(e2e["d2h_bytes_per_step"]) / (e2e["ms_per_step"] * 1e-3) / 1e9
+        e2e["d2h_ceiling_note"] = ("all ranks copy 1 GiB device -> pinned host concurrently with cudaMemcpyAsync (copy engine): the host-side ceiling "
+                                   "(PCIe links + host DRAM ingest) for delivering full trajectories; d2h_gbs_achieved is what the trace delivered")
+        del dsrc, hdst
+
     # ---- the other BASELINE configs on this GPU (N = 1) ----------------------------------------------------
     also = []
     if world == 1 and is_headline and not args.no_also:
@@ -652,6 +674,7 @@ def main():
     # ---- config 5: sharded deposition fan with the north-star collective inside the timed region ------------
     config5 = None
     if is_headline and not args.no_config5:
+        from rays_b200.sharding import reduce_bins, gather_packed_summaries
         rb.initialize(deposition_namelist(args.config5_grid), ray_init=True, device=local_rank)   # every rank launches the whole fan on its GPU
         cfg5 = rb.host_cfg()
         rb.set_config(cfg5)
@@ -672,8 +695,8 @@ def main():
             rb.deposition_fixed(nbins, 0.0, 1.0, d_acc_out=acc.data_ptr())   # this GPU's fixed-point bins
             rb.summaries_pack(summ.data_ptr(), n_max)
             if dist is not None:
-                dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)               # THE collective of the run: 501 int64 (exact sum)
-                dist.all_gather_into_tensor(gathered, summ)                 # per-ray summaries, 6 + 2 nv doubles per ray
+                reduce_bins(acc, dst=0)                                     # THE collective of the run: 501 int64 (exact sum)
+                gather_packed_summaries(summ, gathered)                     # per-ray summaries, 6 + 2 nv doubles per ray
             return st
         for _ in range(2):
             acc.zero_()
@@ -693,8 +716,7 @@ def main():
         acc_h = acc.cpu().numpy()
         # a fresh reduce for the checksum (the timed loop reduced into rank 0's buffer k5 times)
         rb.deposition_fixed(nbins, 0.0, 1.0, d_acc_out=acc.data_ptr())
-        if dist is not None:
-            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        reduce_bins(acc, dst=0)
         torch.cuda.synchronize()
         acc_h = acc.cpu().numpy()
         prof = acc_h.astype(np.float64) * unit

@@ -195,3 +195,40 @@ def test_oracle_reproduces_the_reference_kx_profiles(page):
         swapped = (np.abs(y[0] - b_re) <= tol) & (np.abs(y[2] - a_re) <= tol)
         assert np.all(same | swapped)
         assert np.all(np.abs(np.abs(y[1]) - np.abs(a_im)) <= tol_i) and np.all(np.abs(np.abs(y[3]) - np.abs(b_im)) <= tol_i)
+
+
+# ---- the reference author's Mathematica evaluation of the cold roots in the Solov'ev equilibrium ---------------------------------
+MMA = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_solovev_nx_roots.json")))
+
+
+@pytest.mark.parametrize("page", range(len(MMA["pages"])))
+def test_oracle_reproduces_the_reference_solovev_root_plots(page):
+    """kx_plots_Solovev_90GHz_ECH.pdf (a printed Mathematica notebook of the RAYS author, independent of the Fortran): Re and Im of n_x
+    of the plus (O) and minus (X) roots along the equatorial plane of the two Solov'ev example cases.  Every one of the 1 454 plotted
+    samples must lie on one of the oracle's four root branches (|Re n_x|, |Im n_x| of plus / minus from solve_n1_vs_n2_n3 on the
+    Solov'ev equilibrium) to the PDF's resolution: pins solovev_eq's B(R), n(psi), RLSDP_cold and the n1^2(n3) quadratic with its
+    cutoffs, the right-hand resonance and the evanescent stretch."""
+    import ctypes as C
+    pg = MMA["pages"][page]
+    cfg = init_case(pg["namelist"])
+    L = orc.load()
+
+    def nx(x, mode):
+        cfg.wave_mode = mode
+        re, im = C.c_double(0), C.c_double(0)
+        rv = np.array([min(max(x, 0.2000001), 1.3999999), 0.0, 0.0])
+        assert L.oracle_solve_n1(C.byref(cfg), rv.ctypes.data_as(C.POINTER(C.c_double)), 0.0, pg["n_z"], C.byref(re), C.byref(im)) == 0
+        return complex(re.value, im.value)
+    devs = []
+    for cv in pg["curves"]:
+        x, y = np.array(cv["x"]), np.array(cv["y"])
+        cand = []
+        for mode in (1, 2):
+            v = np.array([nx(xi, mode) for xi in x])
+            cand.append(np.abs(np.abs(v.real if cv["part"] == "re" else v.imag) - y))
+        d = cand[0] if np.median(cand[0]) < np.median(cand[1]) else cand[1]     # the curve is ONE branch
+        assert np.median(d) <= 1.2e-4, (cv["part"], len(x), np.median(d))      # PDF resolution: 1e-3 pt = 1.7e-5 in n_x
+        devs.append(d)
+    d = np.concatenate(devs)
+    # steep stretches (next to the resonance / cutoffs) turn the x resolution of the PDF into a larger n_x deviation
+    assert np.percentile(d, 99) <= 1.0e-3 and d.max() <= 2.5e-3, (np.percentile(d, 99), d.max())
