@@ -273,6 +273,8 @@ int oracle_solve_nsq_theta(const rays_cfg *cfg, const double *rvec, double theta
     for (int i = 0; i < 4; ++i) nsq4[i] = nsq[i + 1];
     return 0;
 }
+// test switch: end rays at the plasma edge like the older generation of the code did (see oracle_old_generation)
+int oracle_set_old_generation(int on) { const int was = oracle_old_generation(); oracle_old_generation() = on; return was; }
 int oracle_num_threads(void) { return omp_get_max_threads(); }
 
 }  // extern "C"

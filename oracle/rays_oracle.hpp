@@ -350,6 +350,15 @@ inline void solovev_psi(const R rvec[3], double bphi0, double iota0, double rmaj
     for (int i = 0; i < 3; ++i) gradpsiN[i] = gradpsi[i] / psiB;
 }
 
+// TEST SWITCH: the example figures of ECH_90GHz_solovev_SG_eq_plane predate RAYS_project; the older generation of the same code
+// (RAYS_code/, OLD/ in SURVEY.md) differs from the current one in how a ray ENDS at the plasma edge:
+//   * RAYS_code/solovev_eq_m.f90:140   if (psiN > 1.) equib_err = 'psi >1 out_of_plasma'   (the current solovev_eq has no such test),
+//   * RAYS_code/ray_tracing.f90:131-140: a point whose check_save raised ANY flag ends the ray and is not counted
+//     (npoints = nstep, :150-153), where the current loop tests stop_ode only.
+// With the switch on the oracle ends rays like that generation did; tests/test_reference_plots.py uses it to show that the two
+// figure rays that are one point shorter than the current code's were drawn by it.  Off (0) everywhere else.
+inline int &oracle_old_generation() { static int flag = 0; return flag; }
+
 // solovev_eq (L/solovev_eq_m.f90:122-276) including its temperature-profile bugs
 template <class R> inline void solovev_eq(const rays_cfg &c, const R rvec[3], ModelOut<R> &m) {
     const rays_solovev_eq &p = c.solovev;
@@ -362,6 +371,7 @@ template <class R> inline void solovev_eq(const rays_cfg &c, const R rvec[3], Mo
     double bp0 = p.bphi0 * p.iota0;
     R psi, gradpsi[3], psiN, gradpsiN[3];
     solovev_psi(rvec, p.bphi0, p.iota0, p.rmaj, p.kappa, p.psiB, psi, gradpsi, psiN, gradpsiN);
+    if (oracle_old_generation() && val(psiN) > 1.0) m.equib_err = RAYS_STOP_OUT_OF_PLASMA;   // RAYS_code/solovev_eq_m.f90:140
     if (m.equib_err != 0) return;
     solovev_field(x, y, z, r, p.bphi0, bp0, p.rmaj, p.kappa, m.bvec, m.gradbtensor);
     switch (p.dens_prof_model) {

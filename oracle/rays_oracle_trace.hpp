@@ -54,6 +54,7 @@ inline void trace_one_ray(const rays_cfg &c, const double *rvec0, const double *
         if (ray_stop.stop_ode) break;
         check_save(c, s, v, resid, ray_stop);
         if (ray_stop.stop_ode) break;
+        if (oracle_old_generation() && ray_stop.ode_stop_flag != 0) break;   // RAYS_code/ray_tracing.f90:131-140 (see oracle_old_generation)
         nstep = nstep + 1;
         if (o.ray_vec) for (int i = 0; i < nv; ++i) o.ray_vec[(size_t)nstep * nv + i] = val(v[i]);
         if (o.residual) o.residual[nstep] = val(resid);
