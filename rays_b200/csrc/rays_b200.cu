@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <cmath>
 #include <cstdio>
@@ -112,6 +113,13 @@ struct Ctx {
     // pinned staging for small results
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // staged copy-out to PAGEABLE result arrays: packed rows HBM -> pinned ring (copy engine) -> caller's arrays (host threads)
+    static constexpr int kRing = 3;
+    DevBuf<double> pack_dev;          // kRing packed chunks
+    DevBuf<long long> pack_off;       // packed offset (doubles) of every ray of the batch
+    double *ring_host = nullptr;      // kRing chunks, page-locked
+    size_t ring_chunk_doubles = 0;
+    cudaEvent_t ev_ring[kRing] = {nullptr, nullptr, nullptr};
 };
 // One context per GPU.  Every entry point works on the CURRENT context of the calling host thread: context 0 unless
 // rays_b200_*_multi selected another one (each of its worker threads drives one GPU).
@@ -259,6 +267,30 @@ __global__ void zero_tail_kernel(double *ray_vec, double *residual, const int *n
     const int end = min(npa, (gmax + 31) / 32 * 32);
     if (ray_vec) for (int i = np * nv + threadIdx.x; i < end * nv; i += blockDim.x) ray_vec[(size_t)iray * npa * nv + i] = 0.0;
     if (residual) for (int i = np + threadIdx.x; i < end; i += blockDim.x) residual[(size_t)iray * npa + i] = 0.0;
+}
+// Packed copy-out (pageable result arrays): the saved points of ray i, [npoints*nv of ray_vec][npoints of residual], go to
+// out + off[i] - off0.  One CTA per ray, 16-byte accesses where the row allows it.
+__global__ void pack_rows_kernel(const double *__restrict__ ray_vec, const double *__restrict__ residual, const int *__restrict__ npoints,
+                                 const long long *__restrict__ off, long long off0, int npa, int nv, double *__restrict__ out) {
+    const long long i = blockIdx.x;
+    const int np = npoints[i];
+    double *dst = out + (off[i] - off0);
+    if (ray_vec) {
+        const double *src = ray_vec + (size_t)i * npa * nv;
+        const int n = np * nv;
+        if ((((size_t)dst | (size_t)src) & 15) == 0) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 *d2 = reinterpret_cast<double2 *>(dst);
+            for (int k = threadIdx.x; k < n / 2; k += blockDim.x) d2[k] = s2[k];
+            if ((n & 1) && threadIdx.x == 0) dst[n - 1] = src[n - 1];
+        } else
+            for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+        dst += n;
+    }
+    if (residual) {
+        const double *src = residual + (size_t)i * npa;
+        for (int k = threadIdx.x; k < np; k += blockDim.x) dst[k] = src[k];
+    }
 }
 // keep rays with iray % world == rank, order preserved
 __global__ void fan_shard_kernel(long long n_out, int rank, int world, const double *rv, const double *nv, const double *w,
@@ -647,6 +679,107 @@ int copy_trajectories(rays_results *res, const std::vector<int> &np, long long f
     return 0;
 }
 
+// Is p ordinary pageable host memory (not page-locked, not registered)?
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+// the staged path serves pageable destinations; RAYS_B200_STAGED_COPY=0 keeps the plain cudaMemcpy2D (measurement aid)
+bool staged_copy_wanted(const rays_results *res) {
+    const char *e = getenv("RAYS_B200_STAGED_COPY");
+    if (e && e[0] == '0') return false;
+    return (res->ray_vec ? is_pageable(res->ray_vec) : true) && (res->residual ? is_pageable(res->residual) : true) && (res->ray_vec || res->residual);
+}
+int g_copy_threads_div = 1;   // GPUs driven by this process (rays_b200_init_multi): the host cores are shared between their copy-outs
+int copy_threads() {
+    if (const char *e = getenv("RAYS_B200_COPY_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 64); }
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(16, (hw > 0 ? hw : 4) / std::max(1, g_copy_threads_div)));
+}
+
+// D2H of trajectories into PAGEABLE arrays (what `allocate(ray_vec(nv, nstep_max+1, nray))` of an unmodified host gives,
+// ray_results_m.f90:132-142).  A cudaMemcpy2D into pageable memory is staged by the driver through one small bounce buffer and
+// reaches ~3 GB/s; here the saved points are packed on the device (exactly the algorithmic bytes), moved by the copy engine into a
+// ring of page-locked chunks, and spread into the caller's rows by host threads while the next chunk is in flight.
+int copy_trajectories_staged(rays_results *res, const std::vector<int> &np, long long first, long long count, const double *tv, const double *tr,
+                             int npa, int nv, RowMap rm = RowMap{}) {
+    Ctx &c = cx();
+    const bool wv = res->ray_vec != nullptr, wr = res->residual != nullptr;
+    if (count <= 0 || (!wv && !wr)) return 0;
+    const int per_pt = (wv ? nv : 0) + (wr ? 1 : 0);
+    constexpr int R = Ctx::kRing;
+    const size_t chunk = (size_t(64) << 20) / 8;   // doubles per chunk
+    if (!c.ring_host || c.ring_chunk_doubles != chunk) {
+        if (c.ring_host) cudaFreeHost(c.ring_host);
+        c.ring_host = nullptr;
+        CK(cudaHostAlloc((void **)&c.ring_host, R * chunk * 8, cudaHostAllocDefault));
+        c.ring_chunk_doubles = chunk;
+        for (int k = 0; k < R; ++k) if (!c.ev_ring[k]) CK(cudaEventCreateWithFlags(&c.ev_ring[k], cudaEventDisableTiming));
+    }
+    CK(c.pack_dev.reserve(R * chunk));
+    std::vector<long long> off((size_t)count + 1);
+    off[0] = 0;
+    for (long long i = 0; i < count; ++i) {
+        const int n = np[(size_t)(first + i)];
+        if (n > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "copy-out: npoints_alloc smaller than the longest ray");
+        off[(size_t)i + 1] = off[(size_t)i] + (long long)n * per_pt;
+    }
+    if ((size_t)npa * per_pt > chunk) return set_err(RAYS_ERR_INVALID_CONFIG, "copy-out: one ray does not fit a staging chunk");
+    CK(c.pack_off.reserve((size_t)count + 1));
+    CK(cudaMemcpyAsync(c.pack_off.p, off.data(), ((size_t)count + 1) * sizeof(long long), cudaMemcpyHostToDevice, c.copy_stream));
+    const int T = copy_threads();
+    const int dev = c.device;
+    std::vector<std::thread> workers[R];
+    std::atomic<int> failed{0};
+    auto join = [&](int slot) { for (auto &t : workers[slot]) t.join(); workers[slot].clear(); };
+    int rc = 0, ic = 0;
+    for (long long a = 0; a < count && !rc; ++ic) {
+        long long b = a + 1;   // rays [a, b) of the batch: as many as fit one chunk
+        while (b < count && (size_t)(off[(size_t)b + 1] - off[(size_t)a]) <= chunk) ++b;
+        const int slot = ic % R;
+        join(slot);
+        double *dchunk = c.pack_dev.p + (size_t)slot * chunk;
+        double *hchunk = c.ring_host + (size_t)slot * chunk;
+        const size_t ndbl = (size_t)(off[(size_t)b] - off[(size_t)a]);
+        cudaError_t e = cudaSuccess;
+        if (ndbl) {
+            pack_rows_kernel<<<(unsigned)(b - a), 128, 0, c.copy_stream>>>(wv ? tv + (size_t)a * npa * nv : nullptr, wr ? tr + (size_t)a * npa : nullptr, c.npoints.p + first + a,
+                                                                          c.pack_off.p + a, off[(size_t)a], npa, nv, dchunk);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hchunk, dchunk, ndbl * 8, cudaMemcpyDeviceToHost, c.copy_stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(c.ev_ring[slot], c.copy_stream);
+        if (e != cudaSuccess) { rc = set_err(RAYS_ERR_CUDA, std::string("staged copy-out: ") + cudaGetErrorString(e)); break; }
+        cudaEvent_t ev = c.ev_ring[slot];
+        const long long base = off[(size_t)a];
+        for (int t = 0; t < T; ++t) {
+            // thread t spreads the rays whose packed data start in its share of the chunk
+            const long long lo_off = base + (long long)(ndbl * (size_t)t / T), hi_off = base + (long long)(ndbl * (size_t)(t + 1) / T);
+            const long long r0 = std::lower_bound(off.begin() + a, off.begin() + b, lo_off) - off.begin();
+            const long long r1 = (t == T - 1) ? b : std::lower_bound(off.begin() + a, off.begin() + b, hi_off) - off.begin();
+            if (r1 <= r0) continue;
+            workers[slot].emplace_back([=, &off, &np, &failed]() {
+                cudaSetDevice(dev);
+                if (cudaEventSynchronize(ev) != cudaSuccess) { failed.store(1); return; }
+                for (long long i = r0; i < r1; ++i) {
+                    const int n = np[(size_t)(first + i)];
+                    const double *src = hchunk + (off[(size_t)i] - base);
+                    const size_t row = (size_t)(rm.row0 + (first + i) * rm.stride);
+                    if (wv) { std::memcpy(res->ray_vec + row * res->npoints_alloc * nv, src, (size_t)n * nv * 8); src += (size_t)n * nv; }
+                    if (wr) std::memcpy(res->residual + row * res->npoints_alloc, src, (size_t)n * 8);
+                }
+            });
+        }
+        a = b;
+    }
+    for (int k = 0; k < R; ++k) join(k);
+    if (!rc && failed.load()) rc = set_err(RAYS_ERR_CUDA, "staged copy-out: a copy of a staging chunk failed");
+    if (!rc) CK(cudaStreamSynchronize(c.copy_stream));
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -710,6 +843,9 @@ int rays_b200_finalize(void) {
     cudaEventDestroy(cx().ev_m0); cudaEventDestroy(cx().ev_m1);
     if (cx().pinned) cudaFreeHost(cx().pinned);
     cx().pinned = nullptr; cx().pinned_bytes = 0;
+    cx().pack_dev.release(); cx().pack_off.release();
+    if (cx().ring_host) cudaFreeHost(cx().ring_host);
+    for (int k = 0; k < Ctx::kRing; ++k) if (cx().ev_ring[k]) cudaEventDestroy(cx().ev_ring[k]);
     cudaEventDestroy(cx().ev0); cudaEventDestroy(cx().ev1);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(cx().ev_batch[i]); cudaEventDestroy(cx().ev_copy[i]); }
     cudaStreamDestroy(cx().stream); cudaStreamDestroy(cx().copy_stream);
@@ -992,10 +1128,14 @@ int rays_b200_results_download(rays_results *res) {
         if (res->npoints_alloc < 1) return set_err(RAYS_ERR_INVALID_CONFIG, "npoints_alloc < 1");
         for (long long i = 0; i < n; ++i)
             if (np[(size_t)i] > res->npoints_alloc) return set_err(RAYS_ERR_INVALID_CONFIG, "rays_b200_results_download: npoints_alloc smaller than the longest ray");
-        zero_tail_kernel<<<(unsigned)n, 64, 0, cx().stream>>>(res->ray_vec ? cx().ray_vec.p : nullptr, res->residual ? cx().residual.p : nullptr, cx().npoints.p, cx().res_npa, nv, n);
-        CK(cudaGetLastError());
-        if ((rc = copy_trajectories(res, np, 0, n, cx().ray_vec.p, cx().residual.p, cx().res_npa, nv, cx().stream))) return rc;
-        CK(cudaStreamSynchronize(cx().stream));
+        if (staged_copy_wanted(res)) {     // pageable arrays: packed rows through the page-locked ring (the stream is idle: synchronised above)
+            if ((rc = copy_trajectories_staged(res, np, 0, n, cx().ray_vec.p, cx().residual.p, cx().res_npa, nv))) return rc;
+        } else {
+            zero_tail_kernel<<<(unsigned)n, 64, 0, cx().stream>>>(res->ray_vec ? cx().ray_vec.p : nullptr, res->residual ? cx().residual.p : nullptr, cx().npoints.p, cx().res_npa, nv, n);
+            CK(cudaGetLastError());
+            if ((rc = copy_trajectories(res, np, 0, n, cx().ray_vec.p, cx().residual.p, cx().res_npa, nv, cx().stream))) return rc;
+            CK(cudaStreamSynchronize(cx().stream));
+        }
     }
     fill_flags(res, codes, 0);
     res->total_trace_time = cx().last_ms * 1e-3;
@@ -1094,6 +1234,7 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         }
     }
     const int nbuf = (batch < n) ? 2 : 1;
+    const bool staged = want_traj && staged_copy_wanted(res);
     if ((rc = ensure_results(n, nv, npa, false))) return rc;
     if (want_traj) {
         CK(cx().ray_vec.reserve((size_t)nbuf * batch * npa * nv));
@@ -1111,7 +1252,7 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         double *tr = want_traj ? cx().residual.p + (size_t)b * batch * npa : nullptr;
         if (ib >= nbuf) CK(cudaStreamWaitEvent(cx().stream, cx().ev_copy[b], 0));   // buffer b free again
         if ((rc = launch_trace(first, count, tv, tr, false))) return rc;
-        if (want_traj) {
+        if (want_traj && !staged) {
             zero_tail_kernel<<<(unsigned)count, 64, 0, cx().stream>>>(res->ray_vec ? tv : nullptr, res->residual ? tr : nullptr, cx().npoints.p + first, npa, nv, count);
             CK(cudaGetLastError());
         }
@@ -1120,7 +1261,9 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         CK(cudaEventRecord(cx().ev_batch[b], cx().stream));
         if (want_traj) {
             CK(cudaEventSynchronize(cx().ev_batch[b]));   // npoints of this batch are on the host: trim the copy
-            if ((rc = copy_trajectories(res, np, first, count, tv, tr, npa, nv, cx().copy_stream, rm))) return rc;
+            if (staged) rc = copy_trajectories_staged(res, np, first, count, tv, tr, npa, nv, rm);   // returns with the batch delivered
+            else rc = copy_trajectories(res, np, first, count, tv, tr, npa, nv, cx().copy_stream, rm);
+            if (rc) return rc;
             CK(cudaEventRecord(cx().ev_copy[b], cx().copy_stream));
         }
     }
@@ -1415,6 +1558,7 @@ int rays_b200_init_multi(int ngpu) {
     g_cur = keep;
     if (rc) return rc;
     mg.n = n;
+    g_copy_threads_div = n;
     if (n > 1) {
         if ((rc = load_nccl())) return rc;
         int devs[kMaxGpus];
@@ -1552,6 +1696,7 @@ int rays_b200_finalize_multi(void) {
     }
     g_cur = keep;
     mg.n = 0;
+    g_copy_threads_div = 1;
     return 0;
 }
 

@@ -336,12 +336,15 @@ def test_host_mirror_program_flow(tmp_path):
     f.close()
 
 
-@pytest.mark.parametrize("slice_steps,register", [("5", "1"), ("5", "0"), ("0", "0"), ("40", "1")])
-def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, register, monkeypatch):
+@pytest.mark.parametrize("slice_steps,register,staged", [("5", "1", "1"), ("5", "0", "1"), ("0", "0", "1"), ("40", "1", "1"), ("5", "0", "0"), ("0", "0", "0")])
+def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, register, staged, monkeypatch):
     """The library's execution options change the schedule and the copy-out path, never the results:
-    time slicing (rays suspended after n steps and re-launched packed) x streaming / batched copy-out."""
+    time slicing (rays suspended after n steps and re-launched packed) x streaming copy-out by the kernel (page-locked arrays) /
+    packed rows through the page-locked ring + host threads (pageable arrays) / plain cudaMemcpy2D into pageable arrays."""
     monkeypatch.setenv("RAYS_B200_SLICE", slice_steps)
     monkeypatch.setenv("RAYS_B200_REGISTER_HOST", register)
+    monkeypatch.setenv("RAYS_B200_STAGED_COPY", staged)
+    monkeypatch.setenv("RAYS_B200_COPY_THREADS", "5")
     cfg = init_case("solovev_fan_1M.in", nstep_max=120)
     r, n, w, _, _ = oracle_fan(cfg, n_r_launch=2, n_theta_launch=3, n_rindex_theta=8, n_rindex_phi=8, dtheta_launch=0.2,
                                delta_rindex_theta=0.05, delta_rindex_phi=0.04)

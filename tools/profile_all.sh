@@ -9,11 +9,19 @@ prof() {  # tag kernel-regex count bench-args...
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$kre -c $cnt -o gpurun_out/r2_prof_$tag python bench.py $COMMON "$@" > gpurun_out/r2_ncu_$tag.log 2>&1
   tail -n 1 gpurun_out/r2_ncu_$tag.log
 }
+post() { bash tools/profile_post.sh "$@"; }
 prof trace_rk4_num trace_rk4_kernel 2                         # headline: first pass + resume pass over the suspended rays
+post trace_rk4_num trace_rk4_kernel 2 2 2 0 0 2
 prof trace_rk4_cold trace_rk4_kernel 2 --deriv cold
+post trace_rk4_cold trace_rk4_kernel 2 2 1 0 0 2
 prof trace_rk4_mirror trace_rk4_kernel 1 --workload mirror_fan_1M
+post trace_rk4_mirror trace_rk4_kernel 4 2 1 0 1 1
 prof trace_rk4_damp trace_rk4_kernel 1 --workload axisym_deposition_fan --config5-grid 1024
+post trace_rk4_damp trace_rk4_kernel 3 2 1 1 0 1
 prof fp64_peak fp64_peak_kernel 2 --rays 16384
+python tools/ncu_summary.py gpurun_out/r2_prof_fp64_peak.ncu-rep 1 > gpurun_out/r2_fp64_peak_ncu_summary.txt 2>&1; rm -f gpurun_out/r2_prof_fp64_peak.ncu-rep
+prof trace_sg2 trace_sg2_kernel 1 --ode SG_ODE --deriv cold --rays 262144
+post trace_sg2 trace_sg2_kernel 2 2 1 0 0 1 keep
 # launch list of the default bench step
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu"
 $CMD > gpurun_out/r2_plain_bench.log 2>&1 &&
