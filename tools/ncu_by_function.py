@@ -36,6 +36,10 @@ rows = list(csv.reader(open(sass)))
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]
+for i, r in enumerate(data):      # a report with several captured launches repeats the header block: keep the first launch
+    if r and r[0] == "Kernel Name":
+        data = data[:i]
+        break
 assert abs(len(data) - len(loc)) <= 2, (len(data), len(loc))
 # map file:line -> function name by scanning the source for function headers
 import os
