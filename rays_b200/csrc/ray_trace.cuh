@@ -530,7 +530,8 @@ struct TraceArgs {
     int slice_steps;
     int resume;
     int sg_align;                   // SG kernel: 1 = lanes advance in alternating predictor / corrector slots (see trace_sg_kernel)
-    double *sg_state;               // slot-machine SG kernel (ray_trace_sg2.cuh): slot memory, grid * sg_state_bytes_per_cta bytes
+    double *sg_state;               // slot-machine SG kernel (ray_trace_sg2.cuh): global slot records, grid * sg_state_bytes_per_cta bytes
+    int sg_slots;                   // ... and the ray slots of one CTA (their hot records are in dynamic shared memory)
     double *cont_state;             // [nray][kContStride]
     int *cont_list;
     unsigned long long *cont_count;
@@ -637,13 +638,16 @@ template <int EQ_> RD_INLINE double dep_abscissa(const double *v) {
 }
 
 constexpr int kTraceBlock = 128;
-// Shampine-Gordon slot machine (ray_trace_sg2.cuh): CTAs of kSgBlock threads own kSgSlots ray slots, two per thread
+// Shampine-Gordon slot machine (ray_trace_sg2.cuh): kSgCtas CTAs of kSgBlock threads per SM, each owning as many ray slots as its
+// share of the SM's shared memory holds (TraceArgs::sg_slots)
 #ifndef RAYS_SG_BLOCK
-#define RAYS_SG_BLOCK 128
+#define RAYS_SG_BLOCK 256
+#endif
+#ifndef RAYS_SG2_MIN_CTAS
+#define RAYS_SG2_MIN_CTAS 1
 #endif
 constexpr int kSgBlock = RAYS_SG_BLOCK;
-constexpr int kSgSlots = 2 * kSgBlock;
-constexpr int kSgWarps = kSgBlock / 32;
+constexpr int kSgCtas = RAYS_SG2_MIN_CTAS;
 constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, resid_prev/last/max, dep_x, dep_Q, rel_err, abs_err
 
 // one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the

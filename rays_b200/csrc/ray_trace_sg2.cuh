@@ -1,4 +1,4 @@
-// ray_trace_sg2.cuh — Shampine-Gordon trace kernel as per-warp SLOT MACHINES.
+// ray_trace_sg2.cuh — Shampine-Gordon trace kernel as a per-CTA SLOT MACHINE with the integrator state in SHARED MEMORY.
 //
 // SG_ode (SG_ode_m.f90:89-159) -> ode/de (ode_RAYS.f90:1-593) -> step (:595-1234) / intrp (:1235-1362), every decision of
 // the reference replayed with the reference's arithmetic, as in the per-lane state machine of ray_trace.cuh — what changes
@@ -7,37 +7,66 @@
 // are accepted, at order k <= 3 (k = 4: 0.05 %): 27 right-hand sides per ray-step, and between two of them each ray needs
 // one of four different bookkeeping blocks.  With one ray pinned to one lane the blocks of a warp run one after another with
 // a third of the lanes each (ncu on the round-1 kernel: 13 of 32 lanes active, 129 KB of divergent code thrashing the
-// instruction cache).  Here every WARP owns kSgSlots ray SLOTS (twice its lanes) whose whole state (ray + integrator
-// history) lives in slot memory (HBM-backed, L1/L2-resident, field-major so that a warp's accesses coalesce), and every
-// iteration of the warp
-//   1. counts what its slots need next (predictor + f(p) + error test | f(yy) + history update | segment boundary:
-//      interpolate + check_save + start derivative | restart after a tolerance raise) and picks the KIND most slots wait for,
-//   2. lane j takes the j-th slot of that kind and runs ONE macro-step: bookkeeping -> ONE right-hand side -> bookkeeping.
-// All lanes of a warp therefore run the same code on 32 different rays whenever 32 slots of one kind exist (with 64 slots
-// there nearly always are), the once-per-segment work (1/27 of the macro-steps) accumulates until it is the largest group
-// instead of running with one or two lanes, and no warp ever waits for another: there is no CTA-level barrier in the loop
-// (the first, CTA-sorted version of this kernel lost 23 % of its stall samples to __syncthreads).
-// Finished rays are copied out / re-filled from the global work queue by the warp at the top of an iteration.
+// instruction cache).
+//
+// Here a CTA owns S ray SLOTS (more than it has threads).  A slot's live integrator state — yy, wt, the divided differences
+// phi(1..5), the step coefficients up to order 3, x, h, ... : SgHot, 87 doubles for nv = 7 — lives in SHARED memory, one
+// contiguous record per slot (odd length: a warp's accesses to one field of 32 consecutive slots are conflict-free); what is
+// touched once per ray-step (s, sout, residual history, deposition carry) and the rows only orders k > 3 reach live in a
+// global, L2-resident record (SgLayout).  The first slot machine kept everything in global memory: ncu showed 1.9 of its
+// 10 stall cycles per issue on those loads, 52 GB of DRAM writes for 2.4 GB of trajectory (the 70 MB hot set thrashing L2)
+// and 2.7 on its three CTA barriers per iteration.
+//
+// Scheduling: every slot sits in exactly one shared-memory RING per kind of macro-step it needs next
+//   PRED   predictor + f(p) + error test            (order <= 3: register-resident bookkeeping, sg3_*)
+//   CORR   f(yy) + history update, next order/step
+//   CHECK  segment boundary: interpolate + check_save + start derivative of the next segment (fused: same point)
+//   START  restart after a tolerance raise / start derivative on its own (rare)
+//   GPRED / GCORR   the same macro-steps for a slot at order k > 3 or with propagated-roundoff control on: the general,
+//          looped code (sg2_*, out of line).  A few steps in ten thousand — but ONE such slot in an iteration made its warp
+//          three times slower and the whole CTA wait at the barrier, so they are batched as kinds of their own.
+//   FIN    ray ended: streaming copy-out of its row by a warp;  IDLE: refill from the global work queue
+// and an iteration of the CTA is: ONE barrier; every thread reads the ring counters and comes to the same choice (the kind
+// most slots wait for); thread j pops the j-th entry; one macro-step = bookkeeping -> ONE right-hand side -> bookkeeping;
+// the thread pushes the slot onto the ring of its next kind (warp-aggregated shared-memory atomics).  All warps of the CTA
+// therefore run the same code at the same time (one instruction stream per SM for the instruction cache), lanes are full
+// whenever 32 slots of a kind exist, and the once-per-segment work (1/27 of the macro-steps) accumulates until it is the
+// largest group instead of running with one or two lanes.
 #pragma once
+#include <climits>
 #include "ray_trace.cuh"
 
 namespace rays_dev {
 
-// kSgSlots (slots per warp, 32 < kSgSlots <= 64: lane l keeps the books of slots l and l + 32) and kSgWarps: ray_trace.cuh
-static_assert(kSgSlots == 2 * kSgBlock, "a thread keeps the kinds of two slots");
-
 enum SgKind : int { K_IDLE = 0, K_PRED, K_CORR, K_CHECK, K_START, K_BEGIN, K_FIN };
+enum SgRing : int { Q_PRED = 0, Q_CORR, Q_CHECK, Q_START, Q_GPRED, Q_GCORR, Q_FIN, Q_IDLE, kSgNQ };
 enum SgBits : int { B_FIRST = 1, B_START = 4, B_PHASE1 = 8, B_NORND = 16, B_STIFF = 32, B_INTRP = 64 };
+constexpr int kSgKM = 3;            // highest order of the register-resident fast path
+constexpr int kSgHotRows = kSgKM + 2;   // phi(1..k+2)
+constexpr int kSgRingCap = 512;     // entries per ring (a power of two >= slots per CTA)
+constexpr int kSgStride = kSgRingCap;   // slot stride of the global records
 
-// field-major slot memory of one warp: double field f of slot j at D[f * kSgSlots + j]
+// global (cold) record of one CTA, field-major: double field f of slot j at D[f * kSgStride + j].  The fields the hot record
+// holds (SgHot) keep their place here but are never touched.
 template <int NV> struct SgLayout {
     enum : int {
         V = 0, YY = V + NV, WT = YY + NV, P = WT + NV, YP = P + NV, PHI = YP + NV,      // phi(l,i) at PHI + i*NV + l, i = 0..16; P, YP: general path only
         ALPHA = PHI + 17 * NV, BETA = ALPHA + 13, SIG = BETA + 13, VV = SIG + 14, WW = VV + 13, G = WW + 14, PSI = G + 14,
-        S_ = PSI + 13, SOUT, REL, ABS, RPREV, RLAST, RMAX, DEPX, DEPQ, PWR, EPS, ABSDEL, TEND, RELEPS, ABSEPS, T0, X, H, HOLD,
-        ROUND, ABSH, XOLD, ERK, ERKM1, IRAY, NDBL
+        S_ = PSI + 13, SOUT, REL, ABS, RPREV, RLAST, RMAX, DEPX, DEPQ, PWR, IRAY, NDBL
     };
-    enum : int { NSTEP = 0, FLAG, P0, SLICE, NS, K, KOLD, IFAIL, KNEW, NOSTEP, KLE4, BITS, FINNP, NINT = 14 };
+    enum : int { NSTEP = 0, FLAG, P0, SLICE, FINNP, NINT = 6 };
+};
+// shared-memory (hot) record of one slot: contiguous, NDBL odd
+template <int NV> struct SgHot {
+    enum : int {
+        YY = 0, WT = NV, PHI = 2 * NV,                     // phi(i, l), i = 1..kSgHotRows, at PHI + (i-1)*NV + l
+        PSI = PHI + kSgHotRows * NV,                       // psi(1..3), alpha(1..3), beta(1..3), sig(1..4), vv(1..3), g(1..4): index i at base + i - 1
+        ALPHA = PSI + kSgKM, BETA = ALPHA + kSgKM, SIG = BETA + kSgKM, VV = SIG + kSgKM + 1, G = VV + kSgKM,
+        X = G + kSgKM + 1, H, HOLD, EPS, XOLD, ERK, ERKM1, T0, ABSDEL, TEND, RELEPS, ABSEPS, ROUND, ABSH,
+        INTS,                                              // 8 ints
+        NDBL = (INTS + 4) | 1
+    };
+    enum : int { I_NS = 0, I_K, I_KOLD, I_IFAIL, I_KNEW, I_NOSTEP, I_KLE4, I_BITS };
 };
 // component loops are unrolled (independent loads in flight) for the specialised kernels, real loops for the generic one
 #ifndef RAYS_SG_UNROLL
@@ -45,25 +74,31 @@ template <int NV> struct SgLayout {
 #endif
 template <int NV> struct SgUnroll { static constexpr int L = (RAYS_SG_UNROLL && NV <= 13) ? NV : 1; };
 
+// accessors of one slot.  The ray vector v shares the storage of yy: intrp forms v from yy when a segment ends and the next
+// segment starts the integrator afresh from v (iflag = 1, ode_RAYS.f90:425-505), so the two are never live at the same time.
 template <int NV> struct SgSlot {
     using L = SgLayout<NV>;
-    double *d;   // &D[slot]
-    int *n;      // &I[slot]
-    RD_INLINE double &f(int field) const { return d[(size_t)field * kSgSlots]; }
-    RD_INLINE int &i(int field) const { return n[(size_t)field * kSgSlots]; }
-    RD_INLINE double &v(int l) const { return f(L::V + l); }
-    RD_INLINE double &yy(int l) const { return f(L::YY + l); }
-    RD_INLINE double &wt(int l) const { return f(L::WT + l); }
+    using HL = SgHot<NV>;
+    double *h;   // shared: this slot's hot record
+    double *d;   // global: &D[slot]
+    int *n;      // global: &I[slot]
+    RD_INLINE double &hs(int field) const { return h[field]; }
+    RD_INLINE int &hi(int idx) const { return reinterpret_cast<int *>(h + HL::INTS)[idx]; }
+    RD_INLINE double &f(int field) const { return d[(size_t)field * kSgStride]; }
+    RD_INLINE int &i(int field) const { return n[(size_t)field * kSgStride]; }
+    RD_INLINE double &v(int l) const { return h[HL::YY + l]; }
+    RD_INLINE double &yy(int l) const { return h[HL::YY + l]; }
+    RD_INLINE double &wt(int l) const { return h[HL::WT + l]; }
     RD_INLINE double &p(int l) const { return f(L::P + l); }
     RD_INLINE double &yp(int l) const { return f(L::YP + l); }
-    RD_INLINE double &phi(int i_, int l) const { return f(L::PHI + i_ * NV + l); }
-    RD_INLINE double &alpha(int i_) const { return f(L::ALPHA + i_); }
-    RD_INLINE double &beta(int i_) const { return f(L::BETA + i_); }
-    RD_INLINE double &sig(int i_) const { return f(L::SIG + i_); }
-    RD_INLINE double &vv(int i_) const { return f(L::VV + i_); }
+    RD_INLINE double &phi(int i_, int l) const { return i_ <= kSgHotRows ? h[HL::PHI + (i_ - 1) * NV + l] : f(L::PHI + i_ * NV + l); }
+    RD_INLINE double &alpha(int i_) const { return i_ <= kSgKM ? h[HL::ALPHA + i_ - 1] : f(L::ALPHA + i_); }
+    RD_INLINE double &beta(int i_) const { return i_ <= kSgKM ? h[HL::BETA + i_ - 1] : f(L::BETA + i_); }
+    RD_INLINE double &sig(int i_) const { return i_ <= kSgKM + 1 ? h[HL::SIG + i_ - 1] : f(L::SIG + i_); }
+    RD_INLINE double &vv(int i_) const { return i_ <= kSgKM ? h[HL::VV + i_ - 1] : f(L::VV + i_); }
     RD_INLINE double &ww(int i_) const { return f(L::WW + i_); }
-    RD_INLINE double &g(int i_) const { return f(L::G + i_); }
-    RD_INLINE double &psi(int i_) const { return f(L::PSI + i_); }
+    RD_INLINE double &g(int i_) const { return i_ <= kSgKM + 1 ? h[HL::G + i_ - 1] : f(L::G + i_); }
+    RD_INLINE double &psi(int i_) const { return i_ <= kSgKM ? h[HL::PSI + i_ - 1] : f(L::PSI + i_); }
 };
 
 // ---- the pieces of `step` on slot memory: the statements of sg_block0 ... sg_intrp (ray_trace.cuh), with the loops over the
@@ -72,24 +107,24 @@ template <int NV> struct SgSlot {
 // one macro-step.
 // step, first block (ode_RAYS.f90:840-852); returns true on crash
 template <int NV> RD_INLINE bool sg2_block0(int neqn, const SgSlot<NV> &W, double &eps) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
-    const double h = W.f(L::H), x = W.f(L::X);
-    if (fabs(h) < fouru * fabs(x)) { W.f(L::H) = copysign(fouru * fabs(x), h); return true; }
+    const double h = W.hs(HL::H), x = W.hs(HL::X);
+    if (fabs(h) < fouru * fabs(x)) { W.hs(HL::H) = copysign(fouru * fabs(x), h); return true; }
     const double p5eps = 0.5 * eps;
     double sum = 0.0;
     #pragma unroll (SgUnroll<NV>::L)
     for (int l = 0; l < NV; ++l) if (l < neqn) { const double q = sg_div(W.yy(l), W.wt(l)); sum = sum + q * q; }
     const double round = twou * sg_sqrt(sum);
-    W.f(L::ROUND) = round;
+    W.hs(HL::ROUND) = round;
     if (p5eps < round) { eps = 2.0 * round * (1.0 + fouru); return true; }
     W.g(1) = 1.0; W.g(2) = 0.5; W.sig(1) = 1.0;
-    W.i(L::IFAIL) = 0;
+    W.hi(HL::I_IFAIL) = 0;
     return false;
 }
 // step, start block after the first derivative evaluation (:858-885)
 template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
     const double p5eps = 0.5 * eps;
     double tot = 0.0;
@@ -99,14 +134,14 @@ template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, 
         const double q = sg_div(yp[l], W.wt(l)); tot = tot + q * q;
     }
     const double total = sg_sqrt(tot);
-    const double h = W.f(L::H);
+    const double h = W.hs(HL::H);
     double absh = fabs(h);
     if (eps < 16.0 * total * h * h) absh = 0.25 * sg_sqrt(sg_div(eps, total));
-    W.f(L::H) = copysign(fmax(absh, fouru * fabs(W.f(L::X))), h);
-    W.f(L::HOLD) = 0.0;
-    W.i(L::K) = 1; W.i(L::KOLD) = 0;
+    W.hs(HL::H) = copysign(fmax(absh, fouru * fabs(W.hs(HL::X))), h);
+    W.hs(HL::HOLD) = 0.0;
+    W.hi(HL::I_K) = 1; W.hi(HL::I_KOLD) = 0;
     bits = (bits & ~B_START) | B_PHASE1 | B_NORND;
-    if (p5eps <= 100.0 * W.f(L::ROUND)) {
+    if (p5eps <= 100.0 * W.hs(HL::ROUND)) {
         bits &= ~B_NORND;
         #pragma unroll (SgUnroll<NV>::L)
         for (int l = 0; l < NV; ++l) if (l < neqn) W.phi(15, l) = 0.0;
@@ -114,12 +149,12 @@ template <int NV> RD_INLINE void sg2_after_start(int neqn, const SgSlot<NV> &W, 
 }
 // step, blocks 1 and 2 (:896-1015): coefficients for this step size/order, then the predicted solution p at x + h
 template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int bits, double (&p)[NV]) {
-    using L = SgLayout<NV>;
-    const int k = W.i(L::K), kold = W.i(L::KOLD);
-    int ns = W.i(L::NS);
-    const double h = W.f(L::H);
+    using HL = SgHot<NV>;
+    const int k = W.hi(HL::I_K), kold = W.hi(HL::I_KOLD);
+    int ns = W.hi(HL::I_NS);
+    const double h = W.hs(HL::H);
     const int kp1 = k + 1, kp2 = k + 2;
-    if (h != W.f(L::HOLD)) ns = 0;
+    if (h != W.hs(HL::HOLD)) ns = 0;
     if (ns <= kold) ns = ns + 1;
     const int nsp1 = ns + 1;
     if (ns <= k) {
@@ -163,7 +198,7 @@ template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int 
             W.g(i) = W.ww(1);
         }
     }
-    W.i(L::NS) = ns;
+    W.hi(HL::I_NS) = ns;
     #pragma unroll 1
     for (int i = nsp1; i <= k; ++i) {
         const double b = W.beta(i);
@@ -199,18 +234,18 @@ template <int NV> RD_INLINE void sg2_predict(int neqn, const SgSlot<NV> &W, int 
             W.phi(16, l) = (pp - y) - tau;
         } else p[l] = y + h * p[l];
     }
-    const double x = W.f(L::X);
-    W.f(L::XOLD) = x;
-    W.f(L::X) = x + h;
-    W.f(L::ABSH) = fabs(h);
+    const double x = W.hs(HL::X);
+    W.hs(HL::XOLD) = x;
+    W.hs(HL::X) = x + h;
+    W.hs(HL::ABSH) = fabs(h);
 }
 // step, after the derivative at the predicted point (:1022-1110): error estimates, accept or fail.
 // returns 0 = accepted (corrected solution formed in yy), 1 = failed: retry with the reduced step, 2 = crash (eps doubled)
 template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W, double &eps, int &bits, const double (&p)[NV], const double (&yp)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
-    const int k = W.i(L::K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
-    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps;
+    const int k = W.hi(HL::I_K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
+    const double absh = W.hs(HL::ABSH), p5eps = 0.5 * eps;
     double erkm2 = 0.0, erkm1 = 0.0, erk = 0.0;
     double dl[NV];   // yp - phi(1)
     #pragma unroll (SgUnroll<NV>::L)
@@ -235,11 +270,11 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
     } else if (0 == km2) {
         if (erkm1 <= 0.5 * erk) knew = km1;
     }
-    W.i(L::KNEW) = knew; W.f(L::ERK) = erk; W.f(L::ERKM1) = erkm1;
-    const double h = W.f(L::H);
+    W.hi(HL::I_KNEW) = knew; W.hs(HL::ERK) = erk; W.hs(HL::ERKM1) = erkm1;
+    const double h = W.hs(HL::H);
     if (err <= eps) {   // accepted: correct (:1123-1141)
-        W.i(L::KOLD) = k;
-        W.f(L::HOLD) = h;
+        W.hi(HL::I_KOLD) = k;
+        W.hs(HL::HOLD) = h;
         const bool nornd = (bits & B_NORND) != 0;
         #pragma unroll (SgUnroll<NV>::L)
         for (int l = 0; l < NV; ++l) if (l < neqn) {
@@ -254,8 +289,8 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
     }
     // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
     bits &= ~B_PHASE1;
-    const double x = W.f(L::XOLD);
-    W.f(L::X) = x;
+    const double x = W.hs(HL::XOLD);
+    W.hs(HL::X) = x;
     double nxt[NV];   // phi(i+1) as it was: row i+1 is restored after row i reads it, so read the rows top-down once
     #pragma unroll (SgUnroll<NV>::L)
     for (int l = 0; l < NV; ++l) if (l < neqn) nxt[l] = W.phi(kp1, l);
@@ -273,29 +308,29 @@ template <int NV> RD_INLINE int sg2_after_predict(int neqn, const SgSlot<NV> &W,
     }
     #pragma unroll 1
     for (int i = 2; i <= k; ++i) W.psi(i - 1) = W.psi(i) - h;
-    const int ifail = W.i(L::IFAIL) + 1;
-    W.i(L::IFAIL) = ifail;
+    const int ifail = W.hi(HL::I_IFAIL) + 1;
+    W.hi(HL::I_IFAIL) = ifail;
     double temp2 = 0.5;
     if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sg_sqrt(sg_div(p5eps, erk)); }
     if (3 <= ifail) knew = 1;
     double hn = temp2 * h;
-    W.i(L::K) = knew;
+    W.hi(HL::I_K) = knew;
     if (fabs(hn) < fouru * fabs(x)) {
-        W.f(L::H) = copysign(fouru * fabs(x), hn);
+        W.hs(HL::H) = copysign(fouru * fabs(x), hn);
         eps = eps + eps;
         return 2;
     }
-    W.f(L::H) = hn;
+    W.hs(HL::H) = hn;
     return 1;
 }
 // step, after the derivative at the corrected point (:1147-1231): update differences, choose order and step
 template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     const double fouru = 4.0 * DBL_EPSILON;
-    int k = W.i(L::K);
-    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.i(L::KNEW), ns = W.i(L::NS);
-    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), erkm1 = W.f(L::ERKM1);
-    double erk = W.f(L::ERK);
+    int k = W.hi(HL::I_K);
+    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.hi(HL::I_KNEW), ns = W.hi(HL::I_NS);
+    const double absh = W.hs(HL::ABSH), p5eps = 0.5 * eps, h = W.hs(HL::H), erkm1 = W.hs(HL::ERKM1);
+    double erk = W.hs(HL::ERK);
     if (knew == km1 || k == 12) bits &= ~B_PHASE1;
     const bool phase1 = (bits & B_PHASE1) != 0;
     const bool want_erkp1 = !phase1 && knew != km1 && kp1 <= ns;
@@ -335,18 +370,18 @@ template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W
             if (p5eps < erk) {
                 const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
-                hnew = copysign(fmax(hnew, fouru * fabs(W.f(L::X))), h);
+                hnew = copysign(fmax(hnew, fouru * fabs(W.hs(HL::X))), h);
             }
         }
     }
-    W.i(L::K) = k;
-    W.f(L::H) = hnew;
+    W.hi(HL::I_K) = k;
+    W.hs(HL::H) = hnew;
 }
 // intrp (ode_RAYS.f90:1235-1362) into the ray vector v; the segment is over, so g/ww of the slot serve as scratch
 template <int NV> RD_INLINE void sg2_intrp(int neqn, const SgSlot<NV> &W, double xout) {
-    using L = SgLayout<NV>;
-    const double hi = xout - W.f(L::X);
-    const int ki = W.i(L::KOLD) + 1;
+    using HL = SgHot<NV>;
+    const double hi = xout - W.hs(HL::X);
+    const int ki = W.hi(HL::I_KOLD) + 1;
     #pragma unroll 1
     for (int i = 1; i <= ki; ++i) W.ww(i) = kSGinv[i];
     W.g(1) = 1.0;
@@ -385,11 +420,11 @@ template <int NV> static RD_NOINLINE void sg2_predict_ool(int neqn, const SgSlot
     for (int l = 0; l < neqn; ++l) W.p(l) = p[l];
 }
 template <int NV> static RD_NOINLINE int sg2_after_predict_ool(int neqn, const SgSlot<NV> W, double eps, int bits) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     double p[NV], yp[NV];
     for (int l = 0; l < NV; ++l) { p[l] = l < neqn ? W.p(l) : 0.0; yp[l] = l < neqn ? W.yp(l) : 0.0; }
     const int r = sg2_after_predict<NV>(neqn, W, eps, bits, p, yp);
-    W.f(L::EPS) = eps; W.i(L::BITS) = bits;      // handed back through the slot
+    W.hs(HL::EPS) = eps; W.hi(HL::I_BITS) = bits;      // handed back through the slot
     return r;
 }
 template <int NV> static RD_NOINLINE int sg2_after_correct_ool(int neqn, const SgSlot<NV> W, double eps, int bits) {
@@ -404,16 +439,15 @@ template <int NV> static RD_NOINLINE int sg2_after_correct_ool(int neqn, const S
 // iteration), the statements of sg2_predict / sg2_after_predict / sg2_after_correct run on register arrays with loops bounded by
 // the compile-time kSgKM and predicated on the run-time k / ns (same operations on the same operands in the same order, so the
 // results are the general path's bit for bit; tests compare the two), and the modified state is stored in one burst.
-constexpr int kSgKM = 3;
 #define SG3_FOR(i, lo, hi) _Pragma("unroll") for (int i = (lo); i <= (hi); ++i)
 #define SG3_L(l) _Pragma("unroll") for (int l = 0; l < NV; ++l)
 
 template <int NV> RD_INLINE void sg3_predict(const SgSlot<NV> &W, double (&p)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     constexpr int KM = kSgKM;
-    const int k = W.i(L::K), kold = W.i(L::KOLD);
-    int ns = W.i(L::NS);
-    const double h = W.f(L::H), hold = W.f(L::HOLD), x = W.f(L::X);
+    const int k = W.hi(HL::I_K), kold = W.hi(HL::I_KOLD);
+    int ns = W.hi(HL::I_NS);
+    const double h = W.hs(HL::H), hold = W.hs(HL::HOLD), x = W.hs(HL::X);
     const int kp1 = k + 1, kp2 = k + 2;
     double psi[KM + 2], alpha[KM + 2], beta[KM + 2], sig[KM + 3], vv[KM + 3], ww[KM + 3], g[KM + 3];
     double phi[KM + 3][NV], yy[NV];
@@ -473,22 +507,22 @@ template <int NV> RD_INLINE void sg3_predict(const SgSlot<NV> &W, double (&p)[NV
     }
     SG3_L(l) p[l] = yy[l] + h * p[l];
     // burst store of what changed
-    W.i(L::NS) = ns;
+    W.hi(HL::I_NS) = ns;
     SG3_FOR(i, 1, KM) if (i <= k) { W.psi(i) = psi[i]; W.alpha(i) = alpha[i]; W.beta(i) = beta[i]; W.vv(i) = vv[i]; }
     SG3_FOR(i, 1, KM + 1) if (i <= kp1) { W.sig(i) = sig[i]; W.g(i) = g[i]; }
     SG3_FOR(i, 1, KM + 2) if (i <= kp2) SG3_L(l) W.phi(i, l) = phi[i][l];
-    W.f(L::XOLD) = x;
-    W.f(L::X) = x + h;
-    W.f(L::ABSH) = fabs(h);
+    W.hs(HL::XOLD) = x;
+    W.hs(HL::X) = x + h;
+    W.hs(HL::ABSH) = fabs(h);
 }
 
 template <int NV> RD_INLINE int sg3_after_predict(const SgSlot<NV> &W, double &eps, int &bits, const double (&p)[NV], const double (&yp)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     constexpr int KM = kSgKM;
     const double fouru = 4.0 * DBL_EPSILON;
-    const int k = W.i(L::K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
-    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), xold = W.f(L::XOLD);
-    const int ifail0 = W.i(L::IFAIL);
+    const int k = W.hi(HL::I_K), kp1 = k + 1, km1 = k - 1, km2 = k - 2;
+    const double absh = W.hs(HL::ABSH), p5eps = 0.5 * eps, h = W.hs(HL::H), xold = W.hs(HL::XOLD);
+    const int ifail0 = W.hi(HL::I_IFAIL);
     double sig[KM + 2], g[KM + 2], beta[KM + 1], psi[KM + 1], wt[NV], phi[KM + 2][NV];
     SG3_FOR(i, 1, KM + 1) { sig[i] = W.sig(i); g[i] = W.g(i); }
     SG3_FOR(i, 1, KM) { beta[i] = W.beta(i); psi[i] = W.psi(i); }
@@ -518,16 +552,16 @@ template <int NV> RD_INLINE int sg3_after_predict(const SgSlot<NV> &W, double &e
     } else if (0 == km2) {
         if (erkm1 <= 0.5 * erk) knew = km1;
     }
-    W.i(L::KNEW) = knew; W.f(L::ERK) = erk; W.f(L::ERKM1) = erkm1;
+    W.hi(HL::I_KNEW) = knew; W.hs(HL::ERK) = erk; W.hs(HL::ERKM1) = erkm1;
     if (err <= eps) {   // accepted: correct (:1123-1141)
-        W.i(L::KOLD) = k;
-        W.f(L::HOLD) = h;
+        W.hi(HL::I_KOLD) = k;
+        W.hs(HL::HOLD) = h;
         SG3_L(l) W.yy(l) = p[l] + h * g_kp1 * dl[l];
         return 0;
     }
     // step failed (:1076-1110): restore x, phi, psi; halve (or more) the step
     bits &= ~B_PHASE1;
-    W.f(L::X) = xold;
+    W.hs(HL::X) = xold;
     SG3_FOR(i, 1, KM) if (i <= k) {        // ascending: row i + 1 is still the unrestored one when row i reads it
         const Rcp bi = rcp_of(beta[i]);
         SG3_L(l) phi[i][l] = sg_quot(phi[i][l] - phi[i + 1][l], bi);
@@ -536,29 +570,29 @@ template <int NV> RD_INLINE int sg3_after_predict(const SgSlot<NV> &W, double &e
     SG3_FOR(i, 1, KM) if (i <= k) SG3_L(l) W.phi(i, l) = phi[i][l];
     SG3_FOR(i, 1, KM - 1) if (i <= k - 1) W.psi(i) = psi[i];
     const int ifail = ifail0 + 1;
-    W.i(L::IFAIL) = ifail;
+    W.hi(HL::I_IFAIL) = ifail;
     double temp2 = 0.5;
     if (3 < ifail) { if (p5eps < 0.25 * erk) temp2 = sg_sqrt(sg_div(p5eps, erk)); }
     if (3 <= ifail) knew = 1;
     const double hn = temp2 * h;
-    W.i(L::K) = knew;
+    W.hi(HL::I_K) = knew;
     if (fabs(hn) < fouru * fabs(xold)) {
-        W.f(L::H) = copysign(fouru * fabs(xold), hn);
+        W.hs(HL::H) = copysign(fouru * fabs(xold), hn);
         eps = eps + eps;
         return 2;
     }
-    W.f(L::H) = hn;
+    W.hs(HL::H) = hn;
     return 1;
 }
 
 template <int NV> RD_INLINE void sg3_after_correct(const SgSlot<NV> &W, double eps, int &bits, const double (&yp)[NV]) {
-    using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
     constexpr int KM = kSgKM;
     const double fouru = 4.0 * DBL_EPSILON;
-    int k = W.i(L::K);
-    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.i(L::KNEW), ns = W.i(L::NS);
-    const double absh = W.f(L::ABSH), p5eps = 0.5 * eps, h = W.f(L::H), erkm1 = W.f(L::ERKM1), x = W.f(L::X);
-    double erk = W.f(L::ERK);
+    int k = W.hi(HL::I_K);
+    const int kp1 = k + 1, kp2 = k + 2, km1 = k - 1, knew = W.hi(HL::I_KNEW), ns = W.hi(HL::I_NS);
+    const double absh = W.hs(HL::ABSH), p5eps = 0.5 * eps, h = W.hs(HL::H), erkm1 = W.hs(HL::ERKM1), x = W.hs(HL::X);
+    double erk = W.hs(HL::ERK);
     double phi[KM + 3][NV], wt[NV];
     SG3_FOR(i, 1, KM + 2) SG3_L(l) phi[i][l] = W.phi(i, l);
     SG3_L(l) wt[l] = W.wt(l);
@@ -601,8 +635,38 @@ template <int NV> RD_INLINE void sg3_after_correct(const SgSlot<NV> &W, double e
             }
         }
     }
-    W.i(L::K) = k;
-    W.f(L::H) = hnew;
+    W.hi(HL::I_K) = k;
+    W.hs(HL::H) = hnew;
+}
+
+// intrp for kold <= kSgKM (ki = kold + 1 <= 4) on registers: the statements of sg2_intrp, loops bounded at compile time
+template <int NV> RD_INLINE void sg3_intrp(const SgSlot<NV> &W, double xout) {
+    using HL = SgHot<NV>;
+    constexpr int KI = kSgKM + 1;
+    const double hi = xout - W.hs(HL::X);
+    const int ki = W.hi(HL::I_KOLD) + 1;
+    double w[KI + 2], g[KI + 1], psi[KI];
+    SG3_FOR(i, 1, KI) w[i] = kSGinv[i];
+    w[KI + 1] = 0.0;
+    SG3_FOR(i, 1, KI - 1) psi[i] = W.psi(i);
+    g[1] = 1.0;
+    SG3_FOR(i, 2, KI) g[i] = 0.0;
+    double term = 0.0;
+    SG3_FOR(j, 2, KI) if (j <= ki) {
+        const double psijm1 = psi[j - 1];
+        const Rcp pj = rcp_of(psijm1);
+        const double gamma = sg_quot(hi + term, pj);
+        const double eta = sg_quot(hi, pj);
+        SG3_FOR(i, 1, KI - 1) if (i <= ki + 1 - j) w[i] = gamma * w[i] - eta * w[i + 1];
+        g[j] = w[1];
+        term = psijm1;
+    }
+    double yo[NV];
+    SG3_L(l) yo[l] = 0.0;
+    _Pragma("unroll") for (int i = KI; i >= 1; --i) if (i <= ki) {       // j = 1..ki of the reference: i = ki + 1 - j descends
+        SG3_L(l) yo[l] = yo[l] + g[i] * W.phi(i, l);
+    }
+    SG3_L(l) W.v(l) = W.yy(l) + hi * yo[l];
 }
 
 // streaming copy-out of one finished ray by the whole warp: out of line, it runs once per ray
@@ -613,23 +677,25 @@ static RD_NOINLINE void sg2_flush_row(const TraceArgs &a, long long ir, int np, 
         copy_row_to_host(a.host_residual + (size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf, a.residual + rw * a.npoints_alloc, np, lane);
 }
 
-template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgSlots * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
+// global record bytes of one CTA; shared-memory bytes of one slot; shared-memory bytes besides the slots (rings; the deposition
+// bins come on top)
+template <int NV> constexpr size_t sg2_state_bytes_per_cta() { return (size_t)kSgStride * (SgLayout<NV>::NDBL * 8 + SgLayout<NV>::NINT * 4); }
+template <int NV> constexpr size_t sg2_hot_bytes_per_slot() { return (size_t)SgHot<NV>::NDBL * 8; }
+constexpr size_t sg2_ring_bytes() { return (size_t)kSgNQ * kSgRingCap * sizeof(unsigned short); }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------------
 #ifndef RAYS_SG_FAST
 #define RAYS_SG_FAST 1
 #endif
-#ifndef RAYS_SG2_MIN_CTAS
-#define RAYS_SG2_MIN_CTAS 2
-#endif
 template <class T>
-__global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
-    constexpr int S = kSgSlots;                 // slots per CTA: two per thread
     constexpr int NT = kSgBlock;
-    constexpr int NW = kSgWarps;
+    constexpr int NW = kSgBlock / 32;
     using L = SgLayout<NV>;
+    using HL = SgHot<NV>;
+    const int S = a.sg_slots;                   // slots of this CTA
     const int nv = T::nv();
     const rays_cfg &c = g_dc.c;
     const int tid = threadIdx.x;
@@ -637,83 +703,95 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
     const int warp = tid >> 5;
     const int maxnum = 500;
     const double fouru = 4.0 * DBL_EPSILON;
-    __shared__ int s_kind[S];
-    __shared__ int s_list[NT];
-    __shared__ int s_wcnt[NW][2][6];
-    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_tail[kSgNQ];
+    __shared__ unsigned s_head[2][kSgNQ];
+    __shared__ unsigned char s_kind[kSgRingCap];
+    __shared__ int s_exhausted;
+    // dynamic shared memory: [deposition bins | hot records | rings]
+    double *const hot = reinterpret_cast<double *>(s_dep_bins) + ((a.dep_smem + 15) / 16) * 2;
+    unsigned short *const ring = reinterpret_cast<unsigned short *>(hot + (size_t)S * HL::NDBL);
     const size_t gcta = blockIdx.x;
-    double *const D = a.sg_state + gcta * L::NDBL * S;
-    int *const I = reinterpret_cast<int *>(a.sg_state + (size_t)gridDim.x * L::NDBL * S) + gcta * L::NINT * S;
+    double *const D = a.sg_state + gcta * L::NDBL * kSgStride;
+    int *const I = reinterpret_cast<int *>(a.sg_state + (size_t)gridDim.x * L::NDBL * kSgStride) + gcta * L::NINT * kSgStride;
     const bool binning = a.dep_acc != nullptr && T::damp();
     const DepBins dbins = dep_begin(a, binning);
     const bool streaming = a.host_ray_vec != nullptr || a.host_residual != nullptr;
     unsigned long long my_steps = 0;
     unsigned my_rhs = 0;
-    unsigned iter = 0;
-    bool exhausted = false;                     // CTA-uniform
-    s_kind[tid] = K_IDLE;
-    s_kind[tid + NT] = K_IDLE;
-    __syncthreads();
+    if (tid < kSgNQ) { s_tail[tid] = tid == Q_IDLE ? (unsigned)S : 0u; s_head[0][tid] = 0u; s_head[1][tid] = 0u; }
+    if (tid == 0) s_exhausted = 0;
+    for (int j = tid; j < S; j += NT) { ring[Q_IDLE * kSgRingCap + j] = (unsigned short)j; s_kind[j] = K_IDLE; }
 
-    for (;; ++iter) {
-        // thread t keeps the books of slots t and t + NT.  ---- 1. census of the CTA's slots: predictor | corrector | segment
-        // boundary | restart | finished | idle.  Three barriers per iteration on the common path (census, list, end of macro-step).
-        int k0 = s_kind[tid], k1 = s_kind[tid + NT];
-        unsigned b0[6], b1[6];
+    // push slot `sl` (or nothing: q < 0) onto ring q: one shared-memory atomic per ring and warp
+    auto push = [&](int q, int sl) {
+        const unsigned m = __match_any_sync(0xffffffffu, q);
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if ((int)lane == leader && q >= 0) base = atomicAdd(&s_tail[q], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (q >= 0) ring[q * kSgRingCap + ((base + __popc(m & ((1u << lane) - 1u))) & (kSgRingCap - 1))] = (unsigned short)sl;
+    };
+
+    for (unsigned iter = 0;; ++iter) {
+        __syncthreads();     // THE barrier of the iteration: the pushes of the last one are visible, the heads of this one are written
+        const int par = iter & 1;
+        unsigned hd[kSgNQ], cnt[kSgNQ];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int kq = q == 0 ? K_PRED : (q == 1 ? K_CORR : (q == 2 ? K_CHECK : (q == 3 ? K_START : (q == 4 ? K_FIN : K_IDLE))));
-            b0[q] = __ballot_sync(0xffffffffu, k0 == kq || (q == 3 && k0 == K_BEGIN));
-            b1[q] = __ballot_sync(0xffffffffu, k1 == kq || (q == 3 && k1 == K_BEGIN));
+        for (int q = 0; q < kSgNQ; ++q) { hd[q] = s_head[par][q]; cnt[q] = s_tail[q] - hd[q]; }
+        const bool exhausted = s_exhausted != 0;
+        // ---- the choice every thread comes to: finished rays first, then a refill when it pays (or nothing else can fill the
+        // CTA), else the macro-step most slots wait for; the rare kinds get their turn when 16 have gathered, when nothing
+        // else is left, or every 256th iteration
+        int q = -1;
+        {
+            int best = Q_PRED;
+            unsigned bc = cnt[Q_PRED];
+            if (cnt[Q_CORR] > bc) { best = Q_CORR; bc = cnt[Q_CORR]; }
+            if (cnt[Q_CHECK] > bc) { best = Q_CHECK; bc = cnt[Q_CHECK]; }
+            int rare = Q_START;
+            unsigned rc = cnt[Q_START];
+            if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }
+            if (cnt[Q_GCORR] > rc) { rare = Q_GCORR; rc = cnt[Q_GCORR]; }
+            if (cnt[Q_FIN] > 0) q = Q_FIN;
+            else if (cnt[Q_IDLE] > 0 && !exhausted && (cnt[Q_IDLE] >= 32u || bc < (unsigned)NT)) q = Q_IDLE;
+            else if (rc > 0 && (rc >= 16u || bc == 0u || (iter & 255u) == 0u)) q = rare;
+            else if (bc > 0) q = best;
         }
-        if (lane < 6) { s_wcnt[warp][0][lane] = __popc(b0[lane]); s_wcnt[warp][1][lane] = __popc(b1[lane]); }
-        __syncthreads();
-        int tot[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            tot[q] = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) tot[q] += s_wcnt[w][0][q] + s_wcnt[w][1][q];
-        }
-        // ---- 2a. rays that ended (one iteration in ~15): streaming copy-out by the warp that keeps the slot's books; slot idle
-        if (tot[4] > 0) {
-            if (streaming) {
-                for (int half = 0; half < 2; ++half) {
-                    unsigned m = half ? b1[4] : b0[4];
-                    while (m) {
-                        const int sl = warp * 32 + __ffs(m) - 1 + NT * half;
-                        m &= m - 1;
-                        const SgSlot<NV> F{D + sl, I + sl};
-                        const long long ir = (long long)F.f(L::IRAY);
-                        const int np = F.i(L::FINNP), pf = F.i(L::P0);
-                        sg2_flush_row(a, ir, np, pf, gcta * S + sl, nv, lane);
-                    }
+        if (q < 0) break;      // every slot idle and the queue empty
+        const unsigned take = q == Q_FIN ? cnt[Q_FIN] : (cnt[q] < (unsigned)NT ? cnt[q] : (unsigned)NT);
+        if (tid < kSgNQ) s_head[par ^ 1][tid] = hd[tid] + (tid == q ? take : 0u);
+        // ---- finished rays: streaming copy-out by the warps, slot idle
+        if (q == Q_FIN) {
+            for (unsigned e = warp; e < take; e += NW) {
+                const int sl = ring[Q_FIN * kSgRingCap + ((hd[Q_FIN] + e) & (kSgRingCap - 1))];
+                if (streaming) {
+                    const SgSlot<NV> F{hot + (size_t)sl * HL::NDBL, D + sl, I + sl};
+                    const long long ir = (long long)F.f(L::IRAY);
+                    const int np = F.i(L::FINNP), pf = F.i(L::P0);
+                    sg2_flush_row(a, ir, np, pf, gcta * S + sl, nv, lane);
                 }
+                if (lane == 0) { s_kind[sl] = K_IDLE; const unsigned pos = atomicAdd(&s_tail[Q_IDLE], 1u); ring[Q_IDLE * kSgRingCap + (pos & (kSgRingCap - 1))] = (unsigned short)sl; }
             }
-            if (k0 == K_FIN) s_kind[tid] = K_IDLE;
-            if (k1 == K_FIN) s_kind[tid + NT] = K_IDLE;
-            __syncthreads();
             continue;
         }
-        // ---- 2b. refill idle slots from the work queue: one atomic per CTA
-        if (tot[5] > 0 && !exhausted) {
-            const int total = tot[5];
-            int before0 = 0, before1 = 0, all0 = 0;     // slots are handed out in slot order: half 0 of every warp, then half 1
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { all0 += s_wcnt[w][0][5]; if (w < warp) { before0 += s_wcnt[w][0][5]; before1 += s_wcnt[w][1][5]; } }
-            if (tid == 0) s_base = atomicAdd(a.queue, (unsigned long long)total);
-            __syncthreads();
-            const unsigned long long base = s_base;
-            for (int half = 0; half < 2; ++half) {
-                const bool want = half ? (k1 == K_IDLE) : (k0 == K_IDLE);
-                const unsigned wb = half ? b1[5] : b0[5];
-                if (want) {
-                    const long long idx = (long long)(base + (unsigned long long)((half ? all0 + before1 : before0) + __popc(wb & ((1u << lane) - 1u))));
-                    if (idx < a.nray) {
-                        const int sl = tid + NT * half;
-                        const SgSlot<NV> W{D + sl, I + sl};
+        const int slot = tid < (int)take ? (int)ring[q * kSgRingCap + ((hd[q] + tid) & (kSgRingCap - 1))] : -1;
+        // ---- refill idle slots from the work queue: one global atomic per warp
+        if (q == Q_IDLE) {
+            const unsigned want = __ballot_sync(0xffffffffu, slot >= 0);
+            int nq = -1;
+            if (want) {
+                unsigned long long base = 0;
+                const int leader = __ffs(want) - 1;
+                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(want));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (slot >= 0) {
+                    const long long idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+                    nq = Q_IDLE;
+                    if (idx >= a.nray) s_exhausted = 1;
+                    else {
+                        const SgSlot<NV> W{hot + (size_t)slot * HL::NDBL, D + slot, I + slot};
                         const long long iray = a.order ? (long long)a.order[idx] : idx;
-                        const size_t row = streaming ? gcta * S + sl : (size_t)iray;
+                        const size_t row = streaming ? gcta * S + slot : (size_t)iray;
                         W.f(L::IRAY) = (double)iray;
                         W.f(L::PWR) = a.ray_pwr_wt ? a.ray_pwr_wt[iray] : 0.0;
                         W.i(L::SLICE) = 0;
@@ -725,7 +803,7 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                             W.f(L::RPREV) = k.resid_prev; W.f(L::RLAST) = k.resid_last; W.f(L::RMAX) = k.resid_max;
                             W.f(L::DEPX) = k.dep_x; W.f(L::DEPQ) = k.dep_Q; W.f(L::REL) = k.rel_err; W.f(L::ABS) = k.abs_err;
                             W.i(L::P0) = streaming ? k.nstep + 1 : 0;
-                            W.i(L::BITS) = 0;
+                            W.hi(HL::I_BITS) = 0;
                         } else {
                             W.f(L::S_) = 0.0; W.f(L::SOUT) = 0.0; W.i(L::NSTEP) = 0; W.i(L::FLAG) = 0; W.i(L::P0) = 0;
                             W.f(L::REL) = c.rel_err0; W.f(L::ABS) = c.abs_err0;   // ray_init_SG_ode (SG_ode_m.f90:73-85)
@@ -737,67 +815,39 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                             }
                             if (a.residual) a.residual[row * a.npoints_alloc] = 0.0;
                             if (a.start_ray_vec) for (int i = 0; i < nv; ++i) a.start_ray_vec[(size_t)iray * nv + i] = v[i];
-                            W.i(L::BITS) = B_FIRST;
+                            W.hi(HL::I_BITS) = B_FIRST;
                         }
 #pragma unroll
                         for (int i = 0; i < NV; ++i) if (i < nv) W.v(i) = v[i];
-                        s_kind[sl] = K_CHECK;
+                        W.hs(HL::EPS) = 0.0;
+                        s_kind[slot] = K_CHECK;
+                        nq = Q_CHECK;
                     }
                 }
             }
-            if (base + (unsigned long long)total >= (unsigned long long)a.nray) exhausted = true;
-            __syncthreads();
+            push(nq, slot);
             continue;
         }
-        if (tot[0] + tot[1] + tot[2] + tot[3] == 0) break;     // every slot idle, queue empty
-        // ---- 3. the whole CTA takes the KIND most slots wait for (restarts after a tolerance raise are rare and get their turn
-        // every 16th iteration): thread j runs the j-th slot of that kind, so every warp executes the same code for about the same time
-        int slot = -1;
-        {
-            int q = 0, best = tot[0];
-            if (tot[1] > best) { q = 1; best = tot[1]; }
-            if (tot[2] > best) { q = 2; best = tot[2]; }
-            if (tot[3] > 0 && (best == 0 || (iter & 15u) == 0u)) q = 3;
-            // position of my slots among the slots of kind q, in slot order (half 0 of all warps first)
-            int bef0 = 0, bef1 = 0, allh0 = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const int c0 = q == 0 ? s_wcnt[w][0][0] : (q == 1 ? s_wcnt[w][0][1] : (q == 2 ? s_wcnt[w][0][2] : s_wcnt[w][0][3]));
-                const int c1 = q == 0 ? s_wcnt[w][1][0] : (q == 1 ? s_wcnt[w][1][1] : (q == 2 ? s_wcnt[w][1][2] : s_wcnt[w][1][3]));
-                allh0 += c0;
-                if (w < warp) { bef0 += c0; bef1 += c1; }
-            }
-            const unsigned m0 = q == 0 ? b0[0] : (q == 1 ? b0[1] : (q == 2 ? b0[2] : b0[3]));
-            const unsigned m1 = q == 0 ? b1[0] : (q == 1 ? b1[1] : (q == 2 ? b1[2] : b1[3]));
-            const unsigned below = (1u << lane) - 1u;
-            if (m0 & (1u << lane)) { const int pos = bef0 + __popc(m0 & below); if (pos < NT) s_list[pos] = tid; }
-            if (m1 & (1u << lane)) { const int pos = allh0 + bef1 + __popc(m1 & below); if (pos < NT) s_list[pos] = tid + NT; }
-            __syncthreads();
-            const int cnt_q = q == 0 ? tot[0] : (q == 1 ? tot[1] : (q == 2 ? tot[2] : tot[3]));
-            if (tid < (cnt_q < NT ? cnt_q : NT)) slot = s_list[tid];
-        }
-        // ---- 4. one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
+        // ---- one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping.  q is the same for the whole CTA:
+        // fast (register-resident) or general bookkeeping is not a per-thread choice
+        const bool gen = q == Q_GPRED || q == Q_GCORR || T::GENERIC || !RAYS_SG_FAST;
         int next = -1;
         if (slot >= 0) {
-            const SgSlot<NV> W{D + slot, I + slot};
+            const SgSlot<NV> W{hot + (size_t)slot * HL::NDBL, D + slot, I + slot};
             const int kind = s_kind[slot];
-            int bits = W.i(L::BITS);
+            int bits = W.hi(HL::I_BITS);
             next = kind;
             int req = 0;   // 1: derivative at yy (start), 2: at the predicted p, 3: at the corrected yy,
                            // 4: check_save of the new point v + the start derivative of the next segment there
             bool stop = false, did_not_start = false, crashed = false, enter = false, de_top = false, have_f1 = false;
             int f1_code = 0;
-            int flag = W.i(L::FLAG);
-            double eps = W.f(L::EPS);
-            const long long iray = (long long)W.f(L::IRAY);
-            const size_t row = streaming ? gcta * S + slot : (size_t)iray;
+            int flag = INT_MIN;            // the ray's sticky flag lives in the global record: read where it can change
+            double eps = W.hs(HL::EPS);
             double uu[NV], ff[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) { uu[i] = 0.0; ff[i] = 0.0; }
-            bool fastk = false;   // this macro-step runs the register-resident bookkeeping
             if (kind == K_PRED) {
-                fastk = !T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND);
-                if (fastk) sg3_predict<NV>(W, uu);
+                if (!gen) sg3_predict<NV>(W, uu);
                 else if (T::GENERIC) sg2_predict<NV>(nv, W, bits, uu);
                 else {
                     sg2_predict_ool<NV>(nv, W, bits);
@@ -811,10 +861,12 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
             else if (kind == K_BEGIN) enter = true;
             else {   // K_CHECK
                 req = 4;
+                flag = W.i(L::FLAG);
                 if (bits & B_INTRP) {   // past the output point: interpolate, segment done (iflag = 2)
                     bits &= ~B_INTRP;
                     const double sout = W.f(L::SOUT);
-                    sg2_intrp<NV>(nv, W, sout);
+                    if (!T::GENERIC && RAYS_SG_FAST && W.hi(HL::I_KOLD) <= kSgKM) sg3_intrp<NV>(W, sout);
+                    else sg2_intrp<NV>(nv, W, sout);
                     W.f(L::S_) = sout;
                     const int sn = W.i(L::SLICE) + 1;
                     W.i(L::SLICE) = sn;
@@ -824,7 +876,7 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                         for (int i = 0; i < NV; ++i) v[i] = i < nv ? W.v(i) : 0.0;
                         const int nstep = W.i(L::NSTEP);
                         RayCarry k{sout, sout, W.f(L::RPREV), W.f(L::RLAST), W.f(L::RMAX), W.f(L::DEPX), W.f(L::DEPQ), W.f(L::REL), W.f(L::ABS), nstep, flag};
-                        suspend_ray(a, iray, v, nv, k);
+                        suspend_ray(a, (long long)W.f(L::IRAY), v, nv, k);
                         W.i(L::FINNP) = nstep + 1 - W.i(L::P0);
                         req = 0; next = K_FIN;
                     }
@@ -835,9 +887,8 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
             // first derivative), saves the point and runs the loop-top tests of ray_tracing.f90:118-172
             if (req) {
                 if (req != 2) {
-                    const int ufield = req == 4 ? L::V : L::YY;
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) if (i < nv) uu[i] = W.f(ufield + i);
+                    for (int i = 0; i < NV; ++i) if (i < nv) uu[i] = W.yy(i);      // v shares yy's storage
                 }
                 Eq<NSM> e;
                 equilibrium<T::EQ, T::NS, true>(uu[0], uu[1], uu[2], e);
@@ -871,6 +922,7 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                             const int nstep = W.i(L::NSTEP) + 1;
                             W.i(L::NSTEP) = nstep;
                             const int pp = nstep - W.i(L::P0);
+                            const size_t row = streaming ? gcta * S + slot : (size_t)(long long)W.f(L::IRAY);
                             if (a.ray_vec) {
                                 double *dst = a.ray_vec + (row * a.npoints_alloc + pp) * nv;
                                 if (T::GENERIC) store_point(dst, uu, nv); else store_point_fixed<NV>(dst, uu);
@@ -909,30 +961,30 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                         else if (req == 1) { sg2_after_start<NV>(nv, W, eps, bits, ff); next = K_PRED; }
                         else if (req == 2) {
                             int r;
-                            if (fastk) r = sg3_after_predict<NV>(W, eps, bits, uu, ff);
+                            if (!gen) r = sg3_after_predict<NV>(W, eps, bits, uu, ff);
                             else if (T::GENERIC) r = sg2_after_predict<NV>(nv, W, eps, bits, uu, ff);
                             else {
 #pragma unroll
                                 for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
                                 r = sg2_after_predict_ool<NV>(nv, W, eps, bits);
-                                eps = W.f(L::EPS); bits = W.i(L::BITS);
+                                eps = W.hs(HL::EPS); bits = W.hi(HL::I_BITS);
                             }
                             if (r == 0) next = K_CORR;
                             else if (r == 1) next = K_PRED;   // failed: predict again with the reduced step
                             else crashed = true;
                         } else {
-                            if (!T::GENERIC && RAYS_SG_FAST && W.i(L::K) <= kSgKM && (bits & B_NORND)) sg3_after_correct<NV>(W, eps, bits, ff);
+                            if (!gen) sg3_after_correct<NV>(W, eps, bits, ff);
                             else if (T::GENERIC) sg2_after_correct<NV>(nv, W, eps, bits, ff);
                             else {
 #pragma unroll
                                 for (int i = 0; i < NV; ++i) if (i < nv) W.yp(i) = ff[i];
                                 bits = sg2_after_correct_ool<NV>(nv, W, eps, bits);
                             }
-                            const int nostep = W.i(L::NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
-                            W.i(L::NOSTEP) = nostep;
-                            int kle4 = W.i(L::KLE4) + 1;
-                            if (4 < W.i(L::KOLD)) kle4 = 0;
-                            W.i(L::KLE4) = kle4;
+                            const int nostep = W.hi(HL::I_NOSTEP) + 1;       // de: step counter and stiffness test (ode_RAYS.f90:578-590)
+                            W.hi(HL::I_NOSTEP) = nostep;
+                            int kle4 = W.hi(HL::I_KLE4) + 1;
+                            if (4 < W.hi(HL::I_KOLD)) kle4 = 0;
+                            W.hi(HL::I_KLE4) = kle4;
                             if (50 <= kle4) bits |= B_STIFF;
                             de_top = true;
                         }
@@ -948,37 +1000,34 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                     if (eps <= 0.0) { stop = true; flag = RAYS_STOP_SG_EPS_LE_0; }
                     else {
                         const double del = sout - s;
-                        W.f(L::T0) = s;
-                        W.f(L::ABSDEL) = fabs(del);
-                        W.f(L::TEND) = s + 10.0 * del;
-                        W.i(L::NOSTEP) = 0; W.i(L::KLE4) = 0;
-                        W.f(L::RELEPS) = rel_err / eps;
-                        W.f(L::ABSEPS) = abs_err / eps;
+                        W.hs(HL::T0) = s;
+                        W.hs(HL::ABSDEL) = fabs(del);
+                        W.hs(HL::TEND) = s + 10.0 * del;
+                        W.hi(HL::I_NOSTEP) = 0; W.hi(HL::I_KLE4) = 0;
+                        W.hs(HL::RELEPS) = rel_err / eps;
+                        W.hs(HL::ABSEPS) = abs_err / eps;
                         bits = (bits & B_FIRST) | B_START | B_NORND;
-                        W.f(L::X) = s;
-#pragma unroll
-                        for (int l = 0; l < NV; ++l) if (l < nv) W.yy(l) = W.v(l);
-                        W.f(L::H) = copysign(fmax(fabs(sout - s), fouru * fabs(s)), sout - s);
-                        W.i(L::NS) = 0; W.i(L::K) = 0; W.i(L::KOLD) = 0; W.f(L::HOLD) = 0.0;
+                        W.hs(HL::X) = s;
+                        // yy = v: the same storage
+                        W.hs(HL::H) = copysign(fmax(fabs(sout - s), fouru * fabs(s)), sout - s);
+                        W.hi(HL::I_NS) = 0; W.hi(HL::I_K) = 0; W.hi(HL::I_KOLD) = 0; W.hs(HL::HOLD) = 0.0;
                         de_top = true;
                     }
                 }
             }
             if (de_top && !stop) {   // top of de's loop (ode_RAYS.f90:509-562)
-                const double x = W.f(L::X);
-                if (W.f(L::ABSDEL) <= fabs(x - W.f(L::T0))) {   // past the output point: the segment ends (the interpolation waits for its batch)
+                const double x = W.hs(HL::X);
+                if (W.hs(HL::ABSDEL) <= fabs(x - W.hs(HL::T0))) {   // past the output point: the segment ends (the interpolation waits for its batch)
                     bits |= B_INTRP;
                     next = K_CHECK;
-                } else if (maxnum <= W.i(L::NOSTEP)) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
+                } else if (maxnum <= W.hi(HL::I_NOSTEP)) {             // iflag = 4 / 5: error return, the ray stops with y = yy, t = x
                     flag = (bits & B_STIFF) ? RAYS_STOP_SG_STIFF : RAYS_STOP_SG_MAXNUM;
-#pragma unroll
-                    for (int l = 0; l < NV; ++l) if (l < nv) W.v(l) = W.yy(l);
-                    W.f(L::S_) = x;
+                    W.f(L::S_) = x;      // v = yy: the same storage
                     stop = true;
                 } else {
-                    const double h = W.f(L::H);
-                    W.f(L::H) = copysign(fmin(fabs(h), fabs(W.f(L::TEND) - x)), h);
-                    const double releps = W.f(L::RELEPS), abseps = W.f(L::ABSEPS);
+                    const double h = W.hs(HL::H);
+                    W.hs(HL::H) = copysign(fmin(fabs(h), fabs(W.hs(HL::TEND) - x)), h);
+                    const double releps = W.hs(HL::RELEPS), abseps = W.hs(HL::ABSEPS);
 #pragma unroll (SgUnroll<NV>::L)
                     for (int l = 0; l < NV; ++l) if (l < nv) W.wt(l) = releps * fabs(W.yy(l)) + abseps;
                     if (sg2_block0<NV>(nv, W, eps)) crashed = true;   // (a start derivative evaluated above is dropped: the restart evaluates it again)
@@ -992,19 +1041,18 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                 }
             }
             if (crashed && !stop) {   // iflag = 3: tolerances raised (ode_RAYS.f90:566-575), then SG_ode's test (SG_ode_m.f90:138-149)
-                const double rel_err = eps * W.f(L::RELEPS), abs_err = eps * W.f(L::ABSEPS);
+                const double rel_err = eps * W.hs(HL::RELEPS), abs_err = eps * W.hs(HL::ABSEPS);
                 W.f(L::REL) = rel_err; W.f(L::ABS) = abs_err;
-#pragma unroll
-                for (int l = 0; l < NV; ++l) if (l < nv) W.v(l) = W.yy(l);
-                W.f(L::S_) = W.f(L::X);
+                W.f(L::S_) = W.hs(HL::X);        // v = yy: the same storage
                 const double total_error = fabs(rel_err) + fabs(abs_err);
                 if (total_error > c.SG_error_limit) { flag = RAYS_STOP_ODE_TOTAL_ERROR; stop = true; }
                 else next = K_BEGIN;           // SG_ode loops: ode again from the current s to sout
             }
-            W.f(L::EPS) = eps;
-            W.i(L::FLAG) = flag;
-            W.i(L::BITS) = bits;
+            W.hs(HL::EPS) = eps;
+            W.hi(HL::I_BITS) = bits;
             if (stop) {
+                const long long iray = (long long)W.f(L::IRAY);
+                if (flag == INT_MIN) flag = W.i(L::FLAG);
                 a.stop_code[iray] = flag;
                 const int nstep = W.i(L::NSTEP);
                 if (did_not_start) {   // only npoints, flag and the first point are set (ray_tracing.f90:101-112)
@@ -1025,11 +1073,23 @@ __global__ void __launch_bounds__(kSgBlock, RAYS_SG2_MIN_CTAS) trace_sg2_kernel(
                 }
                 W.i(L::FINNP) = did_not_start ? 1 : nstep + 1 - W.i(L::P0);
                 next = K_FIN;
-            }
+            } else if (flag != INT_MIN) W.i(L::FLAG) = flag;
+            s_kind[slot] = (unsigned char)next;
         }
-        // ---- 5. books: the kinds the macro-steps left behind
-        if (slot >= 0) s_kind[slot] = next;
-        __syncthreads();
+        // ---- the ring of the next macro-step: predictor / corrector of a slot at order > 3 (or with propagated-roundoff
+        // control on) go to the rings of the general code
+        int nq = -1;
+        if (slot >= 0) {
+            if (next == K_PRED || next == K_CORR) {
+                const int *hi_ints = reinterpret_cast<const int *>(hot + (size_t)slot * HL::NDBL + HL::INTS);
+                const bool fast = T::GENERIC || !RAYS_SG_FAST || (hi_ints[HL::I_K] <= kSgKM && (hi_ints[HL::I_BITS] & B_NORND));   // (one code path: no second ring)
+                nq = next == K_PRED ? (fast ? Q_PRED : Q_GPRED) : (fast ? Q_CORR : Q_GCORR);
+            } else if (next == K_CHECK) nq = Q_CHECK;
+            else if (next == K_START || next == K_BEGIN) nq = Q_START;
+            else nq = streaming ? Q_FIN : Q_IDLE;      // K_FIN: nothing to copy out unless the rows are staged
+            if (next == K_FIN && !streaming) s_kind[slot] = K_IDLE;
+        }
+        push(nq, slot);
     }
     dep_end(a, binning);
     unsigned long long stt = my_steps, rh = my_rhs;

@@ -90,6 +90,7 @@ struct Ctx {
     DevBuf<int> cont_list[2];
     DevBuf<double> sg_state;       // slot memory of the Shampine-Gordon slot-machine kernel
     size_t cached_sgb = 0;
+    int cached_rpc = 0, cached_dep_smem = -1;   // rays in flight per CTA of the selected kernel (for the deposition-bin size it was queried with)
     double last_first_ms = 0, last_resume_ms = 0;
     int last_phases = 0;
     cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
@@ -503,11 +504,12 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     a.dep_smem = (binned && (size_t)cx().dep_bins * 8 <= 40 * 1024) ? cx().dep_bins * 8 : 0;
     int bps = cx().cached_bps;
     const char *name = cx().cached_name;
-    if (bps <= 0 || cx().cached_ops != ops) {   // occupancy of the selected specialisation: queried once per configuration
+    if (bps <= 0 || cx().cached_ops != ops || cx().cached_dep_smem != a.dep_smem) {   // occupancy of the selected specialisation: queried once per configuration
         size_t sgb = 0;
-        CK(ops->trace(cx().sel, a, 0, cx().stream, &bps, &name, &sgb));
+        int rpc = kTraceBlock;
+        CK(ops->trace(cx().sel, a, 0, cx().stream, &bps, &name, &sgb, &rpc));
         if (bps < 1) bps = 1;
-        cx().cached_bps = bps; cx().cached_name = name; cx().cached_ops = ops; cx().cached_sgb = sgb;
+        cx().cached_bps = bps; cx().cached_name = name; cx().cached_ops = ops; cx().cached_sgb = sgb; cx().cached_rpc = rpc; cx().cached_dep_smem = a.dep_smem;
     }
     if (cx().cached_sgb) {   // Shampine-Gordon slot machine: slot memory for every CTA of the largest grid
         CK(cx().sg_state.reserve(((size_t)cx().num_sms * bps * cx().cached_sgb + 7) / 8));
@@ -515,7 +517,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     }
     long long blocks_needed = (count + kTraceBlock - 1) / kTraceBlock;   // (an SG CTA holds twice that many rays; a small fan still spreads over the SMs)
     int grid = (int)std::min<long long>((long long)cx().num_sms * bps, std::max<long long>(blocks_needed, 1));
-    const int rays_per_cta = cx().cached_sgb ? kSgSlots : kTraceBlock;   // rays in flight per CTA (SG slot machine: two slots per thread)
+    const int rays_per_cta = cx().cached_rpc;   // rays in flight per CTA (SG slot machine: its slots)
     if (host) {   // streaming copy-out: per-lane (per-slot) staging rows, finished rays go straight to the caller's arrays
         const size_t lanes = (size_t)grid * rays_per_cta;
         if (host->ray_vec) { CK(cx().ray_vec.reserve(lanes * cx().res_npa * cx().res_nv)); a.ray_vec = cx().ray_vec.p; a.host_ray_vec = host->ray_vec; }
@@ -555,7 +557,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
         CK(cudaMemsetAsync(cx().queue.p + 3, 0, sizeof(unsigned long long), cx().stream));
         const int grid_p = (int)std::min<long long>((long long)cx().num_sms * bps, std::max<long long>((n_this + kTraceBlock - 1) / kTraceBlock, 1));
         CK(cudaEventRecord(cx().ev_m0, cx().stream));
-        CK(ops->trace(cx().sel, a, grid_p, cx().stream, nullptr, nullptr, nullptr));
+        CK(ops->trace(cx().sel, a, grid_p, cx().stream, nullptr, nullptr, nullptr, nullptr));
         CK(cudaEventRecord(cx().ev_m1, cx().stream));
         cx().last_launches += 1;
         cx().last_phases = phase + 1;

@@ -21,18 +21,53 @@ cudaError_t tu_upload(const DevCfg *dc, cudaStream_t st) {
     return cudaMemcpyToSymbolAsync(g_dc, dc, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, st);
 }
 
-template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb, const char *nm) {
+#if RAYS_TU_ODE == 2
+// slots of one slot-machine CTA: what its share of the SM's shared memory holds besides the deposition bins and the rings
+template <class T> cudaError_t sg2_geometry(const TraceArgs &a, int *slots, size_t *dyn_bytes) {
+    static int static_bytes = -1;       // per specialisation: the kernel's static shared memory
+    if (static_bytes < 0) {
+        cudaFuncAttributes fa{};
+        cudaError_t e = cudaFuncGetAttributes(&fa, trace_sg2_kernel<T>);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(trace_sg2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return e;
+        static_bytes = (int)fa.sharedSizeBytes;
+    }
+    const size_t per_cta = (size_t)233472 / kSgCtas - 1024 - (size_t)static_bytes;     // 228 KB per SM, 1 KB reserved per CTA
+    const size_t fixed = ((size_t)(a.dep_smem + 15) / 16) * 16 + sg2_ring_bytes();
+    const size_t hot = sg2_hot_bytes_per_slot<T::NV>();
+    long long s = per_cta > fixed ? (long long)((per_cta - fixed) / hot) : 0;
+    if (s > kSgRingCap) s = kSgRingCap;
+    if (const char *env = getenv("RAYS_B200_SG_SLOTS")) { const int v = atoi(env); if (v > 0 && v < s) s = v; }   // measurement aid
+    if (s < 32) return cudaErrorInvalidConfiguration;
+    *slots = (int)s;
+    *dyn_bytes = fixed + (size_t)s * hot;
+    return cudaSuccess;
+}
+#endif
+
+template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs &a_in, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb, int *rpc, const char *nm) {
     if (name) *name = nm;
     if (sgb) *sgb = 0;
+    if (rpc) *rpc = kTraceBlock;
+    TraceArgs a = a_in;
 #if RAYS_TU_ODE == 2
-    if (sgb && !s.sg_lanes) *sgb = sg2_state_bytes_per_cta<T::NV>();
+    size_t dyn = a.dep_smem;
+    if (!s.sg_lanes) {
+        int slots = 0;
+        cudaError_t e = sg2_geometry<T>(a, &slots, &dyn);
+        if (e != cudaSuccess) return e;
+        a.sg_slots = slots;
+        if (sgb) *sgb = sg2_state_bytes_per_cta<T::NV>();
+        if (rpc) *rpc = slots;
+    }
 #endif
     if (bps) {
 #if RAYS_TU_ODE == 1
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
 #else
         cudaError_t e = s.sg_lanes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0)
-                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kSgBlock, 0);
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kSgBlock, dyn);
 #endif
         if (e != cudaSuccess) return e;
     }
@@ -42,18 +77,18 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
     trace_rk4_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
 #else
     if (s.sg_lanes) trace_sg_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
-    else trace_sg2_kernel<T><<<grid, kSgBlock, a.dep_smem, st>>>(a);
+    else trace_sg2_kernel<T><<<grid, kSgBlock, dyn, st>>>(a);
 #endif
     return cudaGetLastError();
 }
 
 #define RAYS_SEL(DER, DMP, GRD, NM)                                                                            \
     if (s.ray_deriv == DER && !s.generic && s.damp == (DMP == 1) && s.grads == (GRD == 1))                     \
-        return launch_trace<Traits<kEQ, 2, DER, DMP, GRD>>(s, a, grid, st, bps, name, sgb, NM);
+        return launch_trace<Traits<kEQ, 2, DER, DMP, GRD>>(s, a, grid, st, bps, name, sgb, rpc, NM);
 #define RAYS_GEN(DER, NM)                                                                                      \
-    if (s.ray_deriv == DER && s.generic) return launch_trace<Traits<kEQ, 0, DER, -1, -1>>(s, a, grid, st, bps, name, sgb, NM);
+    if (s.ray_deriv == DER && s.generic) return launch_trace<Traits<kEQ, 0, DER, -1, -1>>(s, a, grid, st, bps, name, sgb, rpc, NM);
 
-cudaError_t tu_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb) {
+cudaError_t tu_trace(const KernelSel &s, const TraceArgs &a, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb, int *rpc) {
     RAYS_SEL(RAYS_DERIV_COLD, 0, 0, "trace<ns2,cold,nv7>")
     RAYS_SEL(RAYS_DERIV_COLD, 1, 0, "trace<ns2,cold,damp,nv8>")
     RAYS_SEL(RAYS_DERIV_COLD, 0, 1, "trace<ns2,cold,grads,nv12>")

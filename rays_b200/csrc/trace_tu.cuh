@@ -29,8 +29,10 @@ struct FanLaunchArgs {    // launch-fan kernels (ray_init modules), see trace_tu
 struct TuOps {
     cudaError_t (*upload)(const DevCfg *, cudaStream_t);
     // occupancy query + launch of the trace kernel selected by sel; grid < 0 -> only report
-    // sg_state_bytes_per_cta: slot memory the Shampine-Gordon slot-machine kernel needs per CTA (0 for the other kernels)
-    cudaError_t (*trace)(const KernelSel &, const TraceArgs &, int grid, cudaStream_t, int *blocks_per_sm, const char **name, size_t *sg_state_bytes_per_cta);
+    // sg_state_bytes_per_cta: global slot records the Shampine-Gordon slot-machine kernel needs per CTA (0 for the other kernels);
+    // rays_per_cta: rays one CTA holds in flight (its threads; the slot machine: its slots, as many as shared memory holds)
+    cudaError_t (*trace)(const KernelSel &, const TraceArgs &, int grid, cudaStream_t, int *blocks_per_sm, const char **name, size_t *sg_state_bytes_per_cta,
+                         int *rays_per_cta);
     cudaError_t (*probe_equilibrium)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
     cudaError_t (*probe_rhs)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
     cudaError_t (*probe_check_save)(const KernelSel &, long long, const double *, double *, int *, cudaStream_t);
