@@ -227,6 +227,13 @@ enum SGPhase { SG_IDLE = 0, SG_CHECK, SG_DE_BEGIN, SG_AFTER_CHECK, SG_AFTER_R1, 
 RD_INLINE double sg_quot(double x, const Rcp &c) { return c.d == 0.0 ? x * __longlong_as_double(0x7ff0000000000000LL) : qdiv(x, c); }
 RD_INLINE double sg_sqrt(double x) { return x == __longlong_as_double(0x7ff0000000000000LL) ? x : sqrt_rn(x); }   // sqrt_rn is for finite radicands
 RD_INLINE double sg_div(double x, double d) { return sg_quot(x, rcp_of(d)); }
+// (p5eps/erk)**(1/(k+1)) of the step-size formula (ode_RAYS.f90:1222): the square root is the correctly rounded value of
+// x**0.5 and the fourth root two of them (within an ulp of it, like CUDA's pow), at a tenth of pow's instructions; 0 < x < 1 here
+RD_INLINE double sg_root(double x, int kp1) {
+    if (kp1 == 2) return sqrt_rn(x);
+    if (kp1 == 4) return sqrt_rn(sqrt_rn(x));
+    return pow_ool(x, kSGinv[kp1]);
+}
 // step, first block (:840-852): tests for too small a step / tolerance; returns true on crash
 template <int NV> RD_INLINE bool sg_block0(int neqn, SGWork<NV> &W, double &eps) {
     const double twou = 2.0 * DBL_EPSILON, fouru = 2.0 * twou;
@@ -458,7 +465,7 @@ template <int NV> RD_INLINE void sg_after_correct(int neqn, SGWork<NV> &W, doubl
         if (p5eps < erk * kSGtwo[k + 1]) {
             hnew = h;
             if (p5eps < erk) {
-                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
+                const double r = sg_root(sg_div(p5eps, erk), k + 1);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(W.x)), h);
             }
@@ -532,6 +539,7 @@ struct TraceArgs {
     int sg_align;                   // SG kernel: 1 = lanes advance in alternating predictor / corrector slots (see trace_sg_kernel)
     double *sg_state;               // slot-machine SG kernel (ray_trace_sg2.cuh): global slot records, grid * sg_state_bytes_per_cta bytes
     int sg_slots;                   // ... and the ray slots of one CTA (their hot records are in dynamic shared memory)
+    int sg_mixed;                   // ... 1: every warp of an iteration takes a batch of whatever kind is waiting; 0: one kind per iteration
     double *cont_state;             // [nray][kContStride]
     int *cont_list;
     unsigned long long *cont_count;

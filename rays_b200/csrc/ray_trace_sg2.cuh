@@ -368,7 +368,7 @@ template <int NV> RD_INLINE void sg2_after_correct(int neqn, const SgSlot<NV> &W
         if (p5eps < erk * kSGtwo[k + 1]) {
             hnew = h;
             if (p5eps < erk) {
-                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
+                const double r = sg_root(sg_div(p5eps, erk), k + 1);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(W.hs(HL::X))), h);
             }
@@ -629,7 +629,7 @@ template <int NV> RD_INLINE void sg3_after_correct(const SgSlot<NV> &W, double e
         if (p5eps < erk * kSGtwo[k + 1]) {
             hnew = h;
             if (p5eps < erk) {
-                const double r = pow_ool(sg_div(p5eps, erk), kSGinv[k + 1]);
+                const double r = sg_root(sg_div(p5eps, erk), k + 1);
                 hnew = absh * fmax(0.5, fmin((double)0.9f, r));
                 hnew = copysign(fmax(hnew, fouru * fabs(x)), h);
             }
@@ -739,27 +739,82 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
 #pragma unroll
         for (int q = 0; q < kSgNQ; ++q) { hd[q] = s_head[par][q]; cnt[q] = s_tail[q] - hd[q]; }
         const bool exhausted = s_exhausted != 0;
-        // ---- the choice every thread comes to: finished rays first, then a refill when it pays (or nothing else can fill the
-        // CTA), else the macro-step most slots wait for; the rare kinds get their turn when 16 have gathered, when nothing
-        // else is left, or every 256th iteration
-        int q = -1;
-        {
-            int best = Q_PRED;
-            unsigned bc = cnt[Q_PRED];
-            if (cnt[Q_CORR] > bc) { best = Q_CORR; bc = cnt[Q_CORR]; }
-            if (cnt[Q_CHECK] > bc) { best = Q_CHECK; bc = cnt[Q_CHECK]; }
-            int rare = Q_START;
-            unsigned rc = cnt[Q_START];
-            if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }
-            if (cnt[Q_GCORR] > rc) { rare = Q_GCORR; rc = cnt[Q_GCORR]; }
-            if (cnt[Q_FIN] > 0) q = Q_FIN;
-            else if (cnt[Q_IDLE] > 0 && !exhausted && (cnt[Q_IDLE] >= 32u || bc < (unsigned)NT)) q = Q_IDLE;
-            else if (rc > 0 && (rc >= 16u || bc == 0u || (iter & 255u) == 0u)) q = rare;
-            else if (bc > 0) q = best;
+        // ---- the plan every thread comes to (same counters, same arithmetic): finished rays first, then a refill when it pays
+        // (or the waiting slots cannot fill the CTA); else a COMPUTE iteration, in which every WARP gets a batch of one kind:
+        // full batches of 32 first (predictor, corrector, segment boundary, then the rare kinds), then the largest remainders
+        // for the warps still free.  At the barrier every slot sits in a ring, so with more slots than threads all warps are
+        // busy in every iteration, and a warp runs one kind: fast / general bookkeeping is not a per-thread choice.
+        int q = -1;                  // Q_FIN / Q_IDLE: an iteration of the whole CTA; -2: compute iteration
+        int wq = -1;                 // compute iteration: this warp's ring, ...
+        unsigned wbase = 0, wn = 0;  // ... its first entry (from the head) and its entries
+        unsigned tk[kSgNQ];
+#pragma unroll
+        for (int k = 0; k < kSgNQ; ++k) tk[k] = 0u;
+        const unsigned total = cnt[Q_PRED] + cnt[Q_CORR] + cnt[Q_CHECK] + cnt[Q_START] + cnt[Q_GPRED] + cnt[Q_GCORR];
+        if (cnt[Q_FIN] > 0) { q = Q_FIN; tk[Q_FIN] = cnt[Q_FIN]; }
+        else if (cnt[Q_IDLE] > 0 && !exhausted && (cnt[Q_IDLE] >= 32u || total < (unsigned)NT)) { q = Q_IDLE; tk[Q_IDLE] = cnt[Q_IDLE] < (unsigned)NT ? cnt[Q_IDLE] : (unsigned)NT; }
+        else if (total > 0) {
+            q = -2;
+            int wnext = 0;
+            // sg_mixed = 0: ONE kind per iteration (the one most slots wait for).  The kernels whose right-hand side is short
+            // (deriv_cold) spend half their instructions in the bookkeeping blocks, which differ from kind to kind: with
+            // several kinds in flight the SM's instruction cache thrashes (ncu: hit rate 87 % -> 61 %, 3.7 of 9 stall cycles
+            // per issue on instruction fetch) and an iteration lasts as long as its slowest kind.  deriv_num (14 determinants
+            // per right-hand side) is the other way round: there filling every warp wins (+33 %).
+            if (!a.sg_mixed) {
+                int best = Q_PRED;
+                unsigned bc = cnt[Q_PRED];
+                if (cnt[Q_CORR] > bc) { best = Q_CORR; bc = cnt[Q_CORR]; }
+                if (cnt[Q_CHECK] > bc) { best = Q_CHECK; bc = cnt[Q_CHECK]; }
+                int rare = Q_START;
+                unsigned rc = cnt[Q_START];
+                if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }
+                if (cnt[Q_GCORR] > rc) { rare = Q_GCORR; rc = cnt[Q_GCORR]; }
+                if (rc > 0 && (rc >= 16u || bc == 0u || (iter & 255u) == 0u)) best = rare;
+#pragma unroll
+                for (int k = 0; k < Q_FIN; ++k) if (k != best) cnt[k] = 0u;      // (this iteration sees only that ring)
+            }
+            if (a.sg_mixed && (iter & 63u) == 0u) {    // aging: a rare kind that never fills a batch gets one warp now and then
+                int rare = Q_START;
+                unsigned rc = cnt[Q_START];
+                if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }
+                if (cnt[Q_GCORR] > rc) { rare = Q_GCORR; rc = cnt[Q_GCORR]; }
+                if (rc > 0) {
+                    const unsigned n = rc < 32u ? rc : 32u;
+                    if (warp == 0) { wq = rare; wbase = 0; wn = n; }
+#pragma unroll
+                    for (int k = 0; k < kSgNQ; ++k) if (k == rare) tk[k] = n;
+                    wnext = 1;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < Q_FIN; ++k) {          // full batches
+                const int full = (int)((cnt[k] - tk[k]) >> 5);
+                const int use = full < NW - wnext ? full : NW - wnext;
+                if (warp >= wnext && warp < wnext + use) { wq = k; wbase = tk[k] + 32u * (unsigned)(warp - wnext); wn = 32u; }
+                tk[k] += 32u * (unsigned)use;
+                wnext += use;
+            }
+            for (; wnext < NW; ++wnext) {               // the largest remainders
+                int bk = -1;
+                unsigned br = 0;
+#pragma unroll
+                for (int k = 0; k < Q_FIN; ++k) { const unsigned r = cnt[k] - tk[k]; if (r > br) { br = r; bk = k; } }
+                if (bk < 0) break;
+                const unsigned n = br < 32u ? br : 32u;
+                if (warp == wnext) { wq = bk; wbase = 0; wn = n; }
+#pragma unroll
+                for (int k = 0; k < Q_FIN; ++k) if (k == bk) { if (warp == wnext) wbase = tk[k]; tk[k] += n; }
+            }
         }
-        if (q < 0) break;      // every slot idle and the queue empty
-        const unsigned take = q == Q_FIN ? cnt[Q_FIN] : (cnt[q] < (unsigned)NT ? cnt[q] : (unsigned)NT);
-        if (tid < kSgNQ) s_head[par ^ 1][tid] = hd[tid] + (tid == q ? take : 0u);
+        if (q == -1) break;      // every slot idle and the queue empty
+        if (tid < kSgNQ) {
+            unsigned t = 0;
+#pragma unroll
+            for (int k = 0; k < kSgNQ; ++k) if (tid == k) t = tk[k];
+            s_head[par ^ 1][tid] = hd[tid] + t;
+        }
+        const unsigned take = q == Q_FIN ? tk[Q_FIN] : tk[Q_IDLE];
         // ---- finished rays: streaming copy-out by the warps, slot idle
         if (q == Q_FIN) {
             for (unsigned e = warp; e < take; e += NW) {
@@ -774,9 +829,9 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
             }
             continue;
         }
-        const int slot = tid < (int)take ? (int)ring[q * kSgRingCap + ((hd[q] + tid) & (kSgRingCap - 1))] : -1;
         // ---- refill idle slots from the work queue: one global atomic per warp
         if (q == Q_IDLE) {
+            const int slot = tid < (int)take ? (int)ring[Q_IDLE * kSgRingCap + ((hd[Q_IDLE] + tid) & (kSgRingCap - 1))] : -1;
             const unsigned want = __ballot_sync(0xffffffffu, slot >= 0);
             int nq = -1;
             if (want) {
@@ -828,9 +883,15 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
             push(nq, slot);
             continue;
         }
-        // ---- one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping.  q is the same for the whole CTA:
-        // fast (register-resident) or general bookkeeping is not a per-thread choice
-        const bool gen = q == Q_GPRED || q == Q_GCORR || T::GENERIC || !RAYS_SG_FAST;
+        // ---- one macro-step of the slot: bookkeeping -> one right-hand side -> bookkeeping
+        int slot = -1;
+        if (wq >= 0 && lane < wn) {
+            unsigned hq = 0;
+#pragma unroll
+            for (int k = 0; k < Q_FIN; ++k) if (wq == k) hq = hd[k];
+            slot = (int)ring[wq * kSgRingCap + ((hq + wbase + lane) & (kSgRingCap - 1))];
+        }
+        const bool gen = wq == Q_GPRED || wq == Q_GCORR || T::GENERIC || !RAYS_SG_FAST;
         int next = -1;
         if (slot >= 0) {
             const SgSlot<NV> W{hot + (size_t)slot * HL::NDBL, D + slot, I + slot};

@@ -954,6 +954,11 @@ int rays_b200_set_config(const rays_cfg *cfg) {
     d.rc_rk = mk(d.sv_rk); d.rc_rk2 = mk(d.sv_rk2); d.rc_rmaj = mk(d.sv_rmaj); d.rc_rmaj2 = mk(d.sv_rmaj2); d.rc_psiB = mk(d.sv_psiB);
     d.rc_Aphi_LUFS = mk(c.mirror.Aphi_LUFS);
     d.rc_eq_psibound = mk(c.axisym.eq_psibound);
+    d.hyp_delta[0] = mk(c.mirror.delta_d); d.hyp_two_delta[0] = mk(2.0 * c.mirror.delta_d); d.hyp_t0[0] = mk(std::tanh(c.mirror.AphiN0_d / c.mirror.delta_d));
+    for (int s = 0; s < RAYS_NSPECIES; ++s) {
+        d.hyp_delta[1 + s] = mk(c.mirror.delta_t[s]); d.hyp_two_delta[1 + s] = mk(2.0 * c.mirror.delta_t[s]);
+        d.hyp_t0[1 + s] = mk(std::tanh(c.mirror.AphiN0_t[s] / c.mirror.delta_t[s]));
+    }
     d.rc_two_delta = mk(d.dn_two_delta); d.rc_omg_p = mk(d.dn_omg_p); d.rc_omg_m = mk(d.dn_omg_m); d.rc_omg_p2 = mk(d.dn_omg_p2);
     d.rc_omg_m2 = mk(d.dn_omg_m2); d.rc_k0_p = mk(d.dn_k0_p); d.rc_k0_m = mk(d.dn_k0_m); d.rc_omg_delta = mk(d.dn_omg_delta);
     {   // are the temperatures read by anything on this run's path?
