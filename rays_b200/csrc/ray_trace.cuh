@@ -539,7 +539,7 @@ struct TraceArgs {
     int sg_align;                   // SG kernel: 1 = lanes advance in alternating predictor / corrector slots (see trace_sg_kernel)
     double *sg_state;               // slot-machine SG kernel (ray_trace_sg2.cuh): global slot records, grid * sg_state_bytes_per_cta bytes
     int sg_slots;                   // ... and the ray slots of one CTA (their hot records are in dynamic shared memory)
-    int sg_mixed;                   // ... 1: every warp of an iteration takes a batch of whatever kind is waiting; 0: one kind per iteration
+    int sg_mixed;                   // ... 1: every warp of an iteration takes a batch of whatever kind is waiting; 0: one kind per iteration; 2: predictor + corrector
     double *cont_state;             // [nray][kContStride]
     int *cont_list;
     unsigned long long *cont_count;

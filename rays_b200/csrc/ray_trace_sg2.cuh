@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
             // several kinds in flight the SM's instruction cache thrashes (ncu: hit rate 87 % -> 61 %, 3.7 of 9 stall cycles
             // per issue on instruction fetch) and an iteration lasts as long as its slowest kind.  deriv_num (14 determinants
             // per right-hand side) is the other way round: there filling every warp wins (+33 %).
-            if (!a.sg_mixed) {
+            if (a.sg_mixed != 1) {
                 int best = Q_PRED;
                 unsigned bc = cnt[Q_PRED];
                 if (cnt[Q_CORR] > bc) { best = Q_CORR; bc = cnt[Q_CORR]; }
@@ -771,10 +771,13 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
                 if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }
                 if (cnt[Q_GCORR] > rc) { rare = Q_GCORR; rc = cnt[Q_GCORR]; }
                 if (rc > 0 && (rc >= 16u || bc == 0u || (iter & 255u) == 0u)) best = rare;
+                // sg_mixed = 2: predictor and corrector batches (which share the right-hand side, the largest block) may run
+                // together, the segment-boundary and the rare kinds run on their own
+                const bool pair = a.sg_mixed == 2 && (best == Q_PRED || best == Q_CORR);
 #pragma unroll
-                for (int k = 0; k < Q_FIN; ++k) if (k != best) cnt[k] = 0u;      // (this iteration sees only that ring)
+                for (int k = 0; k < Q_FIN; ++k) if (k != best && !(pair && (k == Q_PRED || k == Q_CORR))) cnt[k] = 0u;      // (this iteration sees only those rings)
             }
-            if (a.sg_mixed && (iter & 63u) == 0u) {    // aging: a rare kind that never fills a batch gets one warp now and then
+            if (a.sg_mixed == 1 && (iter & 63u) == 0u) {    // aging: a rare kind that never fills a batch gets one warp now and then
                 int rare = Q_START;
                 unsigned rc = cnt[Q_START];
                 if (cnt[Q_GPRED] > rc) { rare = Q_GPRED; rc = cnt[Q_GPRED]; }

@@ -59,7 +59,7 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
         if (e != cudaSuccess) return e;
         a.sg_slots = slots;
         a.sg_mixed = T::DERIV == RAYS_DERIV_NUM ? 1 : 0;
-        if (const char *env = getenv("RAYS_B200_SG_MIXED")) { if (env[0]) a.sg_mixed = atoi(env) != 0; }   // measurement aid
+        if (const char *env = getenv("RAYS_B200_SG_MIXED")) { if (env[0]) a.sg_mixed = atoi(env); }   // measurement aid: 0, 1, 2
         if (sgb) *sgb = sg2_state_bytes_per_cta<T::NV>();
         if (rpc) *rpc = slots;
     }

@@ -390,6 +390,13 @@ def test_sg_slot_machine_equals_the_per_lane_kernel_and_the_oracle(monkeypatch):
     rb.set_config(cfg)
     assert np.array_equal(g.npoints, g1.npoints) and np.array_equal(g.ray_stop_code, g1.ray_stop_code)
     assert np.array_equal(g.ray_vec, g1.ray_vec, equal_nan=True) and np.array_equal(g.residual, g1.residual, equal_nan=True)
+    # the scheduling policy of the slot machine (which kinds of macro-step share an iteration) changes the schedule, never a bit
+    for policy in ("0", "1", "2"):
+        monkeypatch.setenv("RAYS_B200_SG_MIXED", policy)
+        gp = rb.trace(cfg, r[idx], n[idx], w[idx])
+        assert np.array_equal(g.npoints, gp.npoints) and np.array_equal(g.ray_stop_code, gp.ray_stop_code), policy
+        assert np.array_equal(g.ray_vec, gp.ray_vec, equal_nan=True) and np.array_equal(g.residual, gp.residual, equal_nan=True), policy
+    monkeypatch.delenv("RAYS_B200_SG_MIXED")
     o, st, nrhs = orc.trace(cfg, r[idx], n[idx], w[idx], nthreads=0)
     assert np.array_equal(g.npoints, o.npoints), np.nonzero(g.npoints != o.npoints)[0][:10]
     assert np.array_equal(g.ray_stop_code, o.ray_stop_code)
