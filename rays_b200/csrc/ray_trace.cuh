@@ -706,7 +706,7 @@ RD_INLINE void resume_ray(const TraceArgs &a, long long iray, double *v, int nv,
 // 256-byte coalesced stores over PCIe, overlapped with the integration of the other rays.
 RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long iray, int npts, int p0, size_t row, int nv, unsigned lane) {
     unsigned m = __ballot_sync(0xffffffffu, finished);
-    if (m == 0u || a.host_ray_vec == nullptr && a.host_residual == nullptr) return;
+    if (RAYS_USUAL(m == 0u || a.host_ray_vec == nullptr && a.host_residual == nullptr)) return;
     __syncwarp();   // orders the finished lanes' trajectory stores before the other lanes' loads
     while (m) {
         const int l = __ffs(m) - 1;
@@ -1083,7 +1083,7 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
     for (;;) {
         // ---- refill from the work queue (one atomic per warp)
         const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
-        if (want) {
+        if (RAYS_RARE(want)) {
             unsigned long long base = 0;
             const int leader = __ffs(want) - 1;
             if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(want));
@@ -1202,12 +1202,12 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
                     }
                 my_rhs += 1;
             }
-            if (!stop && code == 0) {
+            if (RAYS_USUAL(!stop && code == 0)) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) if (i < nv) v[i] = v[i] + qdiv(h * acc[i], g_dc.rc_six);
                 s = sout;
                 ++slice_n;
-                if (a.slice_steps > 0 && slice_n >= a.slice_steps) {   // suspend: packed into full warps by the next launch
+                if (RAYS_RARE(a.slice_steps > 0 && slice_n >= a.slice_steps)) {   // suspend: packed into full warps by the next launch
                     RayCarry k{s, sout, resid_prev, resid_last, resid_max, dep_x, dep_Q, 0.0, 0.0, nstep, flag};
                     suspend_ray(a, iray, v, nv, k);
                     active = false;
