@@ -774,8 +774,22 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
                 // sg_mixed = 2: predictor and corrector batches (which share the right-hand side, the largest block) may run
                 // together, the segment-boundary and the rare kinds run on their own
                 const bool pair = a.sg_mixed == 2 && (best == Q_PRED || best == Q_CORR);
+                if (!pair) {      // one ring: warp w takes its entries 32 w ... (the general plan below cost 10 % of all instructions)
+                    unsigned cb = 0;
 #pragma unroll
-                for (int k = 0; k < Q_FIN; ++k) if (k != best && !(pair && (k == Q_PRED || k == Q_CORR))) cnt[k] = 0u;      // (this iteration sees only those rings)
+                    for (int k = 0; k < Q_FIN; ++k) if (k == best) cb = cnt[k];
+                    const unsigned tkn = cb < (unsigned)NT ? cb : (unsigned)NT;
+#pragma unroll
+                    for (int k = 0; k < Q_FIN; ++k) if (k == best) tk[k] = tkn;
+                    wbase = 32u * (unsigned)warp;
+                    if (wbase < tkn) { wq = best; wn = tkn - wbase < 32u ? tkn - wbase : 32u; }
+                    wnext = NW;       // (no warp left for the loops below)
+#pragma unroll
+                    for (int k = 0; k < Q_FIN; ++k) cnt[k] = tk[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < Q_FIN; ++k) if (k != Q_PRED && k != Q_CORR) cnt[k] = 0u;      // (this iteration sees only those rings)
+                }
             }
             if (a.sg_mixed == 1 && (iter & 63u) == 0u) {    // aging: a rare kind that never fills a batch gets one warp now and then
                 int rare = Q_START;
@@ -790,6 +804,7 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
                     wnext = 1;
                 }
             }
+            if (wnext < NW) {
 #pragma unroll
             for (int k = 0; k < Q_FIN; ++k) {          // full batches
                 const int full = (int)((cnt[k] - tk[k]) >> 5);
@@ -808,6 +823,7 @@ __global__ void __launch_bounds__(kSgBlock, kSgCtas) trace_sg2_kernel(const Trac
                 if (warp == wnext) { wq = bk; wbase = 0; wn = n; }
 #pragma unroll
                 for (int k = 0; k < Q_FIN; ++k) if (k == bk) { if (warp == wnext) wbase = tk[k]; tk[k] += n; }
+            }
             }
         }
         if (q == -1) break;      // every slot idle and the queue empty
