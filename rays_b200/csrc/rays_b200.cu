@@ -886,6 +886,9 @@ int rays_b200_set_config(const rays_cfg *cfg) {
         c.mirror.Br_spline = base; c.mirror.Br_spline.fspl = cx().br.p;
         c.mirror.Bz_spline = base; c.mirror.Bz_spline.fspl = cx().bz.p;
         c.mirror.Aphi_spline = base; c.mirror.Aphi_spline.fspl = cx().aphi.p;
+        d.mir_x1[0] = m.Br_spline.x_grid[0]; d.mir_xn[0] = m.Br_spline.x_grid[nx - 1];
+        d.mir_x1[1] = m.Br_spline.y_grid[0]; d.mir_xn[1] = m.Br_spline.y_grid[ny - 1];
+        for (int k = 0; k < 2; ++k) { d.mir_range[k].d = d.mir_xn[k] - d.mir_x1[k]; d.mir_range[k].r = 1.0 / d.mir_range[k].d; }
     } else {
         rays_spline2d none{};
         c.mirror.Br_spline = none; c.mirror.Bz_spline = none; c.mirror.Aphi_spline = none;
