@@ -3,6 +3,7 @@
 half of them adversarial (divisor just below a power of two with a dividend just below the divisor, where
 the first product is NOT a faithful rounding; all-ones and near-power-of-two mantissas)."""
 import os
+import numpy as np
 import subprocess
 import tempfile
 
@@ -48,3 +49,22 @@ def test_reciprocal_fma_division_is_exact():
         bad, unfaithful = map(int, subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split())
     assert bad == 0
     assert unfaithful > 1000000   # the adversarial cases really do hit the hard region
+
+
+def test_tanh_cosh_from_one_exponential():
+    """hyperbolic_prof on the device (ray_physics.cuh: tanh_cosh) forms tanh(a) = 1 - 2/(e^2a + 1) and cosh(a) = (e^a + 1/e^a)/2 from ONE
+    exponential.  The same formulas in IEEE double against extended precision: absolute error of tanh and relative error of cosh and of
+    1/cosh^2 (what the profile and its derivative use) stay at rounding level over the argument range of the profiles, limits as IEEE's."""
+    a = np.concatenate([np.linspace(-2.0, 45.0, 400001), np.linspace(-1e-3, 1e-3, 20001)])
+    e = np.exp(a)
+    ch = 0.5 * (e + 1.0 / e)
+    th = 1.0 - 2.0 / (e * e + 1.0)
+    al = a.astype(np.longdouble)
+    assert float(np.max(np.abs(th - np.tanh(al)))) < 5e-16
+    assert float(np.max(np.abs((ch - np.cosh(al)) / np.cosh(al)))) < 5e-16
+    s2, s2r = 1.0 / (ch * ch), 1.0 / (np.cosh(al) * np.cosh(al))
+    assert float(np.max(np.abs((s2 - s2r) / s2r))) < 1e-15
+    with np.errstate(over="ignore", divide="ignore"):
+        big = np.array([800.0, -800.0])
+        eb = np.exp(big)
+        assert np.array_equal(1.0 - 2.0 / (eb * eb + 1.0), [1.0, -1.0]) and np.all(np.isinf(0.5 * (eb + 1.0 / eb)))

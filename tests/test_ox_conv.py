@@ -80,7 +80,13 @@ def test_gpu_ox_analysis_equals_oracle(name, ode):
     assert gn == on
     for f in ("ray_number", "step_number", "found_max", "found_cutoff", "converted", "iteration"):
         assert np.array_equal(g[f], o[f]), f
-    assert np.array_equal(g["x_max"], o["x_max"]) and np.array_equal(g["k_max"], o["k_max"]) and np.array_equal(g["alpha_max"], o["alpha_max"])
+    assert np.array_equal(g["x_max"], o["x_max"]) and np.array_equal(g["k_max"], o["k_max"])
+    # alpha at the maximum is the density profile itself: bitwise unless the profile calls libm (the mirror's hyperbolic profile
+    # takes tanh and cosh from one exponential on the device: 3e-16 absolute, tests/test_exact_division.py has the formula's check)
+    if name.startswith("mpex"):
+        assert np.allclose(g["alpha_max"], o["alpha_max"], rtol=1e-14, atol=0)
+    else:
+        assert np.array_equal(g["alpha_max"], o["alpha_max"])
     # the mirror / Gaussian / hyperbolic profiles call libm (tanh, cosh, pow, exp): rounding-level agreement from there on
     assert np.allclose(g["x_cut"], o["x_cut"], rtol=1e-12, atol=1e-15)
     assert np.allclose(g["conv_coeff"], o["conv_coeff"], rtol=1e-9, atol=0)
