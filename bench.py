@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE configs (N = 1 extras)")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--e2e-pinned-only", action="store_true", help="measurement aid: of the end-to-end modes run the page-locked one only")
     ap.add_argument("--config5-grid", type=int, default=2896, help="n_rindex_theta = n_rindex_phi of the deposition fan (2896^2 = 8.39M)")
     ap.add_argument("--cpu-rays", type=int, default=98304, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--ode", default="", help="measurement aid: override ode_solver_name (RK4_ODE | SG_ODE)")
@@ -603,11 +604,12 @@ def main():
         free_pinned()
         h_r, h_n, h_w = rvec0, nvec0, wt
         # (2) the scalable mode: no trajectory arrays, summaries only
-        e2e_summaries, nl, _ = run_e2e(False, False, args.steps, 1)
-        launches += nl
-        e2e_summaries["note"] = "rays_b200_trace with ray_vec = residual = NULL: H2D of the fan, trace without trajectory storage, D2H of the per-ray summaries"
+        if not args.e2e_pinned_only:
+            e2e_summaries, nl, _ = run_e2e(False, False, args.steps, 1)
+            launches += nl
+            e2e_summaries["note"] = "rays_b200_trace with ray_vec = residual = NULL: H2D of the fan, trace without trajectory storage, D2H of the per-ray summaries"
         # (3) an unmodified host: pageable result arrays (batched cudaMemcpy2DAsync copy-out); one warm-up, one step; N = 1 only
-        if world == 1 and is_headline:
+        if world == 1 and is_headline and not args.e2e_pinned_only:
             try:
                 e2e_pageable, nl, _ = run_e2e(True, False, 1, 1)
                 launches += nl

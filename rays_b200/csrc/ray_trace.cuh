@@ -20,6 +20,7 @@ namespace rays_dev {
 template <int EQ_, int NS_, int DERIV_, int DAMP_, int GRADS_> struct Traits {
     static constexpr int EQ = EQ_, NS = NS_, DERIV = DERIV_;
     static constexpr bool GENERIC = DAMP_ < 0;
+    static constexpr int DAMP = DAMP_, GRADS = GRADS_;
     static constexpr int NV = GENERIC ? RAYS_NV_MAX : 7 + (DAMP_ > 0 ? 1 : 0) + (GRADS_ > 0 ? 5 : 0);
     RD_INLINE static bool damp() { return GENERIC ? g_dc.c.damping_model != RAYS_DAMP_NONE : DAMP_ == 1; }
     RD_INLINE static bool grads() { return GENERIC ? g_dc.c.integrate_eq_gradients != 0 : GRADS_ == 1; }
@@ -1049,13 +1050,29 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
 //   unrolled determinants (RAYS_DN_UK = 6): 4 -> 154.6 ms, 3 -> 147.3 ms: with more independent FP64 work per warp the
 //   kernel prefers fewer warps that do not spill (stack 232 -> 48 bytes); 2 -> 176.5 ms
 // deriv_cold on the same fan: 4 -> 42.7 ms, 3 -> 39.3, 2 -> 37.7 (3.9e9 ray-steps/s; 352 bytes of spills at 128 registers, none at 255)
+// deriv_cold + damping (config 5: damp_fund_ECH + fused binning): 42 KB of the kernel's 99 KB are hot, more than the SM's 32 KB
+// instruction cache, and with warps drifting apart every warp fetched every line from L2 for itself (hit rate 63 %, 3.0 of 6.5 stall
+// cycles per issue on instruction fetch).  Rk4Sync: ONE CTA of 256 threads per SM whose warps start every ray-step together
+// (__syncthreads_or at the loop top), so a line fetched by one warp serves all eight: 185.7 -> 144.8 ms per 8.39 M-ray fan.
+// Measured on the other families, where the hot loops fit the cache, the barrier only costs: mirror 251 -> 269 ms, headline
+// 147.4 -> 149.9 (3 x 128) / 150.8 (1 x 384), deriv_cold 37.8 -> 39.3 (2 x 128) / 42.7 (1 x 256); 256 threads without the barrier
+// gain 2 % (181.6 ms).
+#ifndef RAYS_RK4_SYNC_ALL
+#define RAYS_RK4_SYNC_ALL 0   // measurement aid: 1 = the barrier in every RK4 kernel of the translation unit
+#endif
+template <class T> struct Rk4Sync { static constexpr bool value = RAYS_RK4_SYNC_ALL || (!T::GENERIC && T::DAMP == 1 && T::DERIV == RAYS_DERIV_COLD); };
 #ifdef RAYS_RK4_MIN_CTAS
 template <class T> struct Rk4Ctas { static constexpr int value = RAYS_RK4_MIN_CTAS; };
 #else
-template <class T> struct Rk4Ctas { static constexpr int value = T::GENERIC ? 3 : (T::DERIV == RAYS_DERIV_NUM ? 3 : 2); };
+template <class T> struct Rk4Ctas { static constexpr int value = Rk4Sync<T>::value ? 1 : (T::GENERIC ? 3 : (T::DERIV == RAYS_DERIV_NUM ? 3 : 2)); };
+#endif
+#ifdef RAYS_RK4_BLOCK
+template <class T> struct Rk4Block { static constexpr int value = RAYS_RK4_BLOCK; };
+#else
+template <class T> struct Rk4Block { static constexpr int value = Rk4Sync<T>::value ? 2 * kTraceBlock : kTraceBlock; };
 #endif
 template <class T>
-__global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(Rk4Block<T>::value, Rk4Ctas<T>::value) trace_rk4_kernel(const TraceArgs a) {
     constexpr int NV = T::NV;
     constexpr int NSM = NSpec<T::NS>::MAX;
     const int nv = T::nv();
@@ -1080,7 +1097,12 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
     int p0 = 0;          // index (within the ray) of the first point staged in this lane's row (streaming + resume)
     int slice_n = 0;     // steps this ray has taken in this launch
 
+    bool warp_done = false;   // Rk4Sync: this warp has no ray left and only keeps the CTA's barrier company
     for (;;) {
+        if (Rk4Sync<T>::value) {   // the warps of the CTA start every ray-step together (instruction cache, see Rk4Sync)
+            if (!__syncthreads_or(!warp_done)) break;
+            if (warp_done) continue;
+        }
         // ---- refill from the work queue (one atomic per warp)
         const unsigned want = __ballot_sync(0xffffffffu, !active && !exhausted);
         if (RAYS_RARE(want)) {
@@ -1119,7 +1141,10 @@ __global__ void __launch_bounds__(kTraceBlock, Rk4Ctas<T>::value) trace_rk4_kern
             }
         }
         if (__ballot_sync(0xffffffffu, active) == 0u) {
-            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;
+            if (__ballot_sync(0xffffffffu, !exhausted) == 0u) {
+                if (!Rk4Sync<T>::value) break;
+                warp_done = true;
+            }
             continue;
         }
         if (active) {

@@ -49,7 +49,11 @@ template <class T> cudaError_t sg2_geometry(const TraceArgs &a, int *slots, size
 template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs &a_in, int grid, cudaStream_t st, int *bps, const char **name, size_t *sgb, int *rpc, const char *nm) {
     if (name) *name = nm;
     if (sgb) *sgb = 0;
+#if RAYS_TU_ODE == 1
+    if (rpc) *rpc = Rk4Block<T>::value;
+#else
     if (rpc) *rpc = kTraceBlock;
+#endif
     TraceArgs a = a_in;
 #if RAYS_TU_ODE == 2
     size_t dyn = a.dep_smem;
@@ -66,7 +70,7 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
 #endif
     if (bps) {
 #if RAYS_TU_ODE == 1
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, kTraceBlock, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_rk4_kernel<T>, Rk4Block<T>::value, 0);
 #else
         cudaError_t e = s.sg_lanes ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg_kernel<T>, kTraceBlock, 0)
                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, trace_sg2_kernel<T>, kSgBlock, dyn);
@@ -76,7 +80,7 @@ template <class T> cudaError_t launch_trace(const KernelSel &s, const TraceArgs 
     if (grid <= 0) return cudaSuccess;
 #if RAYS_TU_ODE == 1
     (void)s;
-    trace_rk4_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
+    trace_rk4_kernel<T><<<grid, Rk4Block<T>::value, a.dep_smem, st>>>(a);
 #else
     if (s.sg_lanes) trace_sg_kernel<T><<<grid, kTraceBlock, a.dep_smem, st>>>(a);
     else trace_sg2_kernel<T><<<grid, kSgBlock, dyn, st>>>(a);
