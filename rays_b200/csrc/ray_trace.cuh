@@ -1052,8 +1052,11 @@ __global__ void __launch_bounds__(kTraceBlock, RAYS_SG_MIN_CTAS) trace_sg_kernel
 // deriv_cold on the same fan: 4 -> 42.7 ms, 3 -> 39.3, 2 -> 37.7 (3.9e9 ray-steps/s; 352 bytes of spills at 128 registers, none at 255)
 // deriv_cold + damping (config 5: damp_fund_ECH + fused binning): 42 KB of the kernel's 99 KB are hot, more than the SM's 32 KB
 // instruction cache, and with warps drifting apart every warp fetched every line from L2 for itself (hit rate 63 %, 3.0 of 6.5 stall
-// cycles per issue on instruction fetch).  Rk4Sync: ONE CTA of 256 threads per SM whose warps start every ray-step together
-// (__syncthreads_or at the loop top), so a line fetched by one warp serves all eight: 185.7 -> 144.8 ms per 8.39 M-ray fan.
+// cycles per issue on instruction fetch).  Rk4Sync: ONE CTA per SM whose warps start every ray-step together (__syncthreads_or at
+// the loop top), so a line fetched by one warp serves all of them: 185.7 -> 144.8 ms per 8.39 M-ray fan with 256 threads (hit rate
+// 88 %); what was left was `wait` (dependency chains at 2 warps per scheduler), and without the fetch stalls a third warp per
+// scheduler pays for its spills: 384 threads x 168 registers 124.2 ms (320: 150.9, 448: 140.4 - uneven over the four schedulers -
+// 512 x 128 registers: 124.4).
 // Measured on the other families, where the hot loops fit the cache, the barrier only costs: mirror 251 -> 269 ms, headline
 // 147.4 -> 149.9 (3 x 128) / 150.8 (1 x 384), deriv_cold 37.8 -> 39.3 (2 x 128) / 42.7 (1 x 256); 256 threads without the barrier
 // gain 2 % (181.6 ms).
@@ -1069,7 +1072,7 @@ template <class T> struct Rk4Ctas { static constexpr int value = Rk4Sync<T>::val
 #ifdef RAYS_RK4_BLOCK
 template <class T> struct Rk4Block { static constexpr int value = RAYS_RK4_BLOCK; };
 #else
-template <class T> struct Rk4Block { static constexpr int value = Rk4Sync<T>::value ? 2 * kTraceBlock : kTraceBlock; };
+template <class T> struct Rk4Block { static constexpr int value = Rk4Sync<T>::value ? 3 * kTraceBlock : kTraceBlock; };
 #endif
 template <class T>
 __global__ void __launch_bounds__(Rk4Block<T>::value, Rk4Ctas<T>::value) trace_rk4_kernel(const TraceArgs a) {
