@@ -662,12 +662,17 @@ constexpr int kContStride = RAYS_NV_MAX + 11;   // v[nv], s, sout, nstep, flag, 
 // one warp copies n doubles HBM/L2 -> pinned host memory: 8 loads in flight per lane (2 KB per warp) before the
 // 256-byte coalesced stores, so that the copy is bandwidth- rather than latency-bound (a 13 KB ray takes ~7
 // round trips instead of ~50; the latency-bound version cost the warp about one ray-step per finished ray)
+#ifndef RAYS_COPY_ALIGN
+#define RAYS_COPY_ALIGN 128
+#endif
 RD_INLINE void copy_row_to_host(double *__restrict__ dst, const double *__restrict__ src, int n, unsigned lane) {
-    // 16-byte stores on a 16-byte aligned destination (512 contiguous bytes per warp instruction): the head
-    // element goes first when the row starts on an odd 8-byte boundary
-    int head = (reinterpret_cast<uintptr_t>(dst) & 15) ? 1 : 0;
+    // 16-byte stores on a destination aligned to RAYS_COPY_ALIGN bytes (512 contiguous bytes = four whole 128-byte lines per warp
+    // instruction): the head elements go first, one per lane, when the row starts elsewhere (rows of the reference layout start
+    // on 8-byte boundaries only).  Measured end to end, interleaved runs on one box: 16-byte alignment 96.2 / 95.9 ms, 128-byte
+    // 91.5 / 92.1 ms, 256-byte 94.3 / 92.8 ms (262k-ray fan); 317.4 -> 306.5 ms on the 1M-ray fan.
+    int head = (int)((RAYS_COPY_ALIGN - (reinterpret_cast<uintptr_t>(dst) & (RAYS_COPY_ALIGN - 1))) & (RAYS_COPY_ALIGN - 1)) >> 3;
     if (head > n) head = n;
-    if (head && lane == 0) dst[0] = __ldcg(src);
+    if ((int)lane < head) dst[lane] = __ldcg(src + lane);
     dst += head; src += head; n -= head;
     const int n2 = n >> 1;     // pairs
     double2 *__restrict__ d2 = reinterpret_cast<double2 *>(dst);
@@ -1099,7 +1104,6 @@ __global__ void __launch_bounds__(Rk4Block<T>::value, Rk4Ctas<T>::value) trace_r
     int fin_np = 0;
     int p0 = 0;          // index (within the ray) of the first point staged in this lane's row (streaming + resume)
     int slice_n = 0;     // steps this ray has taken in this launch
-
     bool warp_done = false;   // Rk4Sync: this warp has no ray left and only keeps the CTA's barrier company
     for (;;) {
         if (Rk4Sync<T>::value) {   // the warps of the CTA start every ray-step together (instruction cache, see Rk4Sync)
