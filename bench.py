@@ -590,8 +590,11 @@ def main():
                                                  rk4=int(cfg.ode_solver) == 1, tol=float(cfg.abs_err0) * 10))
         e2e, nl, npts_sum = run_e2e(True, True, args.steps, max(1, min(args.warmup, 2)), check=check_batch)
         launches += nl
-        e2e["note"] = ("host fan in (pinned), trajectories + summaries out in the reference layout (pinned); finished rays are copied out by the "
-                       "trace kernel while others integrate; d2h counts saved points + summaries; device_ms = H2D + kernel + summary D2H by CUDA events")
+        e2e["copy_out"] = "copy_out_kernel (concurrent copier)" if "copy_out_kernel" in rb.last_trace_stats()["kernel"] else "in-kernel (flush_finished_rays)"
+        e2e["note"] = ("host fan in (pinned), trajectories + summaries out in the reference layout (pinned); the trace kernels write the trajectories to "
+                       "HBM and append every ended ray to a list that a concurrent copier kernel (second stream, 16 CTAs) drains into the caller's arrays "
+                       "while the other rays integrate (RAYS_B200_COPIER=0, or a fan whose trajectories do not fit in HBM: the trace kernel's warps copy "
+                       "their finished rays themselves); d2h counts saved points + summaries; device_ms = H2D + kernels + summary D2H by CUDA events")
         # spot check: the end-to-end run saved exactly the points the device-resident run counted
         assert npts_sum - nray == ray_steps_per_fan, (npts_sum, nray, ray_steps_per_fan)
         if cmp_parts:

@@ -546,6 +546,10 @@ struct TraceArgs {
     unsigned long long *cont_count;
     unsigned long long *queue;      // next ray index to hand out
     unsigned long long *counters;   // [0] ray-steps, [1] RHS evaluations
+    // copy-out by a concurrent copier kernel (copy_out_kernel): a ray that has ENDED (not merely been suspended) appends its index
+    // to done_list after its trajectory, npoints and summaries are written (done_list is preset to -1; the copier polls the entries)
+    int *done_list;                 // [nray] or NULL
+    unsigned long long *done_count;
     // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_acc == NULL disables it.  Bins are 64-bit FIXED-POINT
     // accumulators (one unit = 1/dep_scale): integer addition is associative, so the profile does not depend on the order in
     // which rays, CTAs or GPUs contribute (SURVEY.md 8e "reproducibility": 1/2/4/8-GPU profiles are bitwise identical).  Each
@@ -731,6 +735,54 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
             double *dst = a.host_residual + (size_t)(a.host_ray0 + ir * a.host_ray_stride) * a.host_npoints_alloc + pf;
             copy_row_to_host(dst, src, np, lane);
         }
+    }
+}
+
+// ---- copier kernel: delivers finished rays to the caller's page-locked arrays WHILE the trace kernels run ----------------
+// The trace kernel of the page-locked end-to-end path used to copy each finished ray out itself (flush_finished_rays): its warps
+// then sit on PCIe back-pressure (14.2 GB per 1M-ray fan against 147 ms of integration), and while a resume pass integrates the
+// longest rays the link is idle.  When the whole fan's trajectories fit in HBM, the trace kernel instead writes them there at
+// full speed and appends each ended ray to done_list; this kernel - a few CTAs on a second stream, resident beside the trace
+// kernel's CTAs for the whole call - takes the entries in order and streams the rows to the host, so that the link is busy from
+// the first finished ray to the last.  It only ever waits for the trace kernels, never the other way round.
+struct CopyOutArgs {
+    long long nray;
+    const int *done_list;           // [nray], preset to -1
+    unsigned long long *claim;      // next entry to take
+    const int *abort_flag;          // set by the host if a trace launch failed
+    int *error_flag;                // set here if an entry did not arrive within the spin budget
+    const int *npoints;
+    const double *ray_vec, *residual;   // [nray][npoints_alloc][nv], [nray][npoints_alloc] (device) or NULL
+    double *host_ray_vec, *host_residual;
+    int npoints_alloc, host_npoints_alloc, nv;
+    long long host_ray0, host_ray_stride;
+    int *started;                   // page-locked host counter: one increment per CTA once it is resident (the host launches the
+                                    // trace kernel after all have reported, or the trace CTAs would fill the SMs first)
+};
+static __global__ void __launch_bounds__(256) copy_out_kernel(const CopyOutArgs c) {
+    const unsigned lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && c.started) { atomicAdd_system(c.started, 1); __threadfence_system(); }
+    for (;;) {
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(c.claim, 1ULL);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if ((long long)k >= c.nray) break;
+        int ir = -1;
+        if (lane == 0) {
+            const long long t0 = clock64();
+            while ((ir = reinterpret_cast<const volatile int *>(c.done_list)[k]) < 0) {
+                if (*reinterpret_cast<const volatile int *>(c.abort_flag)) { ir = -2; break; }
+                if (clock64() - t0 > 10000000000LL) { atomicExch(c.error_flag, 1); ir = -2; break; }   // ~5 s without a new ray: never hang the GPU
+                __nanosleep(256);
+            }
+        }
+        ir = __shfl_sync(0xffffffffu, ir, 0);
+        if (ir < 0) break;
+        __threadfence();
+        const int np = __ldcg(c.npoints + ir);
+        const size_t hrow = (size_t)(c.host_ray0 + (long long)ir * c.host_ray_stride) * c.host_npoints_alloc;
+        if (c.host_ray_vec) copy_row_to_host(c.host_ray_vec + hrow * c.nv, c.ray_vec + (size_t)ir * c.npoints_alloc * c.nv, np * c.nv, lane);
+        if (c.host_residual) copy_row_to_host(c.host_residual + hrow, c.residual + (size_t)ir * c.npoints_alloc, np, lane);
     }
 }
 
@@ -1266,6 +1318,11 @@ __global__ void __launch_bounds__(Rk4Block<T>::value, Rk4Ctas<T>::value) trace_r
                 }
                 active = false;
                 fin = true; fin_np = did_not_start ? 1 : nstep + 1 - p0;
+                if (a.done_list) {   // hand the finished ray to the copier kernel: everything written above must be visible first
+                    __threadfence();
+                    const unsigned long long pos = atomicAdd(a.done_count, 1ULL);
+                    reinterpret_cast<volatile int *>(a.done_list)[pos] = (int)iray;
+                }
             }
         }
         if (streaming) { flush_finished_rays(a, fin, iray, fin_np, p0, row, nv, lane); fin = false; }

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <cmath>
 #include <cstdio>
@@ -85,6 +86,12 @@ struct Ctx {
     DevBuf<double> ray_vec, residual, pwr, endres, maxres, endpar, startv, endv;
     DevBuf<int> npoints, stop;
     DevBuf<unsigned long long> queue;   // [0] queue, [1] ray-steps, [2] RHS evaluations
+    DevBuf<int> done_list;              // copier kernel (copy_out_kernel): rays in the order they ended
+    DevBuf<unsigned long long> copy_ctl;   // [0] done count, [1] claim counter, [2] abort flag (int), [3] error flag (int)
+    bool copier_on = false;             // the trace launches of this call feed done_list
+    int last_copier = 0;                // the last rays_b200_trace delivered its trajectories through the copier kernel
+    std::string kernel_name_buf;        // "<trace kernel> + copy_out_kernel" for rays_b200_last_trace_info
+    int *copier_started = nullptr;      // page-locked, device-visible: CTAs of the copier kernel that are resident
     // time slicing: suspended-ray records and the two resume lists
     DevBuf<double> cont_state;
     DevBuf<int> cont_list[2];
@@ -477,7 +484,9 @@ int ensure_results(long long nray, int nv, int npa, bool traj) {
 // trajectories go to traj_base (indexed from 0 for ray `first`) when non-null
 struct HostOut { double *ray_vec = nullptr, *residual = nullptr; int npa = 0; long long row0 = 0, stride = 1; };   // device-accessible pinned host arrays
 
-int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned, const HostOut *host = nullptr) {
+// prepare_only: make every reservation the launches need and return (device allocations synchronise with running kernels, so the
+// copier path makes them before its copier kernel starts)
+int launch_trace(long long first, long long count, double *traj_base, double *resid_base, bool binned, const HostOut *host = nullptr, bool prepare_only = false) {
     const rays_cfg &c = cx().dc.c;
     const TuOps *ops = tu_ops(c.equilib_model, c.ode_solver);
     if (!ops) return set_err(RAYS_ERR_INVALID_CONFIG, "no kernel for this equilibrium/ode pair");
@@ -499,6 +508,8 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     a.end_ray_vec = cx().endv.p + (size_t)first * cx().res_nv;
     a.queue = cx().queue.p;
     a.counters = cx().queue.p + 1;
+    a.done_list = cx().copier_on ? cx().done_list.p : nullptr;
+    a.done_count = cx().copier_on ? cx().copy_ctl.p : nullptr;
     a.dep_acc = binned ? cx().dep.p : nullptr;
     a.n_bins = cx().dep_bins; a.grid_min = cx().dep_min; a.grid_max = cx().dep_max; a.dep_scale = cx().dep_scale;
     a.dep_smem = (binned && (size_t)cx().dep_bins * 8 <= 40 * 1024) ? cx().dep_bins * 8 : 0;
@@ -543,6 +554,16 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     if (slice > 0) {
         CK(cx().cont_state.reserve((size_t)count * kContStride));
         CK(cx().cont_list[0].reserve((size_t)count)); CK(cx().cont_list[1].reserve((size_t)count));
+    }
+    if (prepare_only) {
+        // ... and run the selected kernel once over an empty fan: a kernel's first launch loads its code (lazy module loading), and
+        // that load can wait for every running kernel - i.e. for the copier, which waits for this one
+        TraceArgs w = a;
+        w.nray = 0; w.slice_steps = 0; w.resume = 0; w.order = nullptr; w.done_list = nullptr; w.done_count = nullptr;
+        w.cont_state = cx().cont_state.p; w.cont_list = cx().cont_list[0].p; w.cont_count = cx().queue.p + 3;
+        CK(ops->trace(cx().sel, w, 1, cx().stream, nullptr, nullptr, nullptr, nullptr));
+        CK(cudaStreamSynchronize(cx().stream));
+        return 0;
     }
     long long n_this = count;
     for (int phase = 0;; ++phase) {
@@ -845,8 +866,9 @@ int rays_b200_finalize(void) {
     cudaEventDestroy(cx().ev_m0); cudaEventDestroy(cx().ev_m1);
     if (cx().pinned) cudaFreeHost(cx().pinned);
     cx().pinned = nullptr; cx().pinned_bytes = 0;
-    cx().pack_dev.release(); cx().pack_off.release();
+    cx().pack_dev.release(); cx().pack_off.release(); cx().done_list.release(); cx().copy_ctl.release();
     if (cx().ring_host) cudaFreeHost(cx().ring_host);
+    if (cx().copier_started) { cudaFreeHost(cx().copier_started); cx().copier_started = nullptr; }
     for (int k = 0; k < Ctx::kRing; ++k) if (cx().ev_ring[k]) cudaEventDestroy(cx().ev_ring[k]);
     cudaEventDestroy(cx().ev0); cudaEventDestroy(cx().ev1);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(cx().ev_batch[i]); cudaEventDestroy(cx().ev_copy[i]); }
@@ -1154,6 +1176,18 @@ int rays_b200_results_download(rays_results *res) {
     return 0;
 }
 
+// The copier path (RAYS_B200_COPIER=0 selects the in-kernel streaming copy-out instead) needs the whole fan's trajectories in HBM
+// (nray x (nstep_max+1) x (nv+1) doubles: 67 GB for the 1M-ray bench fan) and is built into the RK4 kernels (an SG trace is
+// integration-bound: its in-kernel copy-out already hides behind the arithmetic).
+static bool copier_wanted(const rays_cfg &c, long long n, int npa, int nv) {
+    if (c.ode_solver != RAYS_ODE_RK4 || n <= 0 || n >= (1LL << 31)) return false;
+    if (const char *env = getenv("RAYS_B200_COPIER")) { if (env[0] == '0') return false; }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+    const double have = (double)free_b + (double)(cx().ray_vec.n + cx().residual.n) * 8.0;
+    return (double)n * npa * (nv + 1) * 8.0 + (double)n * 64.0 <= 0.85 * have;
+}
+
 // Is [p, p+bytes) page-locked host memory the device can address?  Arrays from rays_b200_host_alloc (or
 // registered by the caller) are used as they are; small pageable arrays (<= 1 GiB) are registered for the
 // duration of the call; larger pageable arrays take the batched fallback, which only touches the pages
@@ -1208,6 +1242,73 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         hv.ray_vec = device_view_of_host(res->ray_vec, (size_t)res->nray * res->npoints_alloc * nv * 8, temp_registered);
         hv.residual = device_view_of_host(res->residual, (size_t)res->nray * res->npoints_alloc * 8, temp_registered);
         streaming = (res->ray_vec == nullptr || hv.ray_vec) && (res->residual == nullptr || hv.residual);
+    }
+    cx().last_copier = 0;
+    if (streaming && copier_wanted(c, n, npa, nv)) {
+        // Copier path (see copy_out_kernel): trajectories of the whole fan to HBM at full speed, a concurrent kernel on the copy
+        // stream delivers every ray to the caller's arrays as soon as it has ended.
+        if ((rc = ensure_results(n, nv, npa, true))) return rc;
+        CK(cx().done_list.reserve((size_t)n));
+        CK(cx().copy_ctl.reserve(4));
+        cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
+        if (!cx().copier_started) CK(cudaHostAlloc((void **)&cx().copier_started, sizeof(int), cudaHostAllocMapped));
+        if ((rc = launch_trace(0, n, hv.ray_vec ? cx().ray_vec.p : nullptr, hv.residual ? cx().residual.p : nullptr, false, nullptr, true))) return rc;
+        CK(cudaMemsetAsync(cx().queue.p, 0, 3 * sizeof(unsigned long long), cx().stream));
+        CK(cudaMemsetAsync(cx().done_list.p, 0xFF, (size_t)n * sizeof(int), cx().stream));
+        CK(cudaMemsetAsync(cx().copy_ctl.p, 0, 4 * sizeof(unsigned long long), cx().stream));
+        CK(cudaEventRecord(cx().ev_batch[0], cx().stream));
+        CK(cudaStreamWaitEvent(cx().copy_stream, cx().ev_batch[0], 0));
+        CopyOutArgs ca{};
+        ca.nray = n; ca.done_list = cx().done_list.p; ca.claim = cx().copy_ctl.p + 1;
+        ca.abort_flag = reinterpret_cast<const int *>(cx().copy_ctl.p + 2); ca.error_flag = reinterpret_cast<int *>(cx().copy_ctl.p + 3);
+        ca.npoints = cx().npoints.p;
+        ca.ray_vec = hv.ray_vec ? cx().ray_vec.p : nullptr; ca.residual = hv.residual ? cx().residual.p : nullptr;
+        ca.host_ray_vec = hv.ray_vec; ca.host_residual = hv.residual;
+        ca.npoints_alloc = npa; ca.host_npoints_alloc = hv.npa; ca.nv = nv; ca.host_ray0 = hv.row0; ca.host_ray_stride = hv.stride;
+        int copy_ctas = 16;
+        if (const char *env = getenv("RAYS_B200_COPY_CTAS")) { if (env[0] && atoi(env) > 0) copy_ctas = atoi(env); }
+        *reinterpret_cast<volatile int *>(cx().copier_started) = 0;
+        CK(cudaHostGetDevicePointer((void **)&ca.started, cx().copier_started, 0));
+        copy_out_kernel<<<copy_ctas, 256, 0, cx().copy_stream>>>(ca);
+        CK(cudaGetLastError());
+        {   // the copier's CTAs must be resident before the trace kernel fills the SMs (they would otherwise start when it ends)
+            const auto t0 = std::chrono::steady_clock::now();
+            while (*reinterpret_cast<volatile int *>(cx().copier_started) < copy_ctas &&
+                   std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(200)) { }
+        }
+        cx().copier_on = true;
+        rc = launch_trace(0, n, hv.ray_vec ? cx().ray_vec.p : nullptr, hv.residual ? cx().residual.p : nullptr, false, nullptr);
+        cx().copier_on = false;
+        if (rc) {   // release the copier before reporting the failure
+            const int one = 1;
+            cudaMemcpyAsync(cx().copy_ctl.p + 2, &one, sizeof(int), cudaMemcpyHostToDevice, cx().stream);
+            cudaStreamSynchronize(cx().stream); cudaStreamSynchronize(cx().copy_stream);
+            return rc;
+        }
+        cx().last_launches += 1;
+        std::vector<int> codes((size_t)n);
+        CK(cudaMemcpyAsync(codes.data(), cx().stop.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        if ((rc = copy_small_results(res, 0, n, rm))) return rc;
+        CK(cudaEventRecord(cx().ev_copy[0], cx().copy_stream));
+        CK(cudaStreamWaitEvent(cx().stream, cx().ev_copy[0], 0));
+        int copy_err = 0;
+        CK(cudaMemcpyAsync(&copy_err, cx().copy_ctl.p + 3, sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaEventRecord(cx().ev1, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
+        if (copy_err) return set_err(RAYS_ERR_CUDA, "rays_b200_trace: the copier kernel gave up waiting for a finished ray");
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
+        cx().last_ms = ms;
+        if ((rc = fetch_counters())) return rc;
+        fill_flags(res, codes, 0, rm);
+        res->total_trace_time = cx().last_ms * 1e-3;
+        res->total_ray_steps = cx().last_steps;
+        if (res->ray_trace_time) for (long long i = 0; i < n; ++i) res->ray_trace_time[rm.row0 + i * rm.stride] = res->total_trace_time / (double)n;
+        cx().dep_fused = false;
+        cx().last_copier = 1;
+        cx().kernel_name_buf = std::string(cx().last_kernel ? cx().last_kernel : "") + " + copy_out_kernel";
+        cx().last_kernel = cx().kernel_name_buf.c_str();
+        return 0;
     }
     if (streaming) {
         if ((rc = ensure_results(n, nv, npa, false))) return rc;

@@ -336,13 +336,19 @@ def test_host_mirror_program_flow(tmp_path):
     f.close()
 
 
-@pytest.mark.parametrize("slice_steps,register,staged", [("5", "1", "1"), ("5", "0", "1"), ("0", "0", "1"), ("40", "1", "1"), ("5", "0", "0"), ("0", "0", "0")])
+@pytest.mark.parametrize("slice_steps,register,staged", [("5", "1", "1"), ("5", "0", "1"), ("0", "0", "1"), ("40", "1", "1"), ("5", "0", "0"), ("0", "0", "0"),
+                                                         ("0", "1", "copier"), ("5", "1", "copier")])
 def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, register, staged, monkeypatch):
     """The library's execution options change the schedule and the copy-out path, never the results:
     time slicing (rays suspended after n steps and re-launched packed) x streaming copy-out by the kernel (page-locked arrays) /
-    packed rows through the page-locked ring + host threads (pageable arrays) / plain cudaMemcpy2D into pageable arrays."""
+    the concurrent copier kernel (page-locked arrays, the default; RAYS_B200_COPIER=0 selects the in-kernel copy) / packed rows through the page-locked ring + host threads
+    (pageable arrays) / plain cudaMemcpy2D into pageable arrays."""
     monkeypatch.setenv("RAYS_B200_SLICE", slice_steps)
     monkeypatch.setenv("RAYS_B200_REGISTER_HOST", register)
+    copier = staged == "copier"
+    monkeypatch.setenv("RAYS_B200_COPIER", "1" if copier else "0")
+    if copier:
+        staged = "1"
     monkeypatch.setenv("RAYS_B200_STAGED_COPY", staged)
     monkeypatch.setenv("RAYS_B200_COPY_THREADS", "5")
     cfg = init_case("solovev_fan_1M.in", nstep_max=120)
@@ -352,6 +358,7 @@ def test_copy_out_paths_and_time_slicing_are_bitwise_identical(slice_steps, regi
     st = rb.last_trace_stats()
     if slice_steps != "0":
         assert st["n_passes"] >= 2
+    assert ("copy_out_kernel" in st["kernel"]) == copier
     _compare_traces(g, o, cfg, 1e-10, bitwise=True)
     # and Shampine-Gordon through the same options
     cfg = init_case("solovev_fan_1M.in", ode_solver_name="SG_ODE", ray_deriv_name="cold", nstep_max=60, rel_err0=1e-6, abs_err0=1e-6,
