@@ -550,6 +550,7 @@ struct TraceArgs {
     // to done_list after its trajectory, npoints and summaries are written (done_list is preset to -1; the copier polls the entries)
     int *done_list;                 // [nray] or NULL
     unsigned long long *done_count;
+    int *trace_started;             // set by the first trace kernel that runs: tells the copier that it is NOT being run alone
     // fused deposition binning (bin_to_uniform_grid_m.f90:155-266); dep_acc == NULL disables it.  Bins are 64-bit FIXED-POINT
     // accumulators (one unit = 1/dep_scale): integer addition is associative, so the profile does not depend on the order in
     // which rays, CTAs or GPUs contribute (SURVEY.md 8e "reproducibility": 1/2/4/8-GPU profiles are bitwise identical).  Each
@@ -750,7 +751,8 @@ struct CopyOutArgs {
     const int *done_list;           // [nray], preset to -1
     unsigned long long *claim;      // next entry to take
     const int *abort_flag;          // set by the host if a trace launch failed
-    int *error_flag;                // set here if an entry did not arrive within the spin budget
+    const int *trace_started;       // set by the trace kernel (TraceArgs::trace_started)
+    int *deferred_flag;             // set here when the kernel stops waiting: the host then delivers the rays after the trace (see below)
     const int *npoints;
     const double *ray_vec, *residual;   // [nray][npoints_alloc][nv], [nray][npoints_alloc] (device) or NULL
     double *host_ray_vec, *host_residual;
@@ -769,10 +771,16 @@ static __global__ void __launch_bounds__(256) copy_out_kernel(const CopyOutArgs 
         if ((long long)k >= c.nray) break;
         int ir = -1;
         if (lane == 0) {
+            // Waiting ends (and the host delivers everything after the trace kernels, with this kernel run once more) when the trace
+            // kernel has not started within ~0.1 s - kernels are being serialised: a profiler, compute-sanitizer,
+            // CUDA_LAUNCH_BLOCKING - or when no ray has ended for ~10 s: the copier must never be what hangs the GPU.
             const long long t0 = clock64();
             while ((ir = reinterpret_cast<const volatile int *>(c.done_list)[k]) < 0) {
-                if (*reinterpret_cast<const volatile int *>(c.abort_flag)) { ir = -2; break; }
-                if (clock64() - t0 > 10000000000LL) { atomicExch(c.error_flag, 1); ir = -2; break; }   // ~5 s without a new ray: never hang the GPU
+                if (*reinterpret_cast<const volatile int *>(c.abort_flag) || *reinterpret_cast<volatile int *>(c.deferred_flag)) { ir = -2; break; }
+                const long long dt = clock64() - t0;
+                if ((dt > 200000000LL && !*reinterpret_cast<const volatile int *>(c.trace_started)) || dt > 20000000000LL) {
+                    atomicExch(c.deferred_flag, 1); ir = -2; break;
+                }
                 __nanosleep(256);
             }
         }
@@ -1156,6 +1164,7 @@ __global__ void __launch_bounds__(Rk4Block<T>::value, Rk4Ctas<T>::value) trace_r
     int fin_np = 0;
     int p0 = 0;          // index (within the ray) of the first point staged in this lane's row (streaming + resume)
     int slice_n = 0;     // steps this ray has taken in this launch
+    if (a.trace_started && blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile int *>(a.trace_started) = 1;
     bool warp_done = false;   // Rk4Sync: this warp has no ray left and only keeps the CTA's barrier company
     for (;;) {
         if (Rk4Sync<T>::value) {   // the warps of the CTA start every ray-step together (instruction cache, see Rk4Sync)

@@ -87,7 +87,7 @@ struct Ctx {
     DevBuf<int> npoints, stop;
     DevBuf<unsigned long long> queue;   // [0] queue, [1] ray-steps, [2] RHS evaluations
     DevBuf<int> done_list;              // copier kernel (copy_out_kernel): rays in the order they ended
-    DevBuf<unsigned long long> copy_ctl;   // [0] done count, [1] claim counter, [2] abort flag (int), [3] error flag (int)
+    DevBuf<unsigned long long> copy_ctl;   // [0] done count, [1] claim counter, [2] abort flag (int), [3] deferred flag (int), [4] trace-started flag (int)
     bool copier_on = false;             // the trace launches of this call feed done_list
     int last_copier = 0;                // the last rays_b200_trace delivered its trajectories through the copier kernel
     std::string kernel_name_buf;        // "<trace kernel> + copy_out_kernel" for rays_b200_last_trace_info
@@ -510,6 +510,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
     a.counters = cx().queue.p + 1;
     a.done_list = cx().copier_on ? cx().done_list.p : nullptr;
     a.done_count = cx().copier_on ? cx().copy_ctl.p : nullptr;
+    a.trace_started = cx().copier_on ? reinterpret_cast<int *>(cx().copy_ctl.p + 4) : nullptr;
     a.dep_acc = binned ? cx().dep.p : nullptr;
     a.n_bins = cx().dep_bins; a.grid_min = cx().dep_min; a.grid_max = cx().dep_max; a.dep_scale = cx().dep_scale;
     a.dep_smem = (binned && (size_t)cx().dep_bins * 8 <= 40 * 1024) ? cx().dep_bins * 8 : 0;
@@ -1249,18 +1250,19 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         // stream delivers every ray to the caller's arrays as soon as it has ended.
         if ((rc = ensure_results(n, nv, npa, true))) return rc;
         CK(cx().done_list.reserve((size_t)n));
-        CK(cx().copy_ctl.reserve(4));
+        CK(cx().copy_ctl.reserve(8));
         cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
         if (!cx().copier_started) CK(cudaHostAlloc((void **)&cx().copier_started, sizeof(int), cudaHostAllocMapped));
         if ((rc = launch_trace(0, n, hv.ray_vec ? cx().ray_vec.p : nullptr, hv.residual ? cx().residual.p : nullptr, false, nullptr, true))) return rc;
         CK(cudaMemsetAsync(cx().queue.p, 0, 3 * sizeof(unsigned long long), cx().stream));
         CK(cudaMemsetAsync(cx().done_list.p, 0xFF, (size_t)n * sizeof(int), cx().stream));
-        CK(cudaMemsetAsync(cx().copy_ctl.p, 0, 4 * sizeof(unsigned long long), cx().stream));
+        CK(cudaMemsetAsync(cx().copy_ctl.p, 0, 8 * sizeof(unsigned long long), cx().stream));
         CK(cudaEventRecord(cx().ev_batch[0], cx().stream));
         CK(cudaStreamWaitEvent(cx().copy_stream, cx().ev_batch[0], 0));
         CopyOutArgs ca{};
         ca.nray = n; ca.done_list = cx().done_list.p; ca.claim = cx().copy_ctl.p + 1;
-        ca.abort_flag = reinterpret_cast<const int *>(cx().copy_ctl.p + 2); ca.error_flag = reinterpret_cast<int *>(cx().copy_ctl.p + 3);
+        ca.abort_flag = reinterpret_cast<const int *>(cx().copy_ctl.p + 2); ca.deferred_flag = reinterpret_cast<int *>(cx().copy_ctl.p + 3);
+        ca.trace_started = reinterpret_cast<const int *>(cx().copy_ctl.p + 4);
         ca.npoints = cx().npoints.p;
         ca.ray_vec = hv.ray_vec ? cx().ray_vec.p : nullptr; ca.residual = hv.residual ? cx().residual.p : nullptr;
         ca.host_ray_vec = hv.ray_vec; ca.host_residual = hv.residual;
@@ -1291,11 +1293,22 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         if ((rc = copy_small_results(res, 0, n, rm))) return rc;
         CK(cudaEventRecord(cx().ev_copy[0], cx().copy_stream));
         CK(cudaStreamWaitEvent(cx().stream, cx().ev_copy[0], 0));
-        int copy_err = 0;
-        CK(cudaMemcpyAsync(&copy_err, cx().copy_ctl.p + 3, sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        int deferred = 0;
+        CK(cudaMemcpyAsync(&deferred, cx().copy_ctl.p + 3, sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        CK(cudaStreamSynchronize(cx().stream));
+        if (deferred) {   // the copier stopped waiting (kernels serialised by a tool, or a very long quiet stretch): every ray has ended by now
+            const int one = 1;
+            CK(cudaMemsetAsync(cx().copy_ctl.p + 1, 0, 3 * sizeof(unsigned long long), cx().stream));   // claim, abort, deferred
+            CK(cudaMemcpyAsync(cx().copy_ctl.p + 4, &one, sizeof(int), cudaMemcpyHostToDevice, cx().stream));
+            ca.started = nullptr;
+            copy_out_kernel<<<4 * cx().num_sms, 256, 0, cx().stream>>>(ca);
+            CK(cudaGetLastError());
+            cx().last_launches += 1;
+            CK(cudaMemcpyAsync(&deferred, cx().copy_ctl.p + 3, sizeof(int), cudaMemcpyDeviceToHost, cx().stream));
+        }
         CK(cudaEventRecord(cx().ev1, cx().stream));
         CK(cudaStreamSynchronize(cx().stream));
-        if (copy_err) return set_err(RAYS_ERR_CUDA, "rays_b200_trace: the copier kernel gave up waiting for a finished ray");
+        if (deferred) return set_err(RAYS_ERR_CUDA, "rays_b200_trace: a ray never reached the copy-out list");
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, cx().ev0, cx().ev1));
         cx().last_ms = ms;
