@@ -564,6 +564,7 @@ int launch_trace(long long first, long long count, double *traj_base, double *re
         w.cont_state = cx().cont_state.p; w.cont_list = cx().cont_list[0].p; w.cont_count = cx().queue.p + 3;
         CK(ops->trace(cx().sel, w, 1, cx().stream, nullptr, nullptr, nullptr, nullptr));
         CK(cudaStreamSynchronize(cx().stream));
+        cx().last_launches += 1;
         return 0;
     }
     long long n_this = count;
