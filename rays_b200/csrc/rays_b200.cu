@@ -1250,6 +1250,7 @@ static int trace_host_impl(const rays_cfg *cfg, const rays_fan *fan, rays_result
         // Copier path (see copy_out_kernel): trajectories of the whole fan to HBM at full speed, a concurrent kernel on the copy
         // stream delivers every ray to the caller's arrays as soon as it has ended.
         if ((rc = ensure_results(n, nv, npa, true))) return rc;
+        cx().have_traj = hv.ray_vec != nullptr && hv.residual != nullptr;   // the device copy is complete only if both arrays were asked for
         CK(cx().done_list.reserve((size_t)n));
         CK(cx().copy_ctl.reserve(8));
         cx().last_launches = 0; cx().last_first_ms = 0; cx().last_resume_ms = 0; cx().last_phases = 0;
