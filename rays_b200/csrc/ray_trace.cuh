@@ -739,61 +739,6 @@ RD_INLINE void flush_finished_rays(const TraceArgs &a, bool finished, long long 
     }
 }
 
-// ---- copier kernel: delivers finished rays to the caller's page-locked arrays WHILE the trace kernels run ----------------
-// The trace kernel of the page-locked end-to-end path used to copy each finished ray out itself (flush_finished_rays): its warps
-// then sit on PCIe back-pressure (14.2 GB per 1M-ray fan against 147 ms of integration), and while a resume pass integrates the
-// longest rays the link is idle.  When the whole fan's trajectories fit in HBM, the trace kernel instead writes them there at
-// full speed and appends each ended ray to done_list; this kernel - a few CTAs on a second stream, resident beside the trace
-// kernel's CTAs for the whole call - takes the entries in order and streams the rows to the host, so that the link is busy from
-// the first finished ray to the last.  It only ever waits for the trace kernels, never the other way round.
-struct CopyOutArgs {
-    long long nray;
-    const int *done_list;           // [nray], preset to -1
-    unsigned long long *claim;      // next entry to take
-    const int *abort_flag;          // set by the host if a trace launch failed
-    const int *trace_started;       // set by the trace kernel (TraceArgs::trace_started)
-    int *deferred_flag;             // set here when the kernel stops waiting: the host then delivers the rays after the trace (see below)
-    const int *npoints;
-    const double *ray_vec, *residual;   // [nray][npoints_alloc][nv], [nray][npoints_alloc] (device) or NULL
-    double *host_ray_vec, *host_residual;
-    int npoints_alloc, host_npoints_alloc, nv;
-    long long host_ray0, host_ray_stride;
-    int *started;                   // page-locked host counter: one increment per CTA once it is resident (the host launches the
-                                    // trace kernel after all have reported, or the trace CTAs would fill the SMs first)
-};
-static __global__ void __launch_bounds__(256) copy_out_kernel(const CopyOutArgs c) {
-    const unsigned lane = threadIdx.x & 31;
-    if (threadIdx.x == 0 && c.started) { atomicAdd_system(c.started, 1); __threadfence_system(); }
-    for (;;) {
-        unsigned long long k = 0;
-        if (lane == 0) k = atomicAdd(c.claim, 1ULL);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if ((long long)k >= c.nray) break;
-        int ir = -1;
-        if (lane == 0) {
-            // Waiting ends (and the host delivers everything after the trace kernels, with this kernel run once more) when the trace
-            // kernel has not started within ~0.1 s - kernels are being serialised: a profiler, compute-sanitizer,
-            // CUDA_LAUNCH_BLOCKING - or when no ray has ended for ~10 s: the copier must never be what hangs the GPU.
-            const long long t0 = clock64();
-            while ((ir = reinterpret_cast<const volatile int *>(c.done_list)[k]) < 0) {
-                if (*reinterpret_cast<const volatile int *>(c.abort_flag) || *reinterpret_cast<volatile int *>(c.deferred_flag)) { ir = -2; break; }
-                const long long dt = clock64() - t0;
-                if ((dt > 200000000LL && !*reinterpret_cast<const volatile int *>(c.trace_started)) || dt > 20000000000LL) {
-                    atomicExch(c.deferred_flag, 1); ir = -2; break;
-                }
-                __nanosleep(256);
-            }
-        }
-        ir = __shfl_sync(0xffffffffu, ir, 0);
-        if (ir < 0) break;
-        __threadfence();
-        const int np = __ldcg(c.npoints + ir);
-        const size_t hrow = (size_t)(c.host_ray0 + (long long)ir * c.host_ray_stride) * c.host_npoints_alloc;
-        if (c.host_ray_vec) copy_row_to_host(c.host_ray_vec + hrow * c.nv, c.ray_vec + (size_t)ir * c.npoints_alloc * c.nv, np * c.nv, lane);
-        if (c.host_residual) copy_row_to_host(c.host_residual + hrow, c.residual + (size_t)ir * c.npoints_alloc, np, lane);
-    }
-}
-
 // ---- Shampine-Gordon trace kernel ---------------------------------------------------------------------------
 // SG_ode (SG_ode_m.f90:89-159) -> ode/de (ode_RAYS.f90:1-593) -> step/intrp as a per-lane state machine.
 // One loop iteration evaluates at most one right-hand side per lane, at a single convergence point of the
