@@ -212,3 +212,56 @@ def test_deposition_profiles_netcdf_contract(tmp_path):
     assert b"".join(f.variables["grid_name"].data[0]).decode() == "psi".ljust(20)
     assert f.RAYS_run_label.decode().strip() == "axisym_deposition_fan" and len(f.date_vector) == 8
     f.close()
+
+
+def test_spline_setup_against_an_independent_implementation():
+    """The host mirror's spline setup (splines_setup.cpp: v_spline / cspline / bcspline, not-a-knot) feeds the GPU path AND the
+    oracle, so GPU-vs-oracle parity cannot see an error in it.  A not-a-knot interpolating cubic (tensor-product bicubic) spline
+    is unique: scipy's CubicSpline / RectBivariateSpline (FITPACK B-splines, a different algorithm) must give the same function
+    and derivatives to rounding level - on a uniform grid and on the MPEX field file's own grid and data."""
+    from scipy.interpolate import CubicSpline, RectBivariateSpline
+    from scipy.io import netcdf_file
+    import _oracle as orc
+    L = _abi.load()
+    rng = np.random.default_rng(11)
+    # 1-D: smooth + rough data
+    nx = 57
+    x = np.linspace(-0.3, 1.7, nx)
+    for y in (np.exp(-x) * np.sin(7.0 * x), rng.normal(size=nx)):
+        f = np.zeros((nx, 4))
+        f[:, 0] = y
+        assert L.rays_host_cspline(x.ctypes.data_as(_abi.c_double_p), nx, f.ctypes.data_as(_abi.c_double_p)) == 0
+        s = _abi.Spline1D()
+        s.nx, s.x_grid, s.fspl = nx, x.ctypes.data_as(_abi.c_double_p), f.ctypes.data_as(_abi.c_double_p)
+        xs = np.sort(rng.uniform(x[0], x[-1], 2000))
+        fo, fpo = np.zeros_like(xs), np.zeros_like(xs)
+        orc.load().oracle_cspeval(C.byref(s), len(xs), xs.ctypes.data_as(_abi.c_double_p), fo.ctypes.data_as(_abi.c_double_p),
+                                  fpo.ctypes.data_as(_abi.c_double_p))
+        ref = CubicSpline(x, y, bc_type="not-a-knot")
+        scale = np.max(np.abs(y))
+        assert np.max(np.abs(fo - ref(xs))) <= 1e-12 * scale
+        assert np.max(np.abs(fpo - ref(xs, 1))) <= 1e-10 * scale / (x[1] - x[0])
+    # 2-D: the shipped MPEX field (51 x 201 grid, Br / Bz / Aphi) and its first derivatives
+    nc = netcdf_file(rb.config_path("mpex/Brz_fields.MPEX_9_filaments_D3-6_ECH_2nd_harm.nc"), "r", mmap=False)
+    rg, zg = np.array(nc.variables["r_grid"].data, dtype=np.float64), np.array(nc.variables["z_grid"].data, dtype=np.float64)
+    for name in ("Br", "Bz", "Aphi"):
+        A = np.array(nc.variables[name].data, dtype=np.float64)          # file order (z, r): Fortran A(r, z)
+        assert A.shape == (len(zg), len(rg))
+        F = np.zeros((len(zg), len(rg), 4, 4))
+        F[:, :, 0, 0] = A
+        assert L.rays_host_bcspline(rg.ctypes.data_as(_abi.c_double_p), len(rg), zg.ctypes.data_as(_abi.c_double_p), len(zg),
+                                    F.ctypes.data_as(_abi.c_double_p)) == 0
+        s2 = _abi.Spline2D()
+        s2.nx, s2.ny = len(rg), len(zg)
+        s2.x_grid, s2.y_grid, s2.fspl = rg.ctypes.data_as(_abi.c_double_p), zg.ctypes.data_as(_abi.c_double_p), F.ctypes.data_as(_abi.c_double_p)
+        n = 3000
+        pr, pz = rng.uniform(rg[0], rg[-1], n), rng.uniform(zg[0], zg[-1], n)
+        f, fx, fy = np.zeros(n), np.zeros(n), np.zeros(n)
+        orc.load().oracle_bcspeval(C.byref(s2), n, pr.ctypes.data_as(_abi.c_double_p), pz.ctypes.data_as(_abi.c_double_p),
+                                   f.ctypes.data_as(_abi.c_double_p), fx.ctypes.data_as(_abi.c_double_p), fy.ctypes.data_as(_abi.c_double_p))
+        ref = RectBivariateSpline(rg, zg, A.T, kx=3, ky=3, s=0)
+        scale = np.max(np.abs(A))
+        assert np.max(np.abs(f - ref.ev(pr, pz))) <= 1e-11 * scale
+        assert np.max(np.abs(fx - ref.ev(pr, pz, dx=1))) <= 1e-9 * scale / (rg[1] - rg[0])
+        assert np.max(np.abs(fy - ref.ev(pr, pz, dy=1))) <= 1e-9 * scale / (zg[1] - zg[0])
+    nc.close()
