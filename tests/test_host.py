@@ -265,3 +265,23 @@ def test_spline_setup_against_an_independent_implementation():
         assert np.max(np.abs(fx - ref.ev(pr, pz, dx=1))) <= 1e-9 * scale / (rg[1] - rg[0])
         assert np.max(np.abs(fy - ref.ev(pr, pz, dy=1))) <= 1e-9 * scale / (zg[1] - zg[0])
     nc.close()
+
+
+def test_host_constants_carry_the_reference_single_precision_literals():
+    """constants_m.f90:38-48, rf_m.f90:87-91, species_m.f90:33-34,150-158: the reference writes pi, clight, mu0's 4.e-7, me and e as
+    default-REAL literals, so the doubles it computes with are float32-rounded (pi is off by 2.8e-8).  The host
+    mirror feeds the same configuration to the GPU path and to the oracle, so this is checked against the arithmetic restated
+    here with numpy float32 round trips, and against the values SURVEY.md A.1 lists - exactly."""
+    f32 = lambda v: float(np.float32(v))
+    pi, clight, me, e = f32(3.1415926535897932385), f32(2.997930e8), f32(9.1094e-31), f32(1.6022e-19)
+    mu0 = pi * f32(4.e-7)
+    eps0 = 1.0 / (mu0 * (clight * clight))
+    assert (pi, clight, mu0, eps0) == (3.1415927410125732, 299792992.0, 1.2566371110902128e-06, 8.8541559251146982e-12)
+    assert (me, e) == (9.1094003725447319e-31, 1.6021999911602857e-19)
+    cfg = init_case("slab_ECH_90GHz_case_1.in")
+    assert cfg.clight == clight and cfg.eps0 == eps0
+    omgrf = 2.0 * pi * 90.e9
+    assert cfg.omgrf == omgrf and cfg.k0 == omgrf / clight
+    assert cfg.nspec == 1
+    assert list(cfg.qs)[:2] == [e * -1.0, e * 1.0] and list(cfg.ms)[:2] == [me * 1.0, me * 3670.0]
+    assert list(cfg.t0s)[:2] == [e * 5.0e3, e * 1.0e2]
